@@ -1,0 +1,513 @@
+// bank.cu -- receiver bank (N x CDemodulator) and its C ABI.
+// Sequencing mirrors CDemodulator::SetDemod / ProcessData, dsp/demodulator.cpp:107-215.
+#include "bank.cuh"
+
+#include <algorithm>
+
+namespace csdr {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+Group::~Group()
+{
+    cudaFree(d_y);
+    cudaFree(d_tap3);
+    cudaFree(d_demod);
+    cudaFree(d_chan_map);
+    cudaFree(d_local_map);
+}
+
+static int block_limit(double in_rate, double out_rate)
+{
+    // m_InBufLimit, dsp/demodulator.cpp:145-146 (same expression, same evaluation order)
+    int limit = (out_rate / 100.0) * in_rate / out_rate;
+    limit &= 0xFFFFFF00;
+    return limit;
+}
+
+}  // namespace csdr
+
+using namespace csdr;
+
+cutesdr_bank::~cutesdr_bank()
+{
+    if (st) cudaStreamSynchronize(st);
+    groups.clear();
+    nb.reset();
+    cudaFree(d_x);
+    cudaFree(d_audio);
+    if (h_stage) cudaFreeHost(h_stage);
+    if (st) cudaStreamDestroy(st);
+}
+
+// push the per-channel parameters of user channel c into its group's stage objects
+static int apply_channel(cutesdr_bank* b, int c, bool new_demod)
+{
+    ChanCfg& cc = b->ch[c];
+    Group& g = *b->groups[cc.group];
+    const int i = cc.local;
+    g.dec.set_frequency(i, cc.dc_nco_freq);
+    CSDR_TRY(g.fir.setup(i, cc.info.LowCut, cc.info.HiCut, cc.demod_cw, g.dec.out_rate()));
+    if (new_demod) g.post.set_mode(i, cc.mode);
+    g.post.set_agc(i, cc.info.AgcOn, cc.info.AgcHangOn, cc.info.AgcThresh, cc.info.AgcManualGain, cc.info.AgcSlope,
+                   cc.info.AgcDecay);
+    if (cc.mode == CUTESDR_DEMOD_FM) g.post.set_fm(i, cc.info.SquelchValue, (double)cc.info.HiCut);
+    if (cc.mode == CUTESDR_DEMOD_AM) g.post.set_am_bandwidth(i, (cc.info.HiCut - cc.info.LowCut) / 2.0);
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank::rebuild()
+{
+    CSDR_CK(cudaSetDevice(device));
+    CSDR_CK(cudaStreamSynchronize(st));
+    groups.clear();
+    std::map<double, std::vector<int>> by_bw;
+    for (int c = 0; c < nch; c++) {
+        if (!ch[c].configured) { set_error("channel %d has no demodulator (call set_demod first)", c); return CUTESDR_E_STATE; }
+        by_bw[ch[c].max_bw].push_back(c);
+    }
+    int newL = -1;
+    for (auto& kv : by_bw) {
+        std::vector<int> lens;
+        double orate = plan_stages(in_rate, kv.first, lens);
+        int lim = block_limit(in_rate, orate);
+        if (newL < 0) newL = lim;
+        else if (lim != newL) { set_error("channel groups disagree on the DSP block length (%d vs %d)", lim, newL); return CUTESDR_E_ARG; }
+    }
+    if (newL <= 0) { set_error("input rate %g too low: DSP block length is %d", in_rate, newL); return CUTESDR_E_ARG; }
+    if (newL != L) {
+        L = newL;
+        cudaFree(d_x);
+        d_x = nullptr;
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        CSDR_CK(cudaMalloc(&d_x, (size_t)(kHaloMax + L) * sizeof(float2)));
+        CSDR_CK(cudaHostAlloc(&h_stage, (size_t)L * sizeof(float2), cudaHostAllocDefault));
+        h_fill = 0;
+    }
+    // a rebuild re-creates every DSP object: the stream restarts from zero state
+    CSDR_CK(cudaMemsetAsync(d_x, 0, (size_t)(kHaloMax + L) * sizeof(float2), st));
+    stream_pos = 0;
+    for (auto& kv : by_bw) {
+        std::unique_ptr<Group> g(new Group());
+        g->max_bw = kv.first;
+        g->chans = kv.second;
+        std::stable_sort(g->chans.begin(), g->chans.end(), [&](int a, int c2) { return ch[a].mode < ch[c2].mode; });
+        const int n = (int)g->chans.size();
+        CSDR_TRY(g->dec.init(n, in_rate, g->max_bw, L, st, &lc));
+        const int stride = g->dec.stride();
+        CSDR_TRY(g->fir.init(n, stride, st, &lc));
+        CSDR_TRY(g->post.init(n, stride, g->dec.out_rate(), kMaxBurstSamples, st, &lc));
+        CSDR_CK(cudaMalloc(&g->d_y, (size_t)kMaxBurstSamples * stride * sizeof(float2)));
+        CSDR_CK(cudaMalloc(&g->d_chan_map, stride * sizeof(int)));
+        CSDR_CK(cudaMalloc(&g->d_local_map, stride * sizeof(int)));
+        std::vector<int> map(stride, 0), ident(stride, 0);
+        for (int i = 0; i < n; i++) { map[i] = g->chans[i]; ident[i] = i; }
+        CSDR_CK(cudaMemcpy(g->d_chan_map, map.data(), stride * sizeof(int), cudaMemcpyHostToDevice));
+        CSDR_CK(cudaMemcpy(g->d_local_map, ident.data(), stride * sizeof(int), cudaMemcpyHostToDevice));
+        if (audio_rate > 0.0) {
+            g->rs.reset(new ResamplerBank());
+            CSDR_TRY(g->rs->init(n, kMaxBurstSamples, st, &lc));
+        }
+        const int gi = (int)groups.size();
+        for (int i = 0; i < n; i++) { ch[g->chans[i]].group = gi; ch[g->chans[i]].local = i; }
+        groups.push_back(std::move(g));
+    }
+    for (int c = 0; c < nch; c++) CSDR_TRY(apply_channel(this, c, true));
+    if (nb_on || nb) {
+        nb.reset(new Blanker());
+        CSDR_TRY(nb->init(L, st, &lc));
+        CSDR_TRY(nb->setup(nb_on, nb_thresh, nb_width, in_rate));
+    }
+    blk_nout.assign(nch, 0);
+    layout_dirty = false;
+    return CUTESDR_OK;
+}
+
+// One DSP block. d_block points at the block's first sample (kHaloMax history in front).
+// audio_off[group] = samples already written for that group's channels in d_audio_out.
+int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max)
+{
+    CSDR_TRY(apply_nco_startup_gain(d_block, stream_pos, L, st, &lc));
+    int nmax = 0;
+    std::fill(blk_nout.begin(), blk_nout.end(), 0);
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        Group& g = *groups[gi];
+        CSDR_TRY(g.dec.run_block(d_block));
+        const long long total = g.dec.total_out();
+        const int nbursts = (int)(total / kBurst - g.bursts_done);
+        g.last_fir_n = 0;
+        if (nbursts <= 0) continue;
+        const int n = nbursts * kBurst;
+        if (n > kMaxBurstSamples) { set_error("more than %d FIR bursts in one DSP block", kMaxBurstSamples / kBurst); return CUTESDR_E_STATE; }
+        CSDR_TRY(g.fir.run(g.dec.ring(), g.bursts_done, nbursts, g.d_y));
+        g.bursts_done += nbursts;
+        g.last_fir_n = n;
+        if (g.any_tap && !g.d_tap3) CSDR_CK(cudaMalloc(&g.d_tap3, (size_t)kMaxBurstSamples * g.dec.stride() * sizeof(float2)));
+        const int off = audio_off ? audio_off[gi] : 0;
+        int produced = n;
+        if (g.rs) {
+            // demod audio goes into the resampler's input rows, the resampler writes the user rows
+            CSDR_TRY(g.post.run(g.d_y, n, g.rs->in_ptr(), g.rs->in_stride(), 0, g.d_local_map, g.any_tap ? g.d_tap3 : nullptr));
+            const double rate = g.dec.out_rate() / audio_rate;     // interface/soundout.cpp:204
+            if (d_audio_out && off + g.rs->max_out(n, rate) > audio_stride) {
+                set_error("audio_stride %d too small for %d resampled samples at offset %d", audio_stride, g.rs->max_out(n, rate), off);
+                return CUTESDR_E_ARG;
+            }
+            CSDR_TRY(g.rs->run(n, rate, d_audio_out, audio_stride, off, g.d_chan_map, &produced));
+        } else {
+            if (d_audio_out && off + n > audio_stride) {
+                set_error("audio_stride %d too small for %d samples at offset %d", audio_stride, n, off);
+                return CUTESDR_E_ARG;
+            }
+            CSDR_TRY(g.post.run(g.d_y, n, d_audio_out, audio_stride, off, g.d_chan_map, g.any_tap ? g.d_tap3 : nullptr));
+        }
+        for (int c : g.chans) blk_nout[c] = produced;
+        nmax = std::max(nmax, produced);
+    }
+    // keep the tail of this block in front of the next one (CIC halo of kernel 1)
+    CSDR_CK(cudaMemcpyAsync(d_block - kHaloMax, d_block + (L - kHaloMax), kHaloMax * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    stream_pos += L;
+    if (n_out_max) *n_out_max = nmax;
+    return CUTESDR_OK;
+}
+
+// slow path: copy the enabled test-bench taps of the block just processed to the host
+int cutesdr_bank::collect_taps()
+{
+    bool any = false;
+    for (auto& g : groups) any |= g->any_tap;
+    if (!any) return CUTESDR_OK;
+    CSDR_CK(cudaStreamSynchronize(st));
+    for (auto& gp : groups) {
+        Group& g = *gp;
+        if (!g.any_tap) continue;
+        const int stride = g.dec.stride();
+        const int n_dec = g.dec.out_per_block();
+        for (int i = 0; i < (int)g.chans.size(); i++) {
+            ChanCfg& cc = ch[g.chans[i]];
+            if (!cc.tap_mask) continue;
+            if (cc.tap_mask & 2u) {   // PROFILE_1: decimated samples of this block
+                std::vector<float2> tmp(n_dec);
+                long long first = g.dec.total_out() - n_dec;
+                for (int k = 0; k < n_dec;) {
+                    int pos = (int)((first + k) & (kDecRing - 1));
+                    int run = std::min(n_dec - k, kDecRing - pos);
+                    CSDR_CK(cudaMemcpy(tmp.data() + k, g.dec.ring() + (size_t)i * kDecRing + pos, run * sizeof(float2), cudaMemcpyDeviceToHost));
+                    k += run;
+                }
+                const float* f = reinterpret_cast<const float*>(tmp.data());
+                cc.tap[1].insert(cc.tap[1].end(), f, f + 2 * n_dec);
+            }
+            const int n = g.last_fir_n;
+            if (n > 0 && (cc.tap_mask & 4u)) {   // PROFILE_2: FIR output column
+                std::vector<float2> tmp(n);
+                CSDR_CK(cudaMemcpy2D(tmp.data(), sizeof(float2), g.d_y + i, (size_t)stride * sizeof(float2), sizeof(float2), n, cudaMemcpyDeviceToHost));
+                const float* f = reinterpret_cast<const float*>(tmp.data());
+                cc.tap[2].insert(cc.tap[2].end(), f, f + 2 * n);
+            }
+            if (n > 0 && (cc.tap_mask & 8u) && g.d_tap3) {   // PROFILE_3: post-AGC column
+                std::vector<float2> tmp(n);
+                CSDR_CK(cudaMemcpy2D(tmp.data(), sizeof(float2), g.d_tap3 + i, (size_t)stride * sizeof(float2), sizeof(float2), n, cudaMemcpyDeviceToHost));
+                const float* f = reinterpret_cast<const float*>(tmp.data());
+                cc.tap[3].insert(cc.tap[3].end(), f, f + 2 * n);
+            }
+        }
+    }
+    return CUTESDR_OK;
+}
+
+extern "C" {
+
+const char* cutesdr_last_error(void) { return g_err.c_str(); }
+const char* cutesdr_version(void) { return "cutesdr_b200 0.1 (sm_100a)"; }
+
+int cutesdr_device_count(int* n)
+{
+    int k = 0;
+    cudaError_t e = cudaGetDeviceCount(&k);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); if (n) *n = 0; return CUTESDR_E_CUDA; }
+    if (n) *n = k;
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_create(cutesdr_bank** out, int n_channels, double in_rate, int device)
+{
+    if (!out || n_channels <= 0 || !(in_rate > 0)) { set_error("bank_create: bad arguments"); return CUTESDR_E_ARG; }
+    *out = nullptr;
+    CSDR_CK(cudaSetDevice(device));
+    std::unique_ptr<cutesdr_bank> b(new cutesdr_bank());
+    b->nch = n_channels;
+    b->in_rate = in_rate;
+    b->device = device;
+    b->ch.resize(n_channels);
+    CSDR_CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+    *out = b.release();
+    return CUTESDR_OK;
+}
+
+void cutesdr_bank_destroy(cutesdr_bank* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    delete b;
+}
+
+int cutesdr_bank_set_demod(cutesdr_bank* b, int c, int mode, const cutesdr_demod_info* info)
+{
+    if (!b || !info || c < 0 || c >= b->nch || mode < 0 || mode > CUTESDR_DEMOD_CWL) { set_error("set_demod: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    ChanCfg& cc = b->ch[c];
+    cc.info = *info;                                   // dsp/demodulator.cpp:110
+    bool new_demod = false;
+    if (cc.mode != mode) {                             // :111-142
+        cc.mode = mode;
+        new_demod = true;
+        if (mode == CUTESDR_DEMOD_LSB || mode == CUTESDR_DEMOD_CWL) cc.max_bw = -cc.info.LowCutmin;
+        else cc.max_bw = cc.info.HiCutmax;
+        if (cc.dc_max_bw != cc.max_bw) {
+            // CDownConvert::SetDataRate rebuilds the chain and ends with SetFrequency(m_NcoFreq),
+            // which adds the current CW offset once more (dsp/downconvert.cpp:98-107,168)
+            cc.dc_max_bw = cc.max_bw;
+            cc.dc_nco_freq = cc.dc_nco_freq + cc.dc_cw;
+            b->layout_dirty = true;
+        }
+    }
+    cc.demod_cw = cc.info.Offset;                      // :143-144
+    cc.dc_cw = cc.demod_cw;
+    const bool first = !cc.configured;
+    cc.configured = true;
+    if (first) b->layout_dirty = true;
+    if (!b->layout_dirty) CSDR_TRY(apply_channel(b, c, new_demod));
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_set_demod_freq(cutesdr_bank* b, int c, double freq)
+{
+    if (!b || c < 0 || c >= b->nch) { set_error("set_demod_freq: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    ChanCfg& cc = b->ch[c];
+    cc.dc_cw = cc.demod_cw;                            // dsp/demodulator.h:68
+    cc.dc_nco_freq = freq + cc.dc_cw;                  // dsp/downconvert.cpp:100-102
+    if (!b->layout_dirty && cc.group >= 0) b->groups[cc.group]->dec.set_frequency(cc.local, cc.dc_nco_freq);
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_get_output_rate(cutesdr_bank* b, int c, double* rate)
+{
+    if (!b || !rate || c < 0 || c >= b->nch) { set_error("get_output_rate: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    std::vector<int> lens;
+    *rate = plan_stages(b->in_rate, b->ch[c].dc_max_bw, lens);
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_block_length(cutesdr_bank* b, int* n)
+{
+    if (!b || !n) { set_error("block_length: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    *n = b->L;
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_get_smeter(cutesdr_bank* b, int c, double* peak, double* ave)
+{
+    if (!b || c < 0 || c >= b->nch) { set_error("get_smeter: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    ChanCfg& cc = b->ch[c];
+    return b->groups[cc.group]->post.read_smeter(cc.local, peak, ave);
+}
+
+int cutesdr_bank_set_noiseproc(cutesdr_bank* b, int on, double threshold, double width_us)
+{
+    if (!b) { set_error("set_noiseproc: bad handle"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    b->nb_on = on != 0;
+    b->nb_thresh = threshold;
+    b->nb_width = width_us;
+    if (!b->layout_dirty) {
+        if (!b->nb) { b->nb.reset(new Blanker()); CSDR_TRY(b->nb->init(b->L, b->st, &b->lc)); }
+        CSDR_TRY(b->nb->setup(b->nb_on, threshold, width_us, b->in_rate));
+    }
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_set_audio_rate(cutesdr_bank* b, double audio_rate)
+{
+    if (!b) { set_error("set_audio_rate: bad handle"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    if (audio_rate != b->audio_rate) { b->audio_rate = audio_rate > 0 ? audio_rate : 0.0; b->layout_dirty = true; }
+    return CUTESDR_OK;
+}
+
+static int ensure_audio(cutesdr_bank* b, int stride)
+{
+    if (stride <= b->audio_cap) return CUTESDR_OK;
+    cudaFree(b->d_audio);
+    b->d_audio = nullptr;
+    b->audio_cap = 0;
+    CSDR_CK(cudaMalloc(&b->d_audio, (size_t)b->nch * stride * sizeof(float)));
+    b->audio_cap = stride;
+    return CUTESDR_OK;
+}
+
+// wideband pre-processing shared by all channels: the noise blanker writes the block buffer
+static int stage_block(cutesdr_bank* b, const float2* src, cudaMemcpyKind kind)
+{
+    float2* dst = b->d_x + kHaloMax;
+    if (b->nb && b->nb->on()) {
+        float2* raw = nullptr;
+        CSDR_CK(cudaMallocAsync(&raw, (size_t)b->L * sizeof(float2), b->st));
+        CSDR_CK(cudaMemcpyAsync(raw, src, (size_t)b->L * sizeof(float2), kind, b->st));
+        int rc = b->nb->run(raw, dst, b->L);
+        CSDR_CK(cudaFreeAsync(raw, b->st));
+        return rc;
+    }
+    CSDR_CK(cudaMemcpyAsync(dst, src, (size_t)b->L * sizeof(float2), kind, b->st));
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out)
+{
+    if (!b || n_in < 0 || (n_in > 0 && !iq) || (audio && audio_stride <= 0)) { set_error("bank_process: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    if (audio) CSDR_TRY(ensure_audio(b, audio_stride));
+    std::vector<int> goff(b->groups.size(), 0);
+    std::vector<int> nout(b->nch, 0);
+    const float2* src = reinterpret_cast<const float2*>(iq);
+    int pos = 0, nmax = 0;
+    while (pos < n_in) {
+        const float2* blk = nullptr;
+        if (b->h_fill == 0 && n_in - pos >= b->L) {      // whole block available: no staging copy
+            blk = src + pos;
+            pos += b->L;
+        } else {
+            int take = std::min(n_in - pos, b->L - b->h_fill);
+            memcpy(b->h_stage + b->h_fill, src + pos, (size_t)take * sizeof(float2));
+            b->h_fill += take;
+            pos += take;
+            if (b->h_fill < b->L) break;
+            blk = b->h_stage;
+            b->h_fill = 0;
+        }
+        CSDR_TRY(stage_block(b, blk, cudaMemcpyHostToDevice));
+        int m = 0;
+        CSDR_TRY(b->run_block(b->d_x + kHaloMax, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
+        for (size_t gi = 0; gi < b->groups.size(); gi++) {
+            Group& g = *b->groups[gi];
+            if (g.chans.empty()) continue;
+            int produced = b->blk_nout[g.chans[0]];
+            if (produced > 0 && audio) {
+                // PROFILE_4 tap = the audio rows themselves
+                for (int c : g.chans) if (b->ch[c].tap_mask & 16u) {
+                    std::vector<float> tmp(produced);
+                    CSDR_CK(cudaMemcpyAsync(tmp.data(), b->d_audio + (size_t)c * b->audio_cap + goff[gi], produced * sizeof(float), cudaMemcpyDeviceToHost, b->st));
+                    CSDR_CK(cudaStreamSynchronize(b->st));
+                    b->ch[c].tap[4].insert(b->ch[c].tap[4].end(), tmp.begin(), tmp.end());
+                }
+            }
+            goff[gi] += produced;
+            for (int c : g.chans) nout[c] += produced;
+            nmax = std::max(nmax, goff[gi]);
+        }
+        CSDR_TRY(b->collect_taps());
+        // the staging buffer (or the caller's memory) must not change until the copy is done
+        CSDR_CK(cudaStreamSynchronize(b->st));
+    }
+    if (audio && nmax > 0) {
+        CSDR_CK(cudaMemcpy2DAsync(audio, (size_t)audio_stride * sizeof(float), b->d_audio, (size_t)b->audio_cap * sizeof(float),
+                                  (size_t)nmax * sizeof(float), b->nch, cudaMemcpyDeviceToHost, b->st));
+    }
+    CSDR_CK(cudaStreamSynchronize(b->st));
+    if (n_out) memcpy(n_out, nout.data(), b->nch * sizeof(int));
+    return nmax;
+}
+
+int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, void* d_audio, int audio_stride, int* n_out_max)
+{
+    if (!b || !d_iq) { set_error("bank_process_device: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    if (n_in != b->L) { set_error("bank_process_device: n_in %d must equal the block length %d", n_in, b->L); return CUTESDR_E_ARG; }
+    CSDR_TRY(stage_block(b, reinterpret_cast<const float2*>(d_iq), cudaMemcpyDeviceToDevice));
+    int m = 0;
+    CSDR_TRY(b->run_block(b->d_x + kHaloMax, reinterpret_cast<float*>(d_audio), audio_stride, nullptr, &m));
+    CSDR_TRY(b->collect_taps());
+    if (n_out_max) *n_out_max = m;
+    return m;
+}
+
+int cutesdr_bank_synchronize(cutesdr_bank* b)
+{
+    if (!b) { set_error("synchronize: bad handle"); return CUTESDR_E_ARG; }
+    CSDR_CK(cudaStreamSynchronize(b->st));
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_stream(cutesdr_bank* b, void** stream)
+{
+    if (!b || !stream) { set_error("bank_stream: bad arguments"); return CUTESDR_E_ARG; }
+    *stream = (void*)b->st;
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_launch_count(cutesdr_bank* b, long long* n)
+{
+    if (!b || !n) { set_error("launch_count: bad arguments"); return CUTESDR_E_ARG; }
+    *n = b->lc.n;
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_tap_enable(cutesdr_bank* b, int c, unsigned profile_mask)
+{
+    if (!b || c < 0 || c >= b->nch) { set_error("tap_enable: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    b->ch[c].tap_mask = profile_mask;
+    for (int p = 1; p <= 4; p++) b->ch[c].tap[p].clear();
+    for (auto& g : b->groups) {
+        g->any_tap = false;
+        for (int u : g->chans) if (b->ch[u].tap_mask & 0xEu) g->any_tap = true;
+    }
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_tap_size(cutesdr_bank* b, int c, int profile, long* n_floats)
+{
+    if (!b || !n_floats || c < 0 || c >= b->nch || profile < 1 || profile > 4) { set_error("tap_size: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    *n_floats = (long)b->ch[c].tap[profile].size();
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_tap_read(cutesdr_bank* b, int c, int profile, float* out, long cap_floats)
+{
+    if (!b || !out || c < 0 || c >= b->nch || profile < 1 || profile > 4) { set_error("tap_read: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    std::vector<float>& v = b->ch[c].tap[profile];
+    long n = std::min<long>(cap_floats, (long)v.size());
+    memcpy(out, v.data(), n * sizeof(float));
+    v.clear();
+    return (int)std::min<long>(n, 0x7fffffff);
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// bank.cuh -- the receiver bank: N x CDemodulator (dsp/demodulator.cpp:47-215) on one wideband
+// stream. Channels that share a decimation chain (same MaxBW -> same stage list and output
+// rate) form a Group whose kernels run batched; groups run back to back on the bank's stream.
+#pragma once
+#include "common.cuh"
+#include "decimator.cuh"
+#include "fastfir.cuh"
+#include "post.cuh"
+#include "resampler.cuh"
+#include "blanker.cuh"
+
+namespace csdr {
+
+struct ChanCfg {
+    int mode = -1;                       // m_DemodMode
+    cutesdr_demod_info info{};           // m_DemodInfo
+    bool configured = false;
+    double demod_cw = 0.0;               // CDemodulator::m_CW_Offset
+    double dc_cw = 0.0;                  // CDownConvert::m_CW_Offset
+    double dc_nco_freq = 0.0;            // CDownConvert::m_NcoFreq (already includes a CW offset)
+    double dc_max_bw = 48000.0;          // CDownConvert::m_MaxBW after SetInputSampleRate
+    double max_bw = 48000.0;             // m_DesiredMaxOutputBandwidth
+    int group = -1, local = -1;
+    unsigned tap_mask = 0;
+    std::vector<float> tap[5];
+};
+
+struct Group {
+    double max_bw = 0;
+    std::vector<int> chans;              // user channel index of each local channel
+    Decimator dec;
+    FirBank fir;
+    PostBank post;
+    std::unique_ptr<ResamplerBank> rs;
+    float2* d_y = nullptr;               // FIR output [t][stride]
+    float2* d_tap3 = nullptr;            // post-AGC tap [t][stride] (allocated on demand)
+    float* d_demod = nullptr;            // demod output [local c][kMaxBurstSamples] when resampling
+    int* d_chan_map = nullptr;
+    int* d_local_map = nullptr;          // identity map (for resampler input rows)
+    long long bursts_done = 0;
+    int last_fir_n = 0;                  // FIR samples produced by the last block
+    bool any_tap = false;
+    ~Group();
+};
+
+constexpr int kMaxBurstSamples = 2 * kBurst;   // a DSP block completes at most two FIR bursts
+
+}  // namespace csdr
+
+struct cutesdr_bank {
+    int nch = 0;
+    double in_rate = 0;
+    int device = 0;
+    cudaStream_t st = 0;
+    csdr::LaunchCounter lc;
+    std::mutex mu;
+    std::vector<csdr::ChanCfg> ch;
+    std::vector<std::unique_ptr<csdr::Group>> groups;
+    bool layout_dirty = true;
+    int L = 0;                           // m_InBufLimit
+    float2* d_x = nullptr;               // [kHaloMax | L]
+    float2* h_stage = nullptr;           // pinned staging of one block
+    int h_fill = 0;
+    long long stream_pos = 0;
+    float* d_audio = nullptr;            // [nch][audio_cap]
+    int audio_cap = 0;
+    double audio_rate = 0.0;             // > 0: CFractResampler to this rate
+    std::unique_ptr<csdr::Blanker> nb;
+    bool nb_on = false;
+    double nb_thresh = 50.0, nb_width = 2.0;
+    std::vector<int> blk_nout;           // per channel, samples produced by the last block
+
+    int rebuild();
+    int run_block(float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);
+    int collect_taps();
+    ~cutesdr_bank();
+};

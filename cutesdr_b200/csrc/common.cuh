@@ -1,0 +1,56 @@
+// common.cuh -- shared declarations for libcutesdr_cuda (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <map>
+#include <memory>
+
+#include "../../include/cutesdr_cuda.h"
+
+namespace csdr {
+
+void set_error(const char* fmt, ...);
+
+#define CSDR_CK(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            csdr::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return CUTESDR_E_CUDA;                                                           \
+        }                                                                                    \
+    } while (0)
+
+#define CSDR_TRY(expr)                    \
+    do {                                  \
+        int rc__ = (expr);                \
+        if (rc__ < 0) return rc__;        \
+    } while (0)
+
+constexpr double kTwoPi = 2.0 * 3.14159265358979323846;   // K_2PI, dsp/datatypes.h:42
+constexpr double kPi = 3.14159265358979323846;
+
+constexpr int kHaloMax = 128;       // complex samples kept in front of every wideband block
+constexpr int kFirFft = 2048;       // CONV_FFT_SIZE, dsp/fastfir.cpp:55
+constexpr int kFirTaps = 1025;      // CONV_FIR_SIZE, dsp/fastfir.cpp:56
+constexpr int kBurst = 1024;        // samples CFastFIR emits per FFT
+constexpr int kDecRing = 4096;      // per-channel ring of decimated samples feeding CFastFIR
+constexpr int kMaxStages = 24;
+constexpr int kAgcBuf = 2048;       // MAX_DELAY_BUF, dsp/agc.h:15
+constexpr int kFirMax = 75;         // MAX_NUMCOEF, dsp/fir.h:15
+
+// Every kernel launch of the library goes through this counter (reported as gpu_launches).
+struct LaunchCounter {
+    long long n = 0;
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int next_pow2(long long v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace csdr

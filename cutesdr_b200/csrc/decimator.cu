@@ -1,0 +1,492 @@
+// decimator.cu -- kernel 1 (fused NCO mix + CIC3 cascade) and kernel 2 (half-band stages).
+//
+// Data layout
+//   wideband block x : complex64[L] in HBM, kHaloMax samples of the previous block in front.
+//   K1  : grid (time tiles, channel blocks). A CTA stages one time tile of x in shared memory
+//         (float4 loads); every LANE is one CHANNEL and walks the tile sequentially, so the
+//         tile is read with broadcast LDS, the oscillator, the mixer product and all CIC3
+//         states live in registers, and nothing is exchanged between lanes. Tiles overlap by
+//         a halo that re-primes the (feed-forward) CIC states, so tiles are independent.
+//         Output (rate fs/2^ncic) goes time-major/channel-minor [row][stride]: one coalesced
+//         256-byte store per warp and output row.
+//   K2  : one launch per half-band stage, thread per (output row, channel), taps in constant
+//         memory, symmetric taps folded; each stage's input is a power-of-two ring of rows so
+//         the N-1 rows of history simply persist between blocks. The last stage transposes
+//         into the per-channel ring [c][kDecRing] that CFastFIR's overlap-save windows read.
+//
+// Reference: CDownConvert::ProcessData and the three DecBy2 classes, dsp/downconvert.cpp:186-460.
+#include "decimator.cuh"
+#include "halfband_tables.h"
+
+namespace csdr {
+
+// ------------------------------------------------------------------------------------------
+// host: stage ladder (dsp/downconvert.cpp:127-166)
+// ------------------------------------------------------------------------------------------
+double plan_stages(double in_rate, double max_bw, std::vector<int>& lens)
+{
+    lens.clear();
+    double f = in_rate;
+    const double last_limit = .5 - csdr_hb_alias_free[CSDR_HB_NUM_KINDS - 1];
+    while (f > (max_bw / last_limit) && f > (7900.0 * 2.0)) {      // MIN_OUTPUT_RATE, :52
+        for (int k = 0; k < CSDR_HB_NUM_KINDS; k++) {
+            if (f >= (max_bw / (.5 - csdr_hb_alias_free[k]))) {
+                lens.push_back(csdr_hb_len[k]);
+                break;
+            }
+        }
+        f /= 2.0;
+    }
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__constant__ float c_hb_taps[88];
+static std::once_flag g_taps_once[16];
+
+static int upload_taps()
+{
+    int dev = 0;
+    CSDR_CK(cudaGetDevice(&dev));
+    cudaError_t err = cudaSuccess;
+    std::call_once(g_taps_once[dev & 15], [&]() {
+        float h[88];
+        for (int i = 0; i < 88; i++) h[i] = (float)csdr_hb_taps[i];
+        err = cudaMemcpyToSymbol(c_hb_taps, h, sizeof(h));
+    });
+    if (err != cudaSuccess) { set_error("tap upload: %s", cudaGetErrorString(err)); return CUTESDR_E_CUDA; }
+    return CUTESDR_OK;
+}
+
+struct OutDesc {
+    float2* p;
+    unsigned mask;        // rows-1 (time-major ring)
+    int stride;           // channels per row
+    int transposed;       // 1: per-channel ring [c][kDecRing]
+    long long base;       // absolute row index of this block's first output
+};
+
+__device__ __forceinline__ void store_out(const OutDesc& od, long long row, int c, float2 v)
+{
+    if (od.transposed)
+        od.p[(size_t)c * kDecRing + (size_t)((od.base + row) & (kDecRing - 1))] = v;
+    else
+        od.p[(size_t)((od.base + row) & od.mask) * od.stride + c] = v;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// exact oscillator seed from the 64-bit phase (turns * 2^64): angle = pi * (hi32 / 2^31)
+__device__ __forceinline__ float2 seed_osc(unsigned long long ph)
+{
+    float t = (float)(int)(unsigned)(ph >> 32) * (1.0f / 2147483648.0f);
+    float s, c;
+    sincospif(t, &s, &c);
+    return make_float2(c, s);
+}
+
+struct CicSt { float2 xodd, xeven; };
+
+template <int NCIC> struct K1Cfg {
+    static constexpr int G = 1 << NCIC;                    // input samples per final CIC output
+    static constexpr int B = G < 32 ? 32 : G;              // unrolled body length
+    static constexpr int H = NCIC == 0 ? 0 : (NCIC <= 4 ? 32 : (2 << NCIC));   // halo >= 2^(ncic+1)-2
+};
+
+// CIC3 decimate-by-2, scale .125 folded into the kernel's output scale
+// (y = odd + Xeven + 3*(Xodd + even), dsp/downconvert.cpp:450-455).
+template <int NCIC, int S, int IDX>
+__device__ __forceinline__ void cic_feed(float2 v, CicSt* st, float2* ev, bool emit, const OutDesc& od,
+                                         long long row0, int c, float scale)
+{
+    if constexpr (S == NCIC) {
+        if (emit) store_out(od, row0 + IDX, c, make_float2(v.x * scale, v.y * scale));
+    } else if constexpr ((IDX & 1) == 0) {
+        ev[S] = v;
+    } else {
+        float2 e = ev[S], r;
+        r.x = (v.x + st[S].xeven.x) + 3.0f * (st[S].xodd.x + e.x);
+        r.y = (v.y + st[S].xeven.y) + 3.0f * (st[S].xodd.y + e.y);
+        st[S].xodd = v;
+        st[S].xeven = e;
+        cic_feed<NCIC, S + 1, (IDX >> 1)>(r, st, ev, emit, od, row0, c, scale);
+    }
+}
+
+template <int NCIC, int K, int B> struct Body {
+    static __device__ __forceinline__ void run(const float2* t, float2& o, float2 w, CicSt* st, float2* ev,
+                                               bool emit, const OutDesc& od, long long row0, int c, float scale)
+    {
+        float2 xv = t[K];                 // all lanes read the same address: broadcast LDS
+        float2 y = cmul(xv, o);           // mixer, dsp/downconvert.cpp:238-239
+        if (K + 1 < B) o = cmul(o, w);    // oscillator step, :211-212
+        cic_feed<NCIC, 0, K>(y, st, ev, emit, od, row0, c, scale);
+        Body<NCIC, K + 1, B>::run(t, o, w, st, ev, emit, od, row0, c, scale);
+    }
+};
+template <int NCIC, int B> struct Body<NCIC, B, B> {
+    static __device__ __forceinline__ void run(const float2*, float2&, float2, CicSt*, float2*, bool,
+                                               const OutDesc&, long long, int, float) {}
+};
+
+// ------------------------------------------------------------------------------------------
+// K1: fused NCO mix + NCIC x CIC3
+// ------------------------------------------------------------------------------------------
+template <int NCIC>
+__global__ void __launch_bounds__(256) k_mix_cic(const float2* __restrict__ x, int L, int tile_len,
+                                                 const NcoDev* __restrict__ nco,
+                                                 const unsigned long long* __restrict__ phase_cur,
+                                                 unsigned long long* __restrict__ phase_next, int nch,
+                                                 OutDesc od, float scale)
+{
+    constexpr int G = K1Cfg<NCIC>::G, B = K1Cfg<NCIC>::B, H = K1Cfg<NCIC>::H;
+    extern __shared__ float4 smem4[];
+    const int t0 = blockIdx.x * tile_len;
+    const int n_tile = min(tile_len, L - t0);
+    const int n_load = n_tile + H;
+    {
+        const float4* src = reinterpret_cast<const float4*>(x + (t0 - H));
+        for (int i = threadIdx.x; i < (n_load >> 1); i += blockDim.x) smem4[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= nch) return;
+
+    const NcoDev p = nco[c];
+    const unsigned long long ph0 = phase_cur[c];
+    if (blockIdx.x == 0) phase_next[c] = ph0 + (unsigned long long)L * p.inc;
+    // sample i of the block is multiplied by e^{j(P + (i+1) inc)} (the reference rotates first)
+    unsigned long long ph = ph0 + (unsigned long long)(long long)(t0 - H + 1) * p.inc;
+    const unsigned long long ph_step = p.inc * (unsigned long long)B;
+    const float2 w1 = make_float2(p.w1c, p.w1s), wg = make_float2(p.wgc, p.wgs);
+
+    CicSt st[NCIC > 0 ? NCIC : 1];
+    float2 ev[NCIC > 0 ? NCIC : 1];
+#pragma unroll
+    for (int s = 0; s < (NCIC > 0 ? NCIC : 1); s++) {
+        st[s].xodd = make_float2(0.f, 0.f);
+        st[s].xeven = make_float2(0.f, 0.f);
+        ev[s] = make_float2(0.f, 0.f);
+    }
+    const float2* tile = reinterpret_cast<const float2*>(smem4);
+    const int nbody = n_load / B;
+    float2 S = make_float2(1.f, 0.f);
+    for (int b = 0; b < nbody; b++) {
+        if ((b & 7) == 0) S = seed_osc(ph);        // exact re-seed: bounds recursion drift
+        float2 o = S;
+        const bool emit = b >= (H / B);
+        const long long row0 = (long long)(t0 / G) + (long long)(b - H / B) * (B / G);
+        Body<NCIC, 0, B>::run(tile + b * B, o, w1, st, ev, emit, od, row0, c, scale);
+        S = cmul(S, wg);
+        ph += ph_step;
+    }
+}
+
+// Slow generic path for block lengths that are not a multiple of 32 (single-object API with odd
+// sizes). Same math, run-time stage count, one tile.
+__global__ void k_mix_cic_generic(const float2* __restrict__ x, int L, int ncic, const NcoDev* __restrict__ nco,
+                                  const unsigned long long* __restrict__ phase_cur,
+                                  unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nch) return;
+    const int H = ncic == 0 ? 0 : (2 << ncic);
+    const NcoDev p = nco[c];
+    const unsigned long long ph0 = phase_cur[c];
+    phase_next[c] = ph0 + (unsigned long long)L * p.inc;
+    const float2 w1 = make_float2(p.w1c, p.w1s);
+    float2 xo[8], xe[8], ev[8];
+    int par[8];
+    for (int s = 0; s < 8; s++) { xo[s] = xe[s] = ev[s] = make_float2(0.f, 0.f); par[s] = 0; }
+    float2 o = make_float2(1.f, 0.f);
+    long long row = -(long long)(H >> ncic);
+    for (int i = -H; i < L; i++) {
+        if (((i + H) & 31) == 0) o = seed_osc(ph0 + (unsigned long long)(long long)(i + 1) * p.inc);
+        float2 v = cmul(x[i], o);
+        o = cmul(o, w1);
+        int s = 0;
+        while (s < ncic) {
+            if (par[s] == 0) { ev[s] = v; par[s] = 1; break; }
+            float2 r;
+            r.x = (v.x + xe[s].x) + 3.0f * (xo[s].x + ev[s].x);
+            r.y = (v.y + xe[s].y) + 3.0f * (xo[s].y + ev[s].y);
+            xo[s] = v; xe[s] = ev[s]; par[s] = 0;
+            v = r;
+            s++;
+        }
+        if (s == ncic) {
+            if (row >= 0) store_out(od, row, c, make_float2(v.x * scale, v.y * scale));
+            row++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: one decimate-by-2 stage, thread per (output row m, channel c)
+//   half-band : y[m] = sum_j h[j] x[2m-(N-1)+j]            (dsp/downconvert.cpp:286-320, 348-423)
+//   N == 3    : CIC3, y[m] = .125 (x[2m+1] + 3x[2m] + 3x[2m-1] + x[2m-2])          (:444-460)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_halfband(const float2* __restrict__ in, unsigned in_mask, long long in_base,
+                                                  int stride, int n_out, int N, int tap_off, OutDesc od)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(idx % stride);
+    const long long m = idx / stride;
+    if (m >= n_out) return;
+    float2 acc;
+    if (N == 3) {
+        const long long a = in_base + 2 * m;
+        const float2 x1 = in[(size_t)((a + 1) & in_mask) * stride + c];
+        const float2 x0 = in[(size_t)(a & in_mask) * stride + c];
+        const float2 xm1 = in[(size_t)((a - 1) & in_mask) * stride + c];
+        const float2 xm2 = in[(size_t)((a - 2) & in_mask) * stride + c];
+        acc.x = .125f * ((x1.x + xm2.x) + 3.0f * (xm1.x + x0.x));
+        acc.y = .125f * ((x1.y + xm2.y) + 3.0f * (xm1.y + x0.y));
+    } else {
+        const long long a = in_base + 2 * m - (N - 1);     // oldest tap
+        const int half = (N - 1) >> 1;
+        const float2 xc = in[(size_t)((a + half) & in_mask) * stride + c];
+        acc.x = 0.5f * xc.x;
+        acc.y = 0.5f * xc.y;
+        int t = tap_off;
+        for (int j = 0; j < half; j += 2, t++) {
+            const float h = c_hb_taps[t];
+            const float2 u = in[(size_t)((a + j) & in_mask) * stride + c];
+            const float2 v = in[(size_t)((a + (N - 1) - j) & in_mask) * stride + c];
+            acc.x = fmaf(h, u.x + v.x, acc.x);
+            acc.y = fmaf(h, u.y + v.y, acc.y);
+        }
+    }
+    store_out(od, m, c, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// NCO start-up amplitude
+// ------------------------------------------------------------------------------------------
+__global__ void k_scale_prefix(float2* x, const float* gain, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float g = gain[i]; x[i].x *= g; x[i].y *= g; }
+}
+
+int apply_nco_startup_gain(float2* d_x, long long stream_pos, int n, cudaStream_t st, LaunchCounter* lc)
+{
+    if (stream_pos >= kNcoStartup || n <= 0) return CUTESDR_OK;
+    static float h_gain[kNcoStartup];
+    static std::once_flag once;
+    std::call_once(once, []() {
+        // a_0 = 1, a_{n+1} = a_n (1.95 - a_n^2): |Osc| seen by stream sample n
+        double a = 1.0;
+        const double steady = sqrt(0.95);
+        for (int i = 0; i < kNcoStartup; i++) { h_gain[i] = (float)(a / steady); a = a * (1.95 - a * a); }
+    });
+    int m = (int)std::min<long long>(n, kNcoStartup - stream_pos);
+    float* d_gain = nullptr;
+    CSDR_CK(cudaMallocAsync(&d_gain, m * sizeof(float), st));
+    CSDR_CK(cudaMemcpyAsync(d_gain, h_gain + stream_pos, m * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_scale_prefix<<<(m + 127) / 128, 128, 0, st>>>(d_x, d_gain, m);
+    if (lc) lc->n++;
+    CSDR_CK(cudaGetLastError());
+    CSDR_CK(cudaFreeAsync(d_gain, st));
+    return CUTESDR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Decimator
+// ------------------------------------------------------------------------------------------
+Decimator::~Decimator()
+{
+    cudaFree(d_nco_);
+    cudaFree(d_phase_[0]);
+    cudaFree(d_phase_[1]);
+    for (float2* p : d_stage_) cudaFree(p);
+    cudaFree(d_ring_);
+}
+
+static int tap_offset_for(int len)
+{
+    for (int k = 1; k < CSDR_HB_NUM_KINDS; k++)
+        if (csdr_hb_len[k] == len) return csdr_hb_tap_off[k];
+    return 0;
+}
+
+int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaStream_t st, LaunchCounter* lc)
+{
+    if (nch <= 0 || block_len <= 0) { set_error("Decimator::init: bad sizes"); return CUTESDR_E_ARG; }
+    nch_ = nch;
+    stride_ = nch >= 32 ? round_up(nch, 32) : next_pow2(nch);
+    in_rate_ = in_rate;
+    block_len_ = block_len;
+    st_ = st;
+    lc_ = lc;
+    out_rate_ = plan_stages(in_rate, max_bw, lens_);
+    if ((int)lens_.size() > kMaxStages) { set_error("too many decimation stages (%d)", (int)lens_.size()); return CUTESDR_E_ARG; }
+    if (block_len % (1 << lens_.size()) != 0) {
+        set_error("block length %d is not a multiple of 2^%d stages (dsp/downconvert.cpp:182-183)", block_len, (int)lens_.size());
+        return CUTESDR_E_ARG;
+    }
+    ncic_ = 0;
+    while (ncic_ < (int)lens_.size() && lens_[ncic_] == 3 && ncic_ < 6) ncic_++;
+    n_out_ = block_len >> lens_.size();
+    if (n_out_ > kDecRing - kFirFft) { set_error("decimated block of %d samples exceeds the FIR ring", n_out_); return CUTESDR_E_ARG; }
+    CSDR_TRY(upload_taps());
+
+    h_nco_.assign(stride_, NcoDev{0ull, 1.f, 0.f, 1.f, 0.f});
+    CSDR_CK(cudaMalloc(&d_nco_, stride_ * sizeof(NcoDev)));
+    for (int k = 0; k < 2; k++) {
+        CSDR_CK(cudaMalloc(&d_phase_[k], stride_ * sizeof(unsigned long long)));
+        CSDR_CK(cudaMemsetAsync(d_phase_[k], 0, stride_ * sizeof(unsigned long long), st_));
+    }
+    const int nhb = (int)lens_.size() - ncic_;
+    for (int s = 0; s < nhb; s++) {
+        int n_rows = block_len >> (ncic_ + s);             // rows this ring receives per block
+        int rows = next_pow2((long long)n_rows + 64);
+        float2* p = nullptr;
+        size_t bytes = (size_t)rows * stride_ * sizeof(float2);
+        CSDR_CK(cudaMalloc(&p, bytes));
+        CSDR_CK(cudaMemsetAsync(p, 0, bytes, st_));
+        d_stage_.push_back(p);
+        stage_rows_.push_back(rows);
+        stage_base_.push_back(0);
+    }
+    size_t rbytes = (size_t)stride_ * kDecRing * sizeof(float2);
+    CSDR_CK(cudaMalloc(&d_ring_, rbytes));
+    CSDR_CK(cudaMemsetAsync(d_ring_, 0, rbytes, st_));
+
+    // time tile: enough CTAs to fill 148 SMs several times over, tile >= 16 halos
+    constexpr int Bs[7] = {32, 32, 32, 32, 32, 32, 64};
+    const int B = Bs[ncic_];
+    const int cta_threads = std::min(256, round_up(stride_, 32));
+    const int chan_blocks = (stride_ + cta_threads - 1) / cta_threads;
+    int tiles_target = (148 * 8 + chan_blocks - 1) / chan_blocks;
+    int tl = block_len / std::max(1, tiles_target);
+    tl = std::max(tl, 512);
+    tl = std::min(tl, 4096);
+    tl = tl / B * B;
+    tile_len_ = std::max(tl, B);
+    dirty_ = true;
+    return CUTESDR_OK;
+}
+
+void Decimator::set_frequency(int i, double nco_freq)
+{
+    // CDownConvert::SetFrequency, dsp/downconvert.cpp:98-107. The phase increment is kept as a
+    // 64-bit binary fraction of a turn so the tile-start phase of every time tile is exact.
+    long double turns = (long double)nco_freq / (long double)in_rate_;
+    turns -= floorl(turns);
+    unsigned long long inc = (unsigned long long)(turns * 18446744073709551616.0L);
+    constexpr int Bs[7] = {32, 32, 32, 32, 32, 32, 64};
+    const int B = Bs[ncic_];
+    const double a1 = kTwoPi * (double)((long double)inc / 18446744073709551616.0L);
+    const unsigned long long incB = inc * (unsigned long long)B;
+    const double aB = kTwoPi * (double)((long double)incB / 18446744073709551616.0L);
+    NcoDev& n = h_nco_[i];
+    n.inc = inc;
+    n.w1c = (float)cos(a1); n.w1s = (float)sin(a1);
+    n.wgc = (float)cos(aB); n.wgs = (float)sin(aB);
+    dirty_ = true;
+}
+
+int Decimator::upload_dirty()
+{
+    if (!dirty_) return CUTESDR_OK;
+    CSDR_CK(cudaMemcpyAsync(d_nco_, h_nco_.data(), stride_ * sizeof(NcoDev), cudaMemcpyHostToDevice, st_));
+    // the async copy reads pageable host memory synchronously with respect to the host, so
+    // h_nco_ may be modified again as soon as this returns
+    dirty_ = false;
+    return CUTESDR_OK;
+}
+
+template <int NCIC>
+static void launch_k1(dim3 grid, int threads, size_t smem, cudaStream_t st, const float2* x, int L, int tile_len,
+                      const NcoDev* nco, const unsigned long long* pc, unsigned long long* pn, int nch, OutDesc od,
+                      float scale)
+{
+    k_mix_cic<NCIC><<<grid, threads, smem, st>>>(x, L, tile_len, nco, pc, pn, nch, od, scale);
+}
+
+int Decimator::run_block(const float2* d_x, int L)
+{
+    CSDR_TRY(upload_dirty());
+    if (L < 0) L = block_len_;
+    if (L == 0) return CUTESDR_OK;
+    if (L > block_len_ || L % (1 << lens_.size()) != 0) {
+        set_error("Decimator::run_block: length %d (capacity %d, must be a multiple of %d)", L, block_len_, 1 << lens_.size());
+        return CUTESDR_E_ARG;
+    }
+    const int nhb = (int)lens_.size() - ncic_;
+    OutDesc od;
+    if (nhb > 0) {
+        od.p = d_stage_[0];
+        od.mask = (unsigned)(stage_rows_[0] - 1);
+        od.stride = stride_;
+        od.transposed = 0;
+        od.base = stage_base_[0];
+    } else {
+        od.p = d_ring_;
+        od.mask = 0;
+        od.stride = stride_;
+        od.transposed = 1;
+        od.base = total_out_;
+    }
+    // steady-state oscillator amplitude sqrt(0.95) and the folded .125 per CIC3 stage
+    const float scale = (float)(sqrt(0.95) * ldexp(1.0, -3 * ncic_));
+    const unsigned long long* pc = d_phase_[phase_cur_];
+    unsigned long long* pn = d_phase_[phase_cur_ ^ 1];
+    if (L % 32 == 0 && (ncic_ < 6 || L % 64 == 0)) {
+        const int threads = std::min(256, round_up(stride_, 32));
+        dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);
+        const int H = ncic_ == 0 ? 0 : (ncic_ <= 4 ? 32 : (2 << ncic_));
+        size_t smem = (size_t)(tile_len_ + H) * sizeof(float2);
+        switch (ncic_) {
+        case 0: launch_k1<0>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
+        case 1: launch_k1<1>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
+        case 2: launch_k1<2>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
+        case 3: launch_k1<3>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
+        case 4: launch_k1<4>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
+        case 5: launch_k1<5>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
+        default: launch_k1<6>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
+        }
+    } else {
+        k_mix_cic_generic<<<(stride_ + 63) / 64, 64, 0, st_>>>(d_x, L, ncic_, d_nco_, pc, pn, stride_, od, scale);
+    }
+    lc_->n++;
+    CSDR_CK(cudaGetLastError());
+    phase_cur_ ^= 1;
+
+    for (int s = 0; s < nhb; s++) {
+        const int N = lens_[ncic_ + s];
+        const int n_in = L >> (ncic_ + s);
+        const int n_out = n_in >> 1;
+        OutDesc o2;
+        if (s + 1 < nhb) {
+            o2.p = d_stage_[s + 1];
+            o2.mask = (unsigned)(stage_rows_[s + 1] - 1);
+            o2.stride = stride_;
+            o2.transposed = 0;
+            o2.base = stage_base_[s + 1];
+        } else {
+            o2.p = d_ring_;
+            o2.mask = 0;
+            o2.stride = stride_;
+            o2.transposed = 1;
+            o2.base = total_out_;
+        }
+        long long work = (long long)n_out * stride_;
+        int blocks = (int)((work + 255) / 256);
+        k_halfband<<<blocks, 256, 0, st_>>>(d_stage_[s], (unsigned)(stage_rows_[s] - 1), stage_base_[s], stride_, n_out, N,
+                                            tap_offset_for(N), o2);
+        lc_->n++;
+        CSDR_CK(cudaGetLastError());
+        stage_base_[s] += n_in;
+    }
+    total_out_ += L >> lens_.size();
+    return CUTESDR_OK;
+}
+
+}  // namespace csdr

@@ -1,0 +1,74 @@
+// decimator.cuh -- batched CDownConvert: NCO mix + CIC3/half-band decimate-by-2 cascade for a
+// group of channels that share one stage list (reference: dsp/downconvert.cpp:98-460).
+#pragma once
+#include "common.cuh"
+
+namespace csdr {
+
+// Stage ladder of CDownConvert::SetDataRate (dsp/downconvert.cpp:114-173).
+// lens: 3 = CIC3, 11..51 = half-band tap count. Returns the output rate.
+double plan_stages(double in_rate, double max_bw, std::vector<int>& lens);
+
+// Amplitude of the reference's quadrature oscillator at stream sample n (its gain servo
+// 1.95-|z|^2 settles |z|^2 at 0.95 from 1.0, dsp/downconvert.cpp:211-216), divided by the
+// steady-state sqrt(0.95) the kernels fold into their output scale. Applied to the first
+// kNcoStartup samples of a stream, in place, on the device copy of the wideband block.
+constexpr int kNcoStartup = 512;
+int apply_nco_startup_gain(float2* d_x, long long stream_pos, int n, cudaStream_t st, LaunchCounter* lc);
+
+struct NcoDev {
+    unsigned long long inc;   // phase increment per input sample, turns * 2^64
+    float w1c, w1s;           // e^{j inc}
+    float wgc, wgs;           // e^{j G inc}, G = 2^ncic
+};
+
+class Decimator {
+public:
+    Decimator() {}
+    ~Decimator();
+    Decimator(const Decimator&) = delete;
+    Decimator& operator=(const Decimator&) = delete;
+
+    // nch channels at in_rate with the stage list for max_bw; block_len wideband samples per
+    // DSP block (multiple of 2^stages, dsp/downconvert.cpp:182-183).
+    int init(int nch, double in_rate, double max_bw, int block_len, cudaStream_t st, LaunchCounter* lc);
+
+    // CDownConvert::SetFrequency for local channel i (freq already includes the CW offset)
+    void set_frequency(int i, double nco_freq);
+
+    // Run one block of L <= block_len samples (L a multiple of 2^stages). d_x points at the first
+    // sample of the block inside a buffer that keeps kHaloMax samples of the previous block in
+    // front of it. L < 0 means the full block length.
+    int run_block(const float2* d_x, int L = -1);
+    int block_len() const { return block_len_; }
+
+    int nch() const { return nch_; }
+    int stride() const { return stride_; }
+    double out_rate() const { return out_rate_; }
+    int out_per_block() const { return n_out_; }
+    long long total_out() const { return total_out_; }   // decimated samples produced so far
+    const std::vector<int>& stages() const { return lens_; }
+    // per-channel ring [c][kDecRing] of decimated samples; sample j lives at j & (kDecRing-1)
+    const float2* ring() const { return d_ring_; }
+
+private:
+    int upload_dirty();
+    int nch_ = 0, stride_ = 0, block_len_ = 0, ncic_ = 0, n_out_ = 0, tile_len_ = 0;
+    double in_rate_ = 0, out_rate_ = 0;
+    std::vector<int> lens_;
+    cudaStream_t st_ = 0;
+    LaunchCounter* lc_ = nullptr;
+    std::vector<NcoDev> h_nco_;
+    bool dirty_ = true;
+    NcoDev* d_nco_ = nullptr;
+    unsigned long long* d_phase_[2] = {nullptr, nullptr};
+    int phase_cur_ = 0;
+    long long total_out_ = 0;
+    std::vector<long long> stage_base_;   // absolute row index of the next row each stage ring receives
+    // stage rings: ring s holds the INPUT rows of half-band stage s (time-major [row][stride])
+    std::vector<float2*> d_stage_;
+    std::vector<int> stage_rows_;      // power of two
+    float2* d_ring_ = nullptr;
+};
+
+}  // namespace csdr

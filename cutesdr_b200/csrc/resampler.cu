@@ -1,0 +1,128 @@
+// resampler.cu -- kernel 5: batched CFractResampler (dsp/fractresampler.cpp:144-352).
+//
+// Every output is an independent 28-tap dot product once its fractional input time is known, so
+// the grid is (outputs x rows). The time sequence itself is the reference's double accumulator
+// (t += Rate; t -= InLength per call): it is identical for all rows of a bank, so the host steps
+// it once per call and ships the times; the kernel turns (j - t)*10000 into the truncated table
+// index with the same double operations the reference uses, so table lookups are identical.
+#include "resampler.cuh"
+
+namespace csdr {
+
+void ResampleClock::advance(int n_in, double rate, std::vector<double>& times)
+{
+    times.clear();
+    int it = (int)t_;
+    while (it < n_in) {
+        times.push_back(t_);
+        t_ += rate;
+        it = (int)t_;
+    }
+    t_ -= (double)n_in;
+}
+
+// w: [nrows][row_len], row = 28 carried samples then the new inputs.
+__global__ void __launch_bounds__(128) k_resample(const float* __restrict__ w, int row_len, int nrows,
+                                                  const double* __restrict__ times, int n_out,
+                                                  const float* __restrict__ sinc, float* __restrict__ out, int out_stride,
+                                                  int out_off, const int* __restrict__ row_map,
+                                                  int16_t* __restrict__ out16, float gain, int interleave16)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (k >= n_out) return;
+    const double t = times[k];
+    const int it = (int)t;
+    const float* x = w + (size_t)r * row_len;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = 1; i <= kRsPeriods; i++) {
+        const int j = it + i;
+        const int s = (int)(((double)j - t) * (double)kRsPts);      // dsp/fractresampler.cpp:168
+        acc = fmaf(x[j], __ldg(sinc + s), acc);
+    }
+    if (out16) {
+        float v = acc * gain;                                       // :228-239 gain, clip, truncate
+        v = fminf(fmaxf(v, -32767.0f), 32767.0f);
+        out16[(size_t)k * interleave16 + r] = (int16_t)v;
+    } else {
+        const int row = row_map ? row_map[r] : r;
+        out[(size_t)row * out_stride + out_off + k] = acc;
+    }
+}
+
+// carry the last 28 inputs of every row to the row's front (dsp/fractresampler.cpp:180-182)
+__global__ void k_resample_carry(float* w, int row_len, int nrows, int n_in)
+{
+    const int r = blockIdx.x;
+    const int i = threadIdx.x;
+    float v = 0.f;
+    if (i < kRsPeriods) v = w[(size_t)r * row_len + n_in + i];
+    __syncthreads();
+    if (i < kRsPeriods) w[(size_t)r * row_len + i] = v;
+}
+
+ResamplerBank::~ResamplerBank()
+{
+    cudaFree(d_w_);
+    cudaFree(d_sinc_);
+    cudaFree(d_times_);
+    if (h_times_) cudaFreeHost(h_times_);
+}
+
+int ResamplerBank::init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc)
+{
+    nrows_ = nrows; max_in_ = max_in; st_ = st; lc_ = lc;
+    row_len_ = round_up(kRsPeriods + max_in, 4);
+    CSDR_CK(cudaMalloc(&d_w_, (size_t)nrows * row_len_ * sizeof(float)));
+    CSDR_CK(cudaMemsetAsync(d_w_, 0, (size_t)nrows * row_len_ * sizeof(float), st_));
+    // window-sinc table, dsp/fractresampler.cpp:104-115 (computed in double, stored float32)
+    std::vector<float> sinc(kRsLen);
+    for (int i = 0; i < kRsLen; i++) {
+        const double win = (0.35875 - 0.48829 * cos((kTwoPi * i) / (kRsLen - 1)) +
+                            0.14128 * cos((2.0 * kTwoPi * i) / (kRsLen - 1)) -
+                            0.01168 * cos((3.0 * kTwoPi * i) / (kRsLen - 1)));
+        const double fi = kPi * (double)(i - kRsLen / 2) / (double)kRsPts;
+        sinc[i] = (float)((i != kRsLen / 2) ? win * sin(fi) / fi : 1.0);
+    }
+    CSDR_CK(cudaMalloc(&d_sinc_, kRsLen * sizeof(float)));
+    CSDR_CK(cudaMemcpyAsync(d_sinc_, sinc.data(), kRsLen * sizeof(float), cudaMemcpyHostToDevice, st_));
+    CSDR_CK(cudaStreamSynchronize(st_));
+    clk_.reset();
+    return CUTESDR_OK;
+}
+
+int ResamplerBank::run(int n_in, double rate, float* d_out, int out_stride, int out_off, const int* d_row_map,
+                       int* n_out, int16_t* d_out16, double gain, int interleave16)
+{
+    if (n_in < 0 || n_in > max_in_ || !(rate > 0)) { set_error("resampler: bad length %d / rate %g", n_in, rate); return CUTESDR_E_ARG; }
+    clk_.advance(n_in, rate, times_);
+    const int m = (int)times_.size();
+    if (n_out) *n_out = m;
+    if (m > 0) {
+        if (m > times_cap_) {
+            cudaFree(d_times_);
+            if (h_times_) cudaFreeHost(h_times_);
+            times_cap_ = std::max(m, 2 * times_cap_) + 64;
+            CSDR_CK(cudaMalloc(&d_times_, times_cap_ * sizeof(double)));
+            CSDR_CK(cudaHostAlloc(&h_times_, times_cap_ * sizeof(double), cudaHostAllocDefault));
+        }
+        // the pinned buffer is rewritten every call: wait for the previous call's copy first
+        CSDR_CK(cudaStreamSynchronize(st_));
+        memcpy(h_times_, times_.data(), m * sizeof(double));
+        CSDR_CK(cudaMemcpyAsync(d_times_, h_times_, m * sizeof(double), cudaMemcpyHostToDevice, st_));
+        if (d_out || d_out16) {
+            dim3 grid((m + 127) / 128, nrows_);
+            k_resample<<<grid, 128, 0, st_>>>(d_w_, row_len_, nrows_, d_times_, m, d_sinc_, d_out, out_stride, out_off,
+                                              d_row_map, d_out16, (float)gain, interleave16);
+            lc_->n++;
+            CSDR_CK(cudaGetLastError());
+        }
+    }
+    k_resample_carry<<<nrows_, 32, 0, st_>>>(d_w_, row_len_, nrows_, n_in);
+    lc_->n++;
+    CSDR_CK(cudaGetLastError());
+    return CUTESDR_OK;
+}
+
+}  // namespace csdr

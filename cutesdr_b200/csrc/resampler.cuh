@@ -1,0 +1,58 @@
+// resampler.cuh -- kernel 5: batched CFractResampler (dsp/fractresampler.cpp:50-352), a 28-tap
+// Blackman-Harris windowed-sinc interpolator read from a 280001-entry table (10000 points per
+// zero crossing, index truncated -- no interpolation between table entries).
+#pragma once
+#include "common.cuh"
+
+namespace csdr {
+
+constexpr int kRsPeriods = 28;                 // SINC_PERIODS
+constexpr int kRsPts = 10000;                  // SINC_PERIOD_PTS
+constexpr int kRsLen = kRsPeriods * kRsPts + 1;
+
+// Output time sequence of one Resample() call, computed exactly like the reference's double
+// accumulator (t += Rate per output, t -= InLength at the end). Shared by all channels of a bank
+// because they share Rate and start together.
+class ResampleClock {
+public:
+    void reset() { t_ = 0.0; }
+    // fills times with the fractional input time of every output produced for n_in inputs
+    void advance(int n_in, double rate, std::vector<double>& times);
+private:
+    double t_ = 0.0;
+};
+
+class ResamplerBank {
+public:
+    ResamplerBank() {}
+    ~ResamplerBank();
+    ResamplerBank(const ResamplerBank&) = delete;
+    ResamplerBank& operator=(const ResamplerBank&) = delete;
+
+    // nrows independent real streams (a complex stream is two rows), at most max_in inputs per call
+    int init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc);
+    // device buffer the producer writes new inputs into: row r starts at in_ptr() + r*in_stride()
+    float* in_ptr() { return d_w_ + kRsPeriods; }
+    int in_stride() const { return row_len_; }
+    int max_out(int n_in, double rate) const { return (int)(n_in / rate) + 8; }
+    // Resample n_in new inputs per row. Output k of row r goes to
+    //   d_out[row_map ? row_map[r] : r][out_stride] + out_off + k   (float32), or, when d_out16 is
+    // given, to int16 after gain + clip + truncation (dsp/fractresampler.cpp:228-239).
+    // Returns the number of outputs per row through *n_out.
+    int run(int n_in, double rate, float* d_out, int out_stride, int out_off, const int* d_row_map, int* n_out,
+            int16_t* d_out16 = nullptr, double gain = 1.0, int interleave16 = 1);
+
+private:
+    int nrows_ = 0, max_in_ = 0, row_len_ = 0;
+    cudaStream_t st_ = 0;
+    LaunchCounter* lc_ = nullptr;
+    ResampleClock clk_;
+    float* d_w_ = nullptr;        // [nrows][28 + max_in] : 28 carried inputs, then the new ones
+    float* d_sinc_ = nullptr;     // [kRsLen]
+    double* d_times_ = nullptr;
+    double* h_times_ = nullptr;   // pinned
+    int times_cap_ = 0;
+    std::vector<double> times_;
+};
+
+}  // namespace csdr

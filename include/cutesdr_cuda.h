@@ -1,0 +1,220 @@
+/* cutesdr_cuda.h -- C ABI of libcutesdr_cuda: the B200 (sm_100a) implementation of
+ * CuteSDR's receive DSP chain as a batched multi-channel receiver.
+ *
+ * The reference has no FFI layer: its dsp/ class headers ARE the API. Each entry point
+ * below therefore names the reference method it replaces (file:line relative to the
+ * reference tree). A maintainer binds them from C++ shims that keep the reference class
+ * names -- see INTEGRATION.md and cutesdr_b200/compat/dsp/ (drop-in headers).
+ *
+ * Conventions
+ *   - every function returns an int status: CUTESDR_OK (0) or a negative CUTESDR_E_*;
+ *     the reference's own return value (sample counts, rates, flags) comes back through
+ *     an out-parameter or, for `*_process`, as a non-negative return value.
+ *   - sample scale is int16 full scale (+-32767), as every dB constant of the reference
+ *     assumes (dsp/fft.cpp:19, dsp/agc.cpp:69, dsp/smeter.cpp:47).
+ *   - complex buffers are interleaved re,im. `*_f32` entry points take complex64 (the fast
+ *     path); the plain ones take the reference's TYPECPX = two doubles (dsp/datatypes.h:25-39).
+ *   - handles are not thread-safe against concurrent `process` calls; setters may be called
+ *     from another thread between blocks (they take the handle's mutex, like the reference's
+ *     per-object QMutex) and take effect at the next DSP block.
+ *   - there is no CPU fallback: without a CUDA device every create call fails with
+ *     CUTESDR_E_CUDA.
+ */
+#ifndef CUTESDR_CUDA_H
+#define CUTESDR_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUTESDR_OK 0
+#define CUTESDR_E_ARG (-1)      /* bad argument / handle */
+#define CUTESDR_E_CUDA (-2)     /* CUDA runtime error (see cutesdr_last_error) */
+#define CUTESDR_E_STATE (-3)    /* call sequence error (e.g. process before set_demod) */
+#define CUTESDR_E_NOMEM (-4)
+
+/* demod modes, dsp/demodulator.h:20-28 */
+#define CUTESDR_DEMOD_AM 0
+#define CUTESDR_DEMOD_SAM 1
+#define CUTESDR_DEMOD_FM 2
+#define CUTESDR_DEMOD_USB 3
+#define CUTESDR_DEMOD_LSB 4
+#define CUTESDR_DEMOD_CWU 5
+#define CUTESDR_DEMOD_CWL 6
+
+/* tDemodInfo without its QString / click-resolution GUI fields, dsp/demodulator.h:35-54 */
+typedef struct cutesdr_demod_info {
+    int HiCut, HiCutmin, HiCutmax;
+    int LowCut, LowCutmin, LowCutmax;
+    int Offset;
+    int SquelchValue;
+    int AgcSlope, AgcThresh, AgcManualGain, AgcDecay;
+    int AgcOn, AgcHangOn;
+} cutesdr_demod_info;
+
+const char* cutesdr_last_error(void);
+const char* cutesdr_version(void);
+int cutesdr_device_count(int* n);
+
+/* ======================================================================================
+ * Receiver bank: N virtual receivers ( = N independent CDemodulator objects,
+ * dsp/demodulator.h:56-100) fed from ONE wideband complex stream.
+ * ====================================================================================== */
+typedef struct cutesdr_bank cutesdr_bank;
+
+/* N x { CDemodulator(); SetInputSampleRate(in_rate) }   dsp/demodulator.cpp:47-60,94-101 */
+int cutesdr_bank_create(cutesdr_bank** out, int n_channels, double in_rate, int device);
+void cutesdr_bank_destroy(cutesdr_bank* b);
+
+/* CDemodulator::SetDemod(Mode, info) for channel ch          dsp/demodulator.cpp:107-157 */
+int cutesdr_bank_set_demod(cutesdr_bank* b, int ch, int mode, const cutesdr_demod_info* info);
+/* CDemodulator::SetDemodFreq(Freq) for channel ch             dsp/demodulator.h:68-69 */
+int cutesdr_bank_set_demod_freq(cutesdr_bank* b, int ch, double freq);
+/* CDemodulator::GetOutputRate()                               dsp/demodulator.h:63 */
+int cutesdr_bank_get_output_rate(cutesdr_bank* b, int ch, double* rate);
+/* m_InBufLimit: input samples per DSP block                   dsp/demodulator.cpp:145-146 */
+int cutesdr_bank_block_length(cutesdr_bank* b, int* n);
+/* GetSMeterPeak()/GetSMeterAve() (peak is reset on read)      dsp/demodulator.h:64-65 */
+int cutesdr_bank_get_smeter(cutesdr_bank* b, int ch, double* peak, double* ave);
+
+/* CSdrInterface::SetupNoiseProc -> CNoiseProc::SetupBlanker on the shared wideband stream
+ *                                                             dsp/noiseproc.cpp:77-119 */
+int cutesdr_bank_set_noiseproc(cutesdr_bank* b, int on, double threshold, double width_us);
+
+/* Optional per-channel CFractResampler to `audio_rate` after the demodulator, as
+ * CSoundOut::PutOutQueue does (interface/soundout.cpp:204,262): Rate = OutputRate/audio_rate.
+ * audio_rate <= 0 disables it (audio is delivered at the demodulator output rate). */
+int cutesdr_bank_set_audio_rate(cutesdr_bank* b, double audio_rate);
+
+/* N x CDemodulator::ProcessData(n_in, iq, audio) -- mono    dsp/demodulator.cpp:163-215
+ * iq: n_in complex64 samples in HOST memory (any n_in; blocks are cut every block_length
+ * samples exactly like m_pDemodInBuf). audio: HOST float32 [n_channels][audio_stride];
+ * n_out[ch] receives the number of samples written for channel ch during this call
+ * (0 or 1024 per completed DSP block without the resampler). Returns the maximum n_out. */
+int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out);
+
+/* Same, with the block already resident in device memory (d_iq: complex64[n_in], n_in must
+ * equal block_length) and results left in device memory: d_audio float32
+ * [n_channels][audio_stride] (may be NULL to keep them internal). Asynchronous on the bank's
+ * stream; *n_out_max is known on return (burst timing is deterministic). */
+int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, void* d_audio, int audio_stride,
+                                int* n_out_max);
+int cutesdr_bank_synchronize(cutesdr_bank* b);
+/* cudaStream_t of the bank, as void* (for event timing on the launching stream) */
+int cutesdr_bank_stream(cutesdr_bank* b, void** stream);
+/* kernels launched by this bank so far */
+int cutesdr_bank_launch_count(cutesdr_bank* b, long long* n);
+
+/* Test-bench taps (the reference's PROFILE_1..4 display taps, gui/testbench.cpp:71-81,
+ * dsp/demodulator.cpp:175,180,187,208): 1 = after CDownConvert (complex), 2 = after CFastFIR
+ * (complex), 3 = after CAgc (complex), 4 = demodulated audio (real). When enabled for a
+ * channel the stream is accumulated on the host as float32 and read back with tap_read. */
+int cutesdr_bank_tap_enable(cutesdr_bank* b, int ch, unsigned profile_mask);
+int cutesdr_bank_tap_size(cutesdr_bank* b, int ch, int profile, long* n_floats);
+int cutesdr_bank_tap_read(cutesdr_bank* b, int ch, int profile, float* out, long cap_floats);
+
+/* ======================================================================================
+ * Single-object entry points (one reference object each; TYPECPX = double pairs)
+ * ====================================================================================== */
+
+/* ---- CDownConvert, dsp/downconvert.h:23-120 ---- */
+typedef struct cutesdr_downconvert cutesdr_downconvert;
+int cutesdr_downconvert_create(cutesdr_downconvert** out, int device);
+void cutesdr_downconvert_destroy(cutesdr_downconvert* h);
+/* SetFrequency                                                 dsp/downconvert.cpp:98-107 */
+int cutesdr_downconvert_set_frequency(cutesdr_downconvert* h, double nco_freq);
+/* SetCwOffset                                                  dsp/downconvert.h:29 */
+int cutesdr_downconvert_set_cw_offset(cutesdr_downconvert* h, double offset);
+/* SetDataRate -> *out_rate                                     dsp/downconvert.cpp:114-173 */
+int cutesdr_downconvert_set_data_rate(cutesdr_downconvert* h, double in_rate, double max_bw, double* out_rate);
+/* stage list as tap counts (3 = CIC3, 11, 15, ... 51) */
+int cutesdr_downconvert_stages(cutesdr_downconvert* h, int* lens, int cap, int* n);
+/* ProcessData(InLength, in, out): returns output count (>=0) or an error (<0). `in` is
+ * NOT modified (the reference overwrites it with the mixer product; no caller reads that).
+ *                                                              dsp/downconvert.cpp:186-263 */
+int cutesdr_downconvert_process(cutesdr_downconvert* h, int n_in, const double* in, double* out);
+int cutesdr_downconvert_process_f32(cutesdr_downconvert* h, int n_in, const float* in, float* out);
+
+/* ---- CFastFIR, dsp/fastfir.h:19-44 ---- */
+typedef struct cutesdr_fastfir cutesdr_fastfir;
+int cutesdr_fastfir_create(cutesdr_fastfir** out, int device);
+void cutesdr_fastfir_destroy(cutesdr_fastfir* h);
+/* SetupParameters(FLoCut, FHiCut, Offset, SampleRate)         dsp/fastfir.cpp:178-259 */
+int cutesdr_fastfir_setup(cutesdr_fastfir* h, double lo_cut, double hi_cut, double offset, double sample_rate);
+/* ProcessData: returns 1024*k output samples (k>=0)            dsp/fastfir.cpp:268-306 */
+int cutesdr_fastfir_process(cutesdr_fastfir* h, int n_in, const double* in, double* out);
+int cutesdr_fastfir_process_f32(cutesdr_fastfir* h, int n_in, const float* in, float* out);
+
+/* ---- CFft (display path), dsp/fft.h:24-85 ---- */
+typedef struct cutesdr_fft cutesdr_fft;
+int cutesdr_fft_create(cutesdr_fft** out, int device);
+void cutesdr_fft_destroy(cutesdr_fft* h);
+/* SetFFTParams(size, invert, dBCompensation, SampleFreq)      dsp/fft.cpp:118-243 */
+int cutesdr_fft_set_params(cutesdr_fft* h, int size, int invert, double db_compensation, double sample_freq);
+/* SetFFTAve / ResetFFT                                         dsp/fft.cpp:103-113,248-259 */
+int cutesdr_fft_set_ave(cutesdr_fft* h, int ave);
+int cutesdr_fft_reset(cutesdr_fft* h);
+/* PutInDisplayFFT(n, InBuf) -> *total_count                   dsp/fft.cpp:267-288 */
+int cutesdr_fft_put(cutesdr_fft* h, int n, const double* in, int* total_count);
+int cutesdr_fft_put_f32(cutesdr_fft* h, int n, const float* in, int* total_count);
+/* same, frame already in device memory (complex64[n]) -- e.g. a slice of the bank's wideband block */
+int cutesdr_fft_put_device(cutesdr_fft* h, int n, const void* d_in, int* total_count);
+int cutesdr_fft_launch_count(cutesdr_fft* h, long long* n);
+/* GetScreenIntegerFFTData(...) -> out[max_width], *overload   dsp/fft.cpp:308-410 */
+int cutesdr_fft_get_screen(cutesdr_fft* h, int max_height, int max_width, double max_db, double min_db,
+                           int start_freq, int stop_freq, int32_t* out, int* overload);
+/* averaged log-power buffer in bels, fft-shifted (index N/2 = DC) -- test tap */
+int cutesdr_fft_get_ave(cutesdr_fft* h, float* out, int cap);
+
+/* ---- CAgc (complex path), dsp/agc.h:18-63 ---- */
+typedef struct cutesdr_agc cutesdr_agc;
+int cutesdr_agc_create(cutesdr_agc** out, int device);
+void cutesdr_agc_destroy(cutesdr_agc* h);
+/* SetParameters                                                dsp/agc.cpp:104-167 */
+int cutesdr_agc_set_parameters(cutesdr_agc* h, int agc_on, int use_hang, int threshold, int manual_gain,
+                               int slope, int decay, double sample_rate);
+/* ProcessData(Length, in, out) complex, in place allowed      dsp/agc.cpp:174-296 */
+int cutesdr_agc_process(cutesdr_agc* h, int n, const double* in, double* out);
+
+/* ---- CFractResampler, dsp/fractresampler.h:16-33 ---- */
+typedef struct cutesdr_resampler cutesdr_resampler;
+int cutesdr_resampler_create(cutesdr_resampler** out, int device);
+void cutesdr_resampler_destroy(cutesdr_resampler* h);
+/* Init(MaxInputSize)                                           dsp/fractresampler.cpp:85-135 */
+int cutesdr_resampler_init(cutesdr_resampler* h, int max_input_size);
+/* Resample overloads: real->real, cpx->cpx, real->int16 (gain, clip), cpx->stereo int16
+ * return output count                                          dsp/fractresampler.cpp:144-352 */
+int cutesdr_resampler_real(cutesdr_resampler* h, int n, double rate, const double* in, double* out);
+int cutesdr_resampler_cpx(cutesdr_resampler* h, int n, double rate, const double* in, double* out);
+int cutesdr_resampler_mono16(cutesdr_resampler* h, int n, double rate, const double* in, int16_t* out, double gain);
+int cutesdr_resampler_stereo16(cutesdr_resampler* h, int n, double rate, const double* in, int16_t* out, double gain);
+
+/* ---- CNoiseProc, dsp/noiseproc.h:23-53 ---- */
+typedef struct cutesdr_noiseproc cutesdr_noiseproc;
+int cutesdr_noiseproc_create(cutesdr_noiseproc** out, int device);
+void cutesdr_noiseproc_destroy(cutesdr_noiseproc* h);
+/* SetupBlanker(On, Threshold, Width, SampleRate)              dsp/noiseproc.cpp:77-119 */
+int cutesdr_noiseproc_setup(cutesdr_noiseproc* h, int on, double threshold, double width_us, double sample_rate);
+/* ProcessBlanker(n, in, out) in place allowed                  dsp/noiseproc.cpp:121-176 */
+int cutesdr_noiseproc_process(cutesdr_noiseproc* h, int n, const double* in, double* out);
+int cutesdr_noiseproc_process_f32(cutesdr_noiseproc* h, int n, const float* in, float* out);
+
+/* ---- CDemodulator (one receiver; a 1-channel bank), dsp/demodulator.h:56-100 ---- */
+typedef struct cutesdr_demodulator cutesdr_demodulator;
+int cutesdr_demodulator_create(cutesdr_demodulator** out, int device);
+void cutesdr_demodulator_destroy(cutesdr_demodulator* h);
+int cutesdr_demodulator_set_input_sample_rate(cutesdr_demodulator* h, double rate);   /* dsp/demodulator.cpp:94-101 */
+int cutesdr_demodulator_set_demod(cutesdr_demodulator* h, int mode, const cutesdr_demod_info* info); /* :107-157 */
+int cutesdr_demodulator_set_demod_freq(cutesdr_demodulator* h, double freq);          /* dsp/demodulator.h:68-69 */
+int cutesdr_demodulator_get_output_rate(cutesdr_demodulator* h, double* rate);
+int cutesdr_demodulator_get_smeter(cutesdr_demodulator* h, double* peak, double* ave);
+/* ProcessData(InLength, TYPECPX* in, TYPEREAL* out) mono; returns samples written to out
+ *                                                              dsp/demodulator.cpp:163-215 */
+int cutesdr_demodulator_process(cutesdr_demodulator* h, int n_in, const double* in, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUTESDR_CUDA_H */

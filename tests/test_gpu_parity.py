@@ -1,0 +1,406 @@
+"""GPU parity: libcutesdr_cuda (through its C ABI) against the CPU oracle on identical inputs.
+
+The checker is oracle/liboracle.so (the restatement, pinned against the compiled reference in
+test_oracle_vs_ref.py) and, where it travelled with the snapshot, oracle/_ref (the reference itself).
+Tolerances: demodulated audio and every complex tap >= 90 dB SNR (the north star's float32
+tolerance); integer screen-FFT bins within +-1; blanker output bit-exact.
+"""
+import numpy as np
+import pytest
+
+import cutesdr_b200 as cs
+from cutesdr_b200 import modes as M
+from cutesdr_b200.synth import carrier_grid, snr_db, syn_iq
+
+pytestmark = pytest.mark.gpu
+
+RNG = np.random.default_rng(99)
+SNR_MIN = 90.0
+
+
+def noise(n, amp=3000.0):
+    return (amp * (RNG.standard_normal(n) + 1j * RNG.standard_normal(n))).astype(np.complex64).astype(np.complex128)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = cs.load_library()
+    n = np.zeros(1, dtype=np.int32)
+    import ctypes as C
+    assert L.cutesdr_device_count(n.ctypes.data_as(C.POINTER(C.c_int))) == 0 and n[0] >= 1, "no CUDA device"
+    return L
+
+
+# ------------------------------------------------------------------------------------------------
+# CDownConvert
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rate,bw,freq", [(2e6, 10000, -250000.0), (2e6, 15000, 401234.5), (2e6, 20000, 123456.7),
+                                          (20e6, 10000, 5.5e6), (20e6, 20000, -3.1e6),
+                                          (100147200.0, 15000, 31.0e6), (200294400.0, 10000, -77.7e6),
+                                          (200294400.0, 20000, 12.3e6)])
+def test_downconvert(lib, orc, rate, bw, freq):
+    a, b = orc.DownConvert(), cs.CDownConvert()
+    ra, rb = a.SetDataRate(rate, bw), b.SetDataRate(rate, bw)
+    assert ra == rb and a.stages() == b.stages()
+    a.SetFrequency(freq)
+    b.SetFrequency(freq)
+    n = int(rate / 100) & ~0xFF
+    nblk = 3 if rate < 50e6 else 2
+    # wideband noise plus a tone near the tuned frequency (so the decimated output is not just noise floor)
+    ya, yb = [], []
+    for k in range(nblk):
+        t = (np.arange(n) + k * n) / rate
+        x = noise(n, 2000.0) + 6000.0 * np.exp(2j * np.pi * (-freq + 1234.0) * t)
+        x = x.astype(np.complex64).astype(np.complex128)
+        ya.append(a.ProcessData(x))
+        yb.append(b.ProcessData(x))
+    ya, yb = np.concatenate(ya), np.concatenate(yb)
+    assert len(ya) == len(yb) == nblk * (n >> len(a.stages()))
+    assert snr_db(ya, yb) > 100.0
+
+
+def test_downconvert_startup_amplitude_and_retune(lib, orc):
+    # the first samples of a stream see the oscillator's gain servo settle from 1.0 to sqrt(.95)
+    a, b = orc.DownConvert(), cs.CDownConvert()
+    for o in (a, b):
+        o.SetDataRate(48000, 20000)      # no decimation stages: output = mixer product
+        o.SetFrequency(1000.0)
+    x = np.full(1024, 1000.0 + 0j)
+    ya, yb = a.ProcessData(x), b.ProcessData(x)
+    assert abs(abs(ya[0]) - 1000.0) < 1e-6 and abs(abs(yb[0]) - 1000.0) < 1e-2
+    assert snr_db(ya, yb) > 110.0
+    for o in (a, b):
+        o.SetFrequency(-3000.0)          # phase-continuous retune
+    ya, yb = a.ProcessData(x), b.ProcessData(x)
+    assert snr_db(ya, yb) > 110.0
+
+
+def test_downconvert_odd_length_uses_generic_path(lib, orc):
+    a, b = orc.DownConvert(), cs.CDownConvert()
+    for o in (a, b):
+        o.SetDataRate(250000.0, 10000)
+        o.SetFrequency(20000.0)
+    dec = 1 << len(a.stages())
+    for n in (dec * 37, dec * 5, dec * 64):
+        x = noise(n)
+        ya, yb = a.ProcessData(x), b.ProcessData(x)
+        assert len(ya) == len(yb)
+        assert snr_db(ya, yb) > 100.0
+
+
+# ------------------------------------------------------------------------------------------------
+# CFastFIR
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lo,hi,off,rate", [(-5000, 5000, 0, 31250.0), (100, 2800, 0, 62500.0),
+                                            (-2800, -100, 0, 97800.0), (-250, 250, 700, 48900.0)])
+def test_fastfir(lib, orc, lo, hi, off, rate):
+    a, b = orc.FastFIR(), cs.CFastFIR()
+    a.SetupParameters(lo, hi, off, rate)
+    b.SetupParameters(lo, hi, off, rate)
+    ya, yb, counts = [], [], []
+    for blk in range(14):
+        x = noise(489 if blk % 3 else 978)
+        u, v = a.ProcessData(x), b.ProcessData(x)
+        assert len(u) == len(v)
+        counts.append(len(u))
+        ya.append(u)
+        yb.append(v)
+    ya, yb = np.concatenate(ya), np.concatenate(yb)
+    assert set(counts) <= {0, 1024} and len(ya) >= 5 * 1024
+    assert snr_db(ya, yb) > 100.0
+
+
+def test_fastfir_invalid_params_keep_old_filter(lib, orc):
+    a, b = orc.FastFIR(), cs.CFastFIR()
+    for o in (a, b):
+        o.SetupParameters(-3000, 3000, 0, 31250.0)
+        o.SetupParameters(3000, -3000, 0, 31250.0)
+    x = noise(4096)
+    assert snr_db(a.ProcessData(x), b.ProcessData(x)) > 100.0
+
+
+# ------------------------------------------------------------------------------------------------
+# CAgc
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hang,slope,thresh,decay", [(0, 0, -100, 200), (1, 5, -80, 500), (0, 10, -20, 20)])
+def test_agc(lib, orc, hang, slope, thresh, decay):
+    rate = 48900.0
+    a, b = orc.Agc(), cs.CAgc()
+    a.SetParameters(1, hang, thresh, 30, slope, decay, rate)
+    b.SetParameters(1, hang, thresh, 30, slope, decay, rate)
+    for blk, amp in enumerate([3000.0, 30.0, 3000.0, 0.3, 10000.0, 100.0]):
+        x = noise(1024, amp)
+        x[100:110] = 0.0
+        ya, yb = a.ProcessData(x), b.ProcessData(x)
+        if blk > 0:
+            assert snr_db(ya, yb) > 120.0          # state is double on both sides; data is float32
+    a, b = orc.Agc(), cs.CAgc()
+    a.SetParameters(0, 0, -100, 45, 0, 200, rate)
+    b.SetParameters(0, 0, -100, 45, 0, 200, rate)
+    x = noise(512)
+    assert snr_db(a.ProcessData(x), b.ProcessData(x)) > 120.0
+
+
+# ------------------------------------------------------------------------------------------------
+# CFractResampler
+# ------------------------------------------------------------------------------------------------
+def test_resampler(lib, orc):
+    a, b = orc.FractResampler(8192), cs.CFractResampler()
+    b.Init(8192)
+    x = noise(6 * 1024).real
+    for k in range(6):
+        ya = a.Resample(x[k * 1024:(k + 1) * 1024], 31250.0 / 48000.0)
+        yb = b.Resample(x[k * 1024:(k + 1) * 1024], 31250.0 / 48000.0)
+        assert len(ya) == len(yb)                 # the time accumulator is stepped identically
+        assert snr_db(ya, yb) > 120.0
+    a, b = orc.FractResampler(8192), cs.CFractResampler()
+    b.Init(8192)
+    z = noise(2048, 20000.0)
+    ya, yb = a.Resample(z, 97800.0 / 48000.0, gain=0.8), b.Resample(z, 97800.0 / 48000.0, gain=0.8)
+    assert ya.shape == yb.shape
+    assert np.max(np.abs(ya.astype(np.int32) - yb.astype(np.int32))) <= 1     # int16 truncation of float32 vs double
+    assert np.max(np.abs(yb)) == 32767
+    ya, yb = a.Resample(z[:1000], 1.0), b.Resample(z[:1000], 1.0)
+    assert snr_db(ya, yb) > 120.0
+    ya, yb = a.Resample(x[:1000], 1.01875, gain=2.0), b.Resample(x[:1000], 1.01875, gain=2.0)
+    assert ya.shape == yb.shape and np.max(np.abs(ya.astype(np.int32) - yb.astype(np.int32))) <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# CNoiseProc
+# ------------------------------------------------------------------------------------------------
+def test_noise_blanker(lib, orc):
+    fs = 2e6
+    a, b = orc.NoiseProc(), cs.CNoiseProc()
+    for o in (a, b):
+        o.SetupBlanker(True, 50.0, 50.0, fs)
+    x = noise(200000, 500.0)
+    x[[15000, 31000, 31040, 52000, 150000]] += 30000.0
+    ya = a.ProcessBlanker(x)
+    yb = np.concatenate([b.ProcessBlanker(x[:70000]), b.ProcessBlanker(x[70000:70001]), b.ProcessBlanker(x[70001:])])
+    assert np.array_equal(ya, yb)                 # delay + zeroing of float32 data: bit exact
+    assert np.sum(ya == 0) >= 5 * 100
+    for o in (a, b):
+        o.SetupBlanker(False, 50.0, 50.0, fs)
+    assert np.array_equal(b.ProcessBlanker(x), x)
+
+
+def test_noise_blanker_wideband_rate(lib, orc):
+    # MagSamples ~ 1e6 at the 200 Msps rate: exercises the big moving-sum window
+    fs = 200294400.0
+    a, b = orc.NoiseProc(), cs.CNoiseProc()
+    for o in (a, b):
+        o.SetupBlanker(True, 50.0, 50.0, fs)
+    x = noise(1 << 21, 800.0)
+    x[[100, 700000, 1500000, 1500500, 2000000]] += 30000.0
+    ya = a.ProcessBlanker(x)
+    yb = b.ProcessBlanker(x)
+    assert np.array_equal(ya, yb)
+
+
+# ------------------------------------------------------------------------------------------------
+# CFft display path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,ave", [(4096, 1), (4096, 4), (512, 2), (2048, 3), (8192, 2), (65536, 1), (65536, 4)])
+def test_display_fft(lib, orc, N, ave):
+    fs = 2e6
+    a, b = orc.Fft(), cs.CFft()
+    for o in (a, b):
+        o.SetFFTParams(N, False, 0.0, fs)
+        o.SetFFTAve(ave)
+    modes = [M.DEMOD_AM] * 16
+    carriers = carrier_grid(16, 100e3)
+    screens = [(255, 800, 0.0, -140.0, -1000000, 1000000), (600, 1000, 0.0, -140.0, -50000, 50000),
+               (300, 1000, -10.0, -120.0, 200000, 300000)]
+    if N == 512:
+        screens = [(255, 400, 0.0, -140.0, -1000000, 1000000), (300, 500, 0.0, -140.0, 200000, 300000)]
+    t = np.arange(N) / fs
+    for frame in range(7):
+        x = syn_iq(fs, N, modes, carriers, seed=20262, n0=frame * N).astype(np.complex128)
+        if frame in (2, 3):
+            x = x + 32767.0 * np.exp(2j * np.pi * 250000 * t)      # full-scale tone -> overload flag
+            x = x.astype(np.complex64).astype(np.complex128)
+        assert a.PutInDisplayFFT(x) == b.PutInDisplayFFT(x) == frame + 1
+        for args in screens:
+            ova, ya = a.GetScreenIntegerFFTData(*args)
+            ovb, yb = b.GetScreenIntegerFFTData(*args)
+            assert ova == ovb
+            assert np.max(np.abs(ya - yb)) <= 1
+        pa, pb = 10.0 ** a.avebuf(), 10.0 ** b.avebuf().astype(np.float64)
+        assert np.max(np.abs(pa - pb)) < 1e-5 * np.max(pa)
+
+
+def test_display_fft_anchor(lib):
+    f = cs.CFft()
+    f.SetFFTParams(4096, False, 0.0, 2e6)
+    f.SetFFTAve(1)
+    t = np.arange(4096) / 2e6
+    f.PutInDisplayFFT(32767 * np.exp(2j * np.pi * 250000 * t))
+    ave = f.avebuf()
+    assert int(np.argmax(ave)) == 2560 and abs(10 * ave[2560] - 6.018479) < 1e-3
+    ov, y = f.GetScreenIntegerFFTData(255, 800, 0.0, -140.0, -1000000, 1000000)
+    assert ov and y[499] == 0 and y[0] == 255 and y[799] == 255
+
+
+# ------------------------------------------------------------------------------------------------
+# CDemodulator (one receiver) per mode, with the PROFILE taps
+# ------------------------------------------------------------------------------------------------
+CHAIN_CASES = [(M.DEMOD_AM, -5000, 5000, 0), (M.DEMOD_SAM, -5000, 5000, 0), (M.DEMOD_FM, -5000, 5000, 0),
+               (M.DEMOD_USB, 100, 2800, 1), (M.DEMOD_LSB, -2800, -100, 0), (M.DEMOD_CWU, -250, 250, 0)]
+# samples to skip before comparing: PLL acquisition / FM DC tracker (see test_oracle_vs_ref.py)
+SKIP = {M.DEMOD_SAM: 5 * 1024, M.DEMOD_FM: 12 * 1024}
+
+
+@pytest.mark.parametrize("mode,lo,hi,hang", CHAIN_CASES)
+def test_demodulator_chain_2msps(lib, orc, mode, lo, hi, hang):
+    fs, fc = 2e6, 250000.0
+    n = 700000
+    iq = syn_iq(fs, n, [mode], [fc], seed=20261, total_amp=8000.0)
+    info = M.demod_info(mode, HiCut=hi, LowCut=lo, AgcHangOn=hang, Offset=700 if mode == M.DEMOD_CWU else 0)
+    a = orc.Demodulator()
+    a.SetInputSampleRate(fs)
+    a.SetDemod(mode, info)
+    a.SetDemodFreq(-fc)
+    ya, ta = a.run(iq, taps=(1, 2, 3, 4))
+    bank = cs.ReceiverBank(1, fs)
+    bank.SetDemod(0, mode, info)
+    bank.SetDemodFreq(0, -fc)
+    assert bank.GetOutputRate(0) == a.GetOutputRate()
+    assert bank.block_length() == a.inbuf_limit()
+    bank.tap_enable(0, (1, 2, 3, 4))
+    # ragged feeding: the bank cuts DSP blocks like m_pDemodInBuf regardless of call sizes
+    outs, pos = [], 0
+    for chunk in (256, 19968, 5000, 100000, 1, n):
+        m = min(chunk, n - pos)
+        audio, n_out = bank.ProcessData(iq[pos:pos + m])
+        outs.append(audio[0, :n_out[0]].copy())
+        pos += m
+    yb = np.concatenate(outs)
+    assert len(yb) == len(ya) > 0
+    t1 = bank.tap_read(0, 1)
+    assert snr_db(ta[1][0::2] + 1j * ta[1][1::2], t1) > 100.0
+    t2 = bank.tap_read(0, 2)
+    assert snr_db(ta[2][0::2] + 1j * ta[2][1::2], t2) > 100.0
+    t3 = bank.tap_read(0, 3)
+    assert snr_db(ta[3][0::2] + 1j * ta[3][1::2], t3) > SNR_MIN
+    t4 = bank.tap_read(0, 4)
+    assert np.array_equal(t4, yb)
+    skip = SKIP.get(mode, 0)
+    assert len(ya) > skip + 4096
+    assert snr_db(ya[skip:], yb[skip:]) > SNR_MIN
+    pk, av = bank.GetSMeter(0)
+    assert abs(av - a.GetSMeterAve()) < 0.02
+
+
+def test_cdemodulator_object_config1(lib, orc):
+    # BASELINE config 1: single-channel AM (10 kHz BW) on 2.0 Msps two-tone IQ, then 48 kHz audio
+    fs, fc = 2e6, 250000.0
+    n = 1000000
+    t = np.arange(n) / fs
+    s = 1 + 0.5 * np.cos(2 * np.pi * 1000 * t) + 0.3 * np.cos(2 * np.pi * 1700 * t)
+    iq = (8000 * s * np.exp(2j * np.pi * fc * t)).astype(np.complex64)
+    info = M.demod_info(M.DEMOD_AM)
+    a = orc.Demodulator()
+    a.SetInputSampleRate(fs)
+    a.SetDemod(M.DEMOD_AM, info)
+    a.SetDemodFreq(-fc)
+    ya = a.run(iq)
+    d = cs.CDemodulator()
+    d.SetInputSampleRate(fs)
+    d.SetDemod(M.DEMOD_AM, info)
+    d.SetDemodFreq(-fc)
+    assert d.GetOutputRate() == 31250.0
+    yb = np.concatenate([d.ProcessData(iq[k:k + 65536].astype(np.complex128)) for k in range(0, n, 65536)])
+    assert len(ya) == len(yb) == 15360
+    assert snr_db(ya, yb) > SNR_MIN
+    ra, rb = orc.FractResampler(8192), cs.CFractResampler()
+    rb.Init(8192)
+    za = np.concatenate([ra.Resample(ya[k:k + 1024], 31250.0 / 48000.0) for k in range(0, len(ya), 1024)])
+    zb = np.concatenate([rb.Resample(yb[k:k + 1024], 31250.0 / 48000.0) for k in range(0, len(yb), 1024)])
+    assert len(za) == len(zb)
+    assert snr_db(za, zb) > SNR_MIN
+
+
+# ------------------------------------------------------------------------------------------------
+# Receiver bank: many channels, mixed modes, bank resampler
+# ------------------------------------------------------------------------------------------------
+def _bank_vs_oracle(orc, fs, modes, carriers, infos, iq, check, audio_rate=0.0, skip_by_mode=SKIP):
+    nch = len(modes)
+    bank = cs.ReceiverBank(nch, fs)
+    if audio_rate:
+        bank.SetAudioRate(audio_rate)
+    for c in range(nch):
+        bank.SetDemod(c, modes[c], infos[c])
+        bank.SetDemodFreq(c, -carriers[c])
+    L = bank.block_length()
+    outs = [[] for _ in range(nch)]
+    for pos in range(0, len(iq) - L + 1, L):
+        audio, n_out = bank.ProcessData(iq[pos:pos + L])
+        for c in check:
+            outs[c].append(audio[c, :n_out[c]].copy())
+    worst = 1e9
+    for c in check:
+        a = orc.Demodulator()
+        a.SetInputSampleRate(fs)
+        a.SetDemod(modes[c], infos[c])
+        a.SetDemodFreq(-carriers[c])
+        ya = a.run(iq[:(len(iq) // L) * L])
+        if audio_rate:
+            r = orc.FractResampler(8192)
+            ya = np.concatenate([r.Resample(ya[k:k + 1024], a.GetOutputRate() / audio_rate) for k in range(0, len(ya), 1024)])
+        yb = np.concatenate(outs[c])
+        assert len(ya) == len(yb) > 0, (c, len(ya), len(yb))
+        skip = skip_by_mode.get(modes[c], 0)
+        if audio_rate:
+            skip = int(skip * audio_rate / a.GetOutputRate())
+        assert len(ya) > skip + 2048, (len(ya), skip)
+        s = snr_db(ya[skip:], yb[skip:])
+        worst = min(worst, s)
+        assert s > SNR_MIN, "channel %d mode %d: %.1f dB" % (c, modes[c], s)
+    return worst
+
+
+def test_bank_mixed_modes_2msps(lib, orc):
+    fs = 2e6
+    nch = 40
+    modes = [[M.DEMOD_AM, M.DEMOD_SAM, M.DEMOD_FM, M.DEMOD_USB, M.DEMOD_LSB][c % 5] for c in range(nch)]
+    carriers = carrier_grid(nch, 45000.0)
+    infos = []
+    for c in range(nch):
+        m = modes[c]
+        if m == M.DEMOD_USB:
+            infos.append(M.demod_info(m, HiCut=2800, LowCut=100, AgcHangOn=(c % 8 == 3)))
+        elif m == M.DEMOD_LSB:
+            infos.append(M.demod_info(m, HiCut=-100, LowCut=-2800, AgcDecay=500))
+        elif m == M.DEMOD_AM:
+            infos.append(M.demod_info(m, HiCut=4000 + 100 * c, LowCut=-4000 - 100 * c, AgcSlope=c % 10))
+        else:
+            infos.append(M.demod_info(m))
+    iq = syn_iq(fs, 700000, modes, carriers, seed=20263)
+    _bank_vs_oracle(orc, fs, modes, carriers, infos, iq, check=list(range(0, nch, 3)) + [1, 2])
+
+
+def test_bank_usb_lsb_20msps_config3_slice(lib, orc):
+    # BASELINE config 3 shape (USB/LSB bank on a 20 Msps stream), reduced to 64 channels / 0.12 s so the
+    # CPU oracle finishes in seconds; the full 256-channel run is bench.py's workload
+    fs = 20e6
+    nch = 64
+    modes = [M.DEMOD_USB if c < nch // 2 else M.DEMOD_LSB for c in range(nch)]
+    carriers = carrier_grid(nch, 62500.0)
+    infos = [M.demod_info(M.DEMOD_USB, HiCut=2800, LowCut=100) if m == M.DEMOD_USB else
+             M.demod_info(M.DEMOD_LSB, HiCut=-100, LowCut=-2800) for m in modes]
+    iq = syn_iq(fs, 12 * 199936, modes, carriers, seed=20263)
+    _bank_vs_oracle(orc, fs, modes, carriers, infos, iq, check=[0, 13, 31, 32, 50, 63])
+
+
+def test_bank_nbfm_resampled_100msps_config4_slice(lib, orc):
+    # BASELINE config 4 shape: NBFM -> LP biquad -> CFractResampler to 48 kHz on the "100 Msps" stream
+    # (100 147 200 sps), 32 channels / 20 blocks
+    fs = 100147200.0
+    nch = 16
+    modes = [M.DEMOD_FM] * nch
+    carriers = carrier_grid(nch, 78125.0) + 1.0e6
+    infos = [M.demod_info(M.DEMOD_FM) for _ in range(nch)]
+    iq = syn_iq(fs, 24 * 1001472, modes, carriers, seed=20264)
+    _bank_vs_oracle(orc, fs, modes, carriers, infos, iq, check=[0, 7, 15], audio_rate=48000.0,
+                    skip_by_mode={M.DEMOD_FM: 7 * 1024})
