@@ -476,6 +476,35 @@ int cutesdr_bank_launch_count(cutesdr_bank* b, long long* n)
     return CUTESDR_OK;
 }
 
+int cutesdr_bank_kernel_timing(cutesdr_bank* b, int enable)
+{
+    if (!b) { set_error("kernel_timing: bad handle"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    for (auto& g : b->groups) g->dec.enable_timing(enable != 0);
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_kernel_time(cutesdr_bank* b, int which, double* ms_total, long long* launches)
+{
+    if (!b || which != 0) { set_error("kernel_time: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    double ms = 0.0;
+    long long n = 0;
+    for (auto& g : b->groups) {
+        double m = 0.0;
+        long long k = 0;
+        CSDR_TRY(g->dec.read_timing(&m, &k));
+        ms += m;
+        n += k;
+    }
+    if (ms_total) *ms_total = ms;
+    if (launches) *launches = n;
+    return CUTESDR_OK;
+}
+
 int cutesdr_bank_tap_enable(cutesdr_bank* b, int c, unsigned profile_mask)
 {
     if (!b || c < 0 || c >= b->nch) { set_error("tap_enable: bad arguments"); return CUTESDR_E_ARG; }

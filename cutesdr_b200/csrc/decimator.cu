@@ -299,8 +299,26 @@ int apply_nco_startup_gain(float2* d_x, long long stream_pos, int n, cudaStream_
 // ------------------------------------------------------------------------------------------
 // Decimator
 // ------------------------------------------------------------------------------------------
+int Decimator::read_timing(double* ms_total, long long* launches)
+{
+    CSDR_CK(cudaStreamSynchronize(st_));
+    for (size_t i = 0; i < ev_used_; i++) {
+        float ms = 0.f;
+        CSDR_CK(cudaEventElapsedTime(&ms, ev_pool_[i].first, ev_pool_[i].second));
+        k1_ms_ += ms;
+        k1_n_++;
+    }
+    ev_used_ = 0;
+    if (ms_total) *ms_total = k1_ms_;
+    if (launches) *launches = k1_n_;
+    k1_ms_ = 0.0;
+    k1_n_ = 0;
+    return CUTESDR_OK;
+}
+
 Decimator::~Decimator()
 {
+    for (auto& p : ev_pool_) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaFree(d_nco_);
     cudaFree(d_phase_[0]);
     cudaFree(d_phase_[1]);
@@ -438,6 +456,19 @@ int Decimator::run_block(const float2* d_x, int L)
     const float scale = (float)(sqrt(0.95) * ldexp(1.0, -3 * ncic_));
     const unsigned long long* pc = d_phase_[phase_cur_];
     unsigned long long* pn = d_phase_[phase_cur_ ^ 1];
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    if (timing_ && ev_used_ < 8192) {
+        if (ev_used_ == ev_pool_.size()) {
+            cudaEvent_t a, b2;
+            CSDR_CK(cudaEventCreate(&a));
+            CSDR_CK(cudaEventCreate(&b2));
+            ev_pool_.push_back({a, b2});
+        }
+        ev_a = ev_pool_[ev_used_].first;
+        ev_b = ev_pool_[ev_used_].second;
+        ev_used_++;
+        CSDR_CK(cudaEventRecord(ev_a, st_));
+    }
     if (L % 32 == 0 && (ncic_ < 6 || L % 64 == 0)) {
         const int threads = std::min(256, round_up(stride_, 32));
         dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);
@@ -457,6 +488,7 @@ int Decimator::run_block(const float2* d_x, int L)
     }
     lc_->n++;
     CSDR_CK(cudaGetLastError());
+    if (ev_b) CSDR_CK(cudaEventRecord(ev_b, st_));
     phase_cur_ ^= 1;
 
     for (int s = 0; s < nhb; s++) {

@@ -41,6 +41,9 @@ public:
     // front of it. L < 0 means the full block length.
     int run_block(const float2* d_x, int L = -1);
     int block_len() const { return block_len_; }
+    // CUDA-event timing of kernel 1 on the launching stream (bench.py's roofline line)
+    void enable_timing(bool on) { timing_ = on; }
+    int read_timing(double* ms_total, long long* launches);
 
     int nch() const { return nch_; }
     int stride() const { return stride_; }
@@ -69,6 +72,11 @@ private:
     std::vector<float2*> d_stage_;
     std::vector<int> stage_rows_;      // power of two
     float2* d_ring_ = nullptr;
+    bool timing_ = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool_;
+    size_t ev_used_ = 0;
+    double k1_ms_ = 0.0;
+    long long k1_n_ = 0;
 };
 
 }  // namespace csdr

@@ -113,6 +113,14 @@ class ReceiverBank:
         check(self.L.cutesdr_bank_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def kernel_timing(self, enable=True):
+        check(self.L.cutesdr_bank_kernel_timing(self.h, int(bool(enable))))
+
+    def kernel_time(self, which=0):
+        ms, n = C.c_double(), C.c_longlong()
+        check(self.L.cutesdr_bank_kernel_time(self.h, int(which), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def stream(self):
         s = C.c_void_p()
         check(self.L.cutesdr_bank_stream(self.h, C.byref(s)))

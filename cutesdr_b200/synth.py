@@ -28,7 +28,11 @@ def baseband(mode, c, t):
         b1 = 0.6 * 2500.0 / f1
         b2 = 0.4 * 2500.0 / f2
         return np.exp(1j * (b1 * np.sin(2 * np.pi * f1 * t) + b2 * np.sin(2 * np.pi * f2 * t)))
-    sign = 1.0 if mode in (DEMOD_USB, DEMOD_CWU) else -1.0
+    if mode in (DEMOD_CWU, DEMOD_CWL):
+        # carrier plus a weak +-(60 + c mod 50) Hz sideband: both inside a +-250 Hz CW filter
+        fo = 60.0 + (c % 50)
+        return 1.0 + 0.2 * np.exp(2j * np.pi * fo * t)
+    sign = 1.0 if mode == DEMOD_USB else -1.0
     return 0.5 * np.exp(sign * 2j * np.pi * f1 * t) + 0.5 * np.exp(sign * 2j * np.pi * f2 * t)
 
 

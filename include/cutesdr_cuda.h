@@ -106,6 +106,11 @@ int cutesdr_bank_synchronize(cutesdr_bank* b);
 int cutesdr_bank_stream(cutesdr_bank* b, void** stream);
 /* kernels launched by this bank so far */
 int cutesdr_bank_launch_count(cutesdr_bank* b, long long* n);
+/* CUDA-event timing of the dominant kernel on the bank's stream. kernel_timing(1) brackets every
+ * launch of kernel `which` (0 = k_mix_cic, the fused NCO + CIC cascade) with two events;
+ * kernel_time returns the accumulated milliseconds and launch count since the last read. */
+int cutesdr_bank_kernel_timing(cutesdr_bank* b, int enable);
+int cutesdr_bank_kernel_time(cutesdr_bank* b, int which, double* ms_total, long long* launches);
 
 /* Test-bench taps (the reference's PROFILE_1..4 display taps, gui/testbench.cpp:71-81,
  * dsp/demodulator.cpp:175,180,187,208): 1 = after CDownConvert (complex), 2 = after CFastFIR
