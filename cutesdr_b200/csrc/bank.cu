@@ -20,8 +20,6 @@ void set_error(const char* fmt, ...)
 
 Group::~Group()
 {
-    cudaFree(d_y);
-    cudaFree(d_tap3);
     cudaFree(d_demod);
     cudaFree(d_chan_map);
     cudaFree(d_local_map);
@@ -108,7 +106,6 @@ int cutesdr_bank::rebuild()
         const int stride = g->dec.stride();
         CSDR_TRY(g->fir.init(n, stride, st, &lc));
         CSDR_TRY(g->post.init(n, stride, g->dec.out_rate(), kMaxBurstSamples, st, &lc));
-        CSDR_CK(cudaMalloc(&g->d_y, (size_t)kMaxBurstSamples * stride * sizeof(float2)));
         CSDR_CK(cudaMalloc(&g->d_chan_map, stride * sizeof(int)));
         CSDR_CK(cudaMalloc(&g->d_local_map, stride * sizeof(int)));
         std::vector<int> map(stride, 0), ident(stride, 0);
@@ -150,15 +147,14 @@ int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_strid
         if (nbursts <= 0) continue;
         const int n = nbursts * kBurst;
         if (n > kMaxBurstSamples) { set_error("more than %d FIR bursts in one DSP block", kMaxBurstSamples / kBurst); return CUTESDR_E_STATE; }
-        CSDR_TRY(g.fir.run(g.dec.ring(), g.bursts_done, nbursts, g.d_y));
+        CSDR_TRY(g.fir.run(g.dec.ring(), g.bursts_done, nbursts, g.post.y_in(), g.post.y_stride()));
         g.bursts_done += nbursts;
         g.last_fir_n = n;
-        if (g.any_tap && !g.d_tap3) CSDR_CK(cudaMalloc(&g.d_tap3, (size_t)kMaxBurstSamples * g.dec.stride() * sizeof(float2)));
         const int off = audio_off ? audio_off[gi] : 0;
         int produced = n;
         if (g.rs) {
             // demod audio goes into the resampler's input rows, the resampler writes the user rows
-            CSDR_TRY(g.post.run(g.d_y, n, g.rs->in_ptr(), g.rs->in_stride(), 0, g.d_local_map, g.any_tap ? g.d_tap3 : nullptr));
+            CSDR_TRY(g.post.run(n, g.rs->in_ptr(), g.rs->in_stride(), 0, g.d_local_map));
             const double rate = g.dec.out_rate() / audio_rate;     // interface/soundout.cpp:204
             if (d_audio_out && off + g.rs->max_out(n, rate) > audio_stride) {
                 set_error("audio_stride %d too small for %d resampled samples at offset %d", audio_stride, g.rs->max_out(n, rate), off);
@@ -170,7 +166,7 @@ int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_strid
                 set_error("audio_stride %d too small for %d samples at offset %d", audio_stride, n, off);
                 return CUTESDR_E_ARG;
             }
-            CSDR_TRY(g.post.run(g.d_y, n, d_audio_out, audio_stride, off, g.d_chan_map, g.any_tap ? g.d_tap3 : nullptr));
+            CSDR_TRY(g.post.run(n, d_audio_out, audio_stride, off, g.d_chan_map));
         }
         for (int c : g.chans) blk_nout[c] = produced;
         nmax = std::max(nmax, produced);
@@ -192,7 +188,6 @@ int cutesdr_bank::collect_taps()
     for (auto& gp : groups) {
         Group& g = *gp;
         if (!g.any_tap) continue;
-        const int stride = g.dec.stride();
         const int n_dec = g.dec.out_per_block();
         for (int i = 0; i < (int)g.chans.size(); i++) {
             ChanCfg& cc = ch[g.chans[i]];
@@ -210,15 +205,16 @@ int cutesdr_bank::collect_taps()
                 cc.tap[1].insert(cc.tap[1].end(), f, f + 2 * n_dec);
             }
             const int n = g.last_fir_n;
-            if (n > 0 && (cc.tap_mask & 4u)) {   // PROFILE_2: FIR output column
+            if (n > 0 && (cc.tap_mask & 4u)) {   // PROFILE_2: FIR output row (the post stage has already shifted its
+                                                 // delay history, so the burst now ends at y_in()-... : read it from there)
                 std::vector<float2> tmp(n);
-                CSDR_CK(cudaMemcpy2D(tmp.data(), sizeof(float2), g.d_y + i, (size_t)stride * sizeof(float2), sizeof(float2), n, cudaMemcpyDeviceToHost));
+                CSDR_CK(cudaMemcpy(tmp.data(), g.post.y_in() + (size_t)i * g.post.y_stride() - n, n * sizeof(float2), cudaMemcpyDeviceToHost));
                 const float* f = reinterpret_cast<const float*>(tmp.data());
                 cc.tap[2].insert(cc.tap[2].end(), f, f + 2 * n);
             }
-            if (n > 0 && (cc.tap_mask & 8u) && g.d_tap3) {   // PROFILE_3: post-AGC column
+            if (n > 0 && (cc.tap_mask & 8u)) {   // PROFILE_3: post-AGC row
                 std::vector<float2> tmp(n);
-                CSDR_CK(cudaMemcpy2D(tmp.data(), sizeof(float2), g.d_tap3 + i, (size_t)stride * sizeof(float2), sizeof(float2), n, cudaMemcpyDeviceToHost));
+                CSDR_CK(cudaMemcpy(tmp.data(), g.post.tap3() + (size_t)i * g.post.tap3_stride(), n * sizeof(float2), cudaMemcpyDeviceToHost));
                 const float* f = reinterpret_cast<const float*>(tmp.data());
                 cc.tap[3].insert(cc.tap[3].end(), f, f + 2 * n);
             }

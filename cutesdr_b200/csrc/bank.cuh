@@ -32,8 +32,6 @@ struct Group {
     FirBank fir;
     PostBank post;
     std::unique_ptr<ResamplerBank> rs;
-    float2* d_y = nullptr;               // FIR output [t][stride]
-    float2* d_tap3 = nullptr;            // post-AGC tap [t][stride] (allocated on demand)
     float* d_demod = nullptr;            // demod output [local c][kMaxBurstSamples] when resampling
     int* d_chan_map = nullptr;
     int* d_local_map = nullptr;          // identity map (for resampler input rows)

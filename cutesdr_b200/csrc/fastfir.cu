@@ -7,7 +7,7 @@
 //
 // Layout: input windows come from the per-channel ring [c][kDecRing] the decimator fills;
 // H lives as complex64 [n_filters][2048] (channels with equal (lo,hi,offset,rate) share a row);
-// output goes time-major [t][stride] so the sequential per-channel stage reads coalesced.
+// output goes channel-major [c][row_stride] (one contiguous 1024-sample run per burst and channel).
 // The FFT is a shared-memory Stockham autosort (radix-2, ping-pong buffers, 32 KB).
 #include "fastfir.cuh"
 
@@ -138,9 +138,9 @@ __global__ void __launch_bounds__(256) k_fastfir(const float2* __restrict__ ring
         __syncthreads();
         float2* t = src; src = dst; dst = t;
     }
-    // keep samples 1024..2047 (dsp/fastfir.cpp:291-294)
-    float2* yo = y + (size_t)blockIdx.y * kBurst * stride + c;
-    for (int i = threadIdx.x; i < kBurst; i += 256) yo[(size_t)i * stride] = src[kBurst + i];
+    // keep samples 1024..2047 (dsp/fastfir.cpp:291-294); channel-major rows: coalesced stores
+    float2* yo = y + (size_t)c * stride + (size_t)blockIdx.y * kBurst;
+    for (int i = threadIdx.x; i < kBurst; i += 256) yo[i] = src[kBurst + i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -214,12 +214,12 @@ int FirBank::upload()
     return CUTESDR_OK;
 }
 
-int FirBank::run(const float2* d_ring, long long first_burst, int nb, float2* d_y)
+int FirBank::run(const float2* d_ring, long long first_burst, int nb, float2* d_y, int y_stride)
 {
     if (nb <= 0) return CUTESDR_OK;
     CSDR_TRY(upload());
     dim3 grid(nch_, nb);
-    k_fastfir<<<grid, 256, 0, st_>>>(d_ring, first_burst, d_H_, d_id_, d_tw_, d_y, stride_);
+    k_fastfir<<<grid, 256, 0, st_>>>(d_ring, first_burst, d_H_, d_id_, d_tw_, d_y, y_stride);
     lc_->n++;
     CSDR_CK(cudaGetLastError());
     return CUTESDR_OK;

@@ -15,8 +15,8 @@ public:
     // CFastFIR::SetupParameters for local channel i
     int setup(int i, double lo, double hi, double offset, double rate);
     // nb overlap-save bursts starting at burst index first_burst: burst b filters ring samples
-    // [b*1024-1024, b*1024+1024) and emits 1024 outputs into d_y[(k*1024+t)*stride + c].
-    int run(const float2* d_ring, long long first_burst, int nb, float2* d_y);
+    // [b*1024-1024, b*1024+1024) and emits 1024 outputs into d_y[c*y_stride + k*1024 + t].
+    int run(const float2* d_ring, long long first_burst, int nb, float2* d_y, int y_stride);
     int num_filters() const { return nfilt_; }
 
 private:

@@ -232,7 +232,7 @@ struct cutesdr_fastfir : HandleBase {
             total_in += m;
             done += m;
             if (total_in / kBurst > bursts_done) {
-                CSDR_TRY(fir.run(d_ring, bursts_done, 1, d_y));
+                CSDR_TRY(fir.run(d_ring, bursts_done, 1, d_y, kBurst));
                 bursts_done++;
                 CSDR_CK(cudaMemcpyAsync(h_buf, d_y, kBurst * sizeof(float2), cudaMemcpyDeviceToHost, st));
                 CSDR_CK(cudaStreamSynchronize(st));
@@ -302,8 +302,6 @@ int cutesdr_fastfir_process_f32(cutesdr_fastfir* h, int n_in, const float* in, f
 struct cutesdr_agc : HandleBase {
     std::unique_ptr<PostBank> post;
     double rate = 100.0;           // CAgc ctor, dsp/agc.cpp:88
-    float2* d_in = nullptr;
-    float2* d_out = nullptr;
     float2* h_buf = nullptr;
     int* d_map = nullptr;
     static constexpr int kChunk = 4096;
@@ -311,7 +309,7 @@ struct cutesdr_agc : HandleBase {
     {
         if (st) cudaStreamSynchronize(st);
         post.reset();
-        cudaFree(d_in); cudaFree(d_out); cudaFree(d_map);
+        cudaFree(d_map);
         if (h_buf) cudaFreeHost(h_buf);
         close();
     }
@@ -325,8 +323,6 @@ int cutesdr_agc_create(cutesdr_agc** out, int device)
     *out = nullptr;
     std::unique_ptr<cutesdr_agc> h(new cutesdr_agc());
     CSDR_TRY(h->open(device));
-    CSDR_CK(cudaMalloc(&h->d_in, cutesdr_agc::kChunk * sizeof(float2)));
-    CSDR_CK(cudaMalloc(&h->d_out, cutesdr_agc::kChunk * sizeof(float2)));
     CSDR_CK(cudaMalloc(&h->d_map, sizeof(int)));
     CSDR_CK(cudaMemset(h->d_map, 0, sizeof(int)));
     CSDR_CK(cudaHostAlloc(&h->h_buf, cutesdr_agc::kChunk * sizeof(float2), cudaHostAllocDefault));
@@ -367,9 +363,9 @@ int cutesdr_agc_process(cutesdr_agc* h, int n, const double* in, double* out)
     for (int done = 0; done < n;) {
         const int m = std::min(cutesdr_agc::kChunk, n - done);
         for (int i = 0; i < m; i++) h->h_buf[i] = make_float2((float)in[2 * (done + i)], (float)in[2 * (done + i) + 1]);
-        CSDR_CK(cudaMemcpyAsync(h->d_in, h->h_buf, (size_t)m * sizeof(float2), cudaMemcpyHostToDevice, h->st));
-        CSDR_TRY(h->post->run(h->d_in, m, nullptr, 0, 0, h->d_map, h->d_out));
-        CSDR_CK(cudaMemcpyAsync(h->h_buf, h->d_out, (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, h->st));
+        CSDR_CK(cudaMemcpyAsync(h->post->y_in(), h->h_buf, (size_t)m * sizeof(float2), cudaMemcpyHostToDevice, h->st));
+        CSDR_TRY(h->post->run(m, nullptr, 0, 0, h->d_map));
+        CSDR_CK(cudaMemcpyAsync(h->h_buf, h->post->tap3(), (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, h->st));
         CSDR_CK(cudaStreamSynchronize(h->st));
         for (int i = 0; i < m; i++) { out[2 * (done + i)] = h->h_buf[i].x; out[2 * (done + i) + 1] = h->h_buf[i].y; }
         done += m;

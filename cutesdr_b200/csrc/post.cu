@@ -1,11 +1,17 @@
-// post.cu -- kernel 4: S-meter, AGC and demodulator recursions, one THREAD per channel.
+// post.cu -- kernel group 4: S-meter, AGC and the demodulators on 1024-sample bursts.
 //
-// These stages are recurrences in time (AGC averagers with data-dependent rise/fall constants,
-// the hang timer, second-order PLLs through atan2/sin/cos, DC trackers, a biquad), so time is
-// sequential per channel and channels are the parallel axis: lane = channel, all streams
-// time-major [t][stride] so a warp touches one contiguous row per step. Recurrent state is kept
-// in double precision -- the averagers have time constants of 1e4 samples and float32 rounding
-// in the recursion would sit near -85 dB -- while the burst data itself is float32.
+// Everything that is pointwise or feed-forward in time runs time-parallel, one CTA per channel:
+//   k_post_pre  : S-meter dB values, AGC log-magnitudes and their exact sliding-window maximum
+//                 (doubling in shared memory; the reference's peak tracker IS a windowed max)
+//   k_post_mid  : AGC gain law (pow) x delayed signal, then envelope / phase angle per mode
+//   k_post_fir  : Kaiser FIRs (AM post filter, FM squelch high-pass), squelch decision, biquad
+// Only the true recurrences stay sequential, one LANE per channel:
+//   k_post_seq1 : S-meter attack/decay poles, AGC attack/decay averagers + hang timer
+//   k_post_seq2 : AM/SAM DC blockers and the SAM/FM second-order PLLs. The PLL detector
+//                 atan2(Im(x e^{-j phi}), Re(..)) equals wrap(arg(x) - phi); arg(x) is computed
+//                 time-parallel in k_post_mid, so the sequential loop is adds, a wrap and a clamp.
+// Recurrent state is double precision (averagers with 1e4-sample time constants would sit near
+// -85 dB in float32); burst data is float32. All rows are channel-major [c][row].
 #include "post.cuh"
 
 namespace csdr {
@@ -73,104 +79,135 @@ int design_kaiser_hp(double scale, double astop, double fpass, double fstop, dou
 }
 
 // ------------------------------------------------------------------------------------------
-// device state layout (struct of arrays, [field][stride])
+// device state layout: scalars are struct-of-arrays [field][stride]
 // ------------------------------------------------------------------------------------------
 enum { P_AGC_ON, P_AGC_HANG, P_KNEE, P_GAIN_SLOPE, P_FIXED_GAIN, P_MANUAL_GAIN, P_A_RISE, P_A_FALL, P_D_RISE,
        P_D_FALL, P_HANG_TIME, P_SQ_THRESH, P_NTAPS, P_COUNT };
-enum { S_SM_ATT, S_SM_DEC, S_SM_AVE, S_SM_PEAK, S_AGC_PEAK, S_AGC_ATT, S_AGC_DEC, S_Z1, S_PHASE, S_FREQ, S_FM_DC,
+enum { S_SM_ATT, S_SM_DEC, S_SM_AVE, S_SM_PEAK, S_AGC_ATT, S_AGC_DEC, S_Z1, S_PHASE, S_FREQ, S_FM_DC,
        S_SQ_AVE, S_LP_W1, S_LP_W2, S_COUNT };
-enum { I_AGC_DPTR, I_AGC_MPOS, I_AGC_HANGT, I_SQUELCHED, I_COUNT };
+enum { I_AGC_HANGT, I_SQUELCHED, I_COUNT };
 enum { R_AGC = 1, R_DEMOD = 2, R_FIR = 4, R_SMETER = 8 };
 
 constexpr int kHist = kFirMax - 1;
 
-__global__ void __launch_bounds__(64) k_post(const float2* __restrict__ y, int n, int nch, int stride, PostUniform u,
-                                             const double* __restrict__ par, const double* __restrict__ taps,
-                                             const int* __restrict__ mode_arr, int* __restrict__ reset_arr,
-                                             double* __restrict__ state, int* __restrict__ istate,
-                                             float2* __restrict__ agc_delay, double* __restrict__ agc_mag,
-                                             double* __restrict__ v, float* __restrict__ audio, int audio_stride,
-                                             int audio_off, const int* __restrict__ chan_map, float2* __restrict__ tap3)
+struct PostBufs {
+    float2* y; int y_row;          // [c][kYHist + max_n]
+    double* magh;                  // [c][kAgcBuf]
+    double* smag; double* peak; float2* z; double* u; double* th; int row;   // [c][max_n]
+    double* v; int v_row;          // [c][kHist + max_n]
+    const double* par; const double* taps; const int* mode; int* reset;
+    double* state; int* istate;
+    int nch, stride;
+};
+
+#define PAR(f) b.par[(size_t)(f) * b.stride + c]
+#define ST(f) b.state[(size_t)(f) * b.stride + c]
+#define IST(f) b.istate[(size_t)(f) * b.stride + c]
+
+// ---- state (re)initialisation for channels whose reset flags are raised; CTA per channel
+__global__ void __launch_bounds__(128) k_post_reset(PostBufs b)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nch) return;
-#define PAR(f) par[(size_t)(f) * stride + c]
-#define ST(f) state[(size_t)(f) * stride + c]
-#define IST(f) istate[(size_t)(f) * stride + c]
-    const int mode = mode_arr[c];
-    const int rf = reset_arr[c];
-    if (rf) {
+    const int c = blockIdx.x;
+    const int rf = b.reset[c];
+    if (!rf) return;
+    if (rf & R_AGC) {       // dsp/agc.cpp:121-136: delay line zero, magnitude window -16, averagers -5
+        for (int i = threadIdx.x; i < kYHist; i += blockDim.x) b.y[(size_t)c * b.y_row + i] = make_float2(0.f, 0.f);
+        for (int i = threadIdx.x; i < kAgcBuf; i += blockDim.x) b.magh[(size_t)c * kAgcBuf + i] = -16.0;
+    }
+    if (rf & R_FIR) for (int i = threadIdx.x; i < kHist; i += blockDim.x) b.v[(size_t)c * b.v_row + i] = 0.0;
+    if (threadIdx.x == 0) {
         if (rf & R_SMETER) { ST(S_SM_ATT) = -120.0; ST(S_SM_DEC) = -120.0; ST(S_SM_AVE) = 0.0; ST(S_SM_PEAK) = 0.0; }
-        if (rf & R_AGC) {      // dsp/agc.cpp:121-136
-            for (int i = 0; i < kAgcBuf; i++) {
-                agc_delay[(size_t)i * stride + c] = make_float2(0.f, 0.f);
-                agc_mag[(size_t)i * stride + c] = -16.0;
-            }
-            IST(I_AGC_DPTR) = 0; IST(I_AGC_HANGT) = 0; IST(I_AGC_MPOS) = 0;
-            ST(S_AGC_PEAK) = -16.0; ST(S_AGC_DEC) = -5.0; ST(S_AGC_ATT) = -5.0;
-        }
+        if (rf & R_AGC) { IST(I_AGC_HANGT) = 0; ST(S_AGC_DEC) = -5.0; ST(S_AGC_ATT) = -5.0; }
         if (rf & R_DEMOD) {
             ST(S_Z1) = 0.0; ST(S_PHASE) = 0.0; ST(S_FREQ) = 0.0; ST(S_FM_DC) = 0.0; ST(S_SQ_AVE) = 0.0;
             ST(S_LP_W1) = 0.0; ST(S_LP_W2) = 0.0;
             IST(I_SQUELCHED) = 1;
         }
-        if (rf & R_FIR) for (int i = 0; i < kHist; i++) v[(size_t)i * stride + c] = 0.0;
-        reset_arr[c] = 0;
+        b.reset[c] = 0;
     }
+}
 
-    // ---- parameters
-    const bool agc_on = PAR(P_AGC_ON) != 0.0, use_hang = PAR(P_AGC_HANG) != 0.0;
-    const double knee = PAR(P_KNEE), gain_slope = PAR(P_GAIN_SLOPE), fixed_gain = PAR(P_FIXED_GAIN);
-    const double manual_gain = PAR(P_MANUAL_GAIN);
-    const double a_rise = PAR(P_A_RISE), a_fall = PAR(P_A_FALL), d_rise = PAR(P_D_RISE), d_fall = PAR(P_D_FALL);
-    const int hang_time = (int)PAR(P_HANG_TIME);
-    const int ntaps = (int)PAR(P_NTAPS);
-
-    // ---- state
-    double sm_att = ST(S_SM_ATT), sm_dec = ST(S_SM_DEC), sm_ave = ST(S_SM_AVE), sm_peak = ST(S_SM_PEAK);
-    double peak = ST(S_AGC_PEAK), att = ST(S_AGC_ATT), dec = ST(S_AGC_DEC);
-    int dptr = IST(I_AGC_DPTR), mpos = IST(I_AGC_MPOS), hang_timer = IST(I_AGC_HANGT);
-    double z1 = ST(S_Z1), phase = ST(S_PHASE), freq = ST(S_FREQ), fm_dc = ST(S_FM_DC);
-
-    const double pll_alpha = mode == POST_FM ? u.fm_alpha : u.sam_alpha;
-    const double pll_beta = mode == POST_FM ? u.fm_beta : u.sam_beta;
-    const double pll_lo = mode == POST_FM ? u.fm_lo : u.sam_lo;
-    const double pll_hi = mode == POST_FM ? u.fm_hi : u.sam_hi;
-    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + audio_off : nullptr;
-
-    for (int i = 0; i < n; i++) {
-        const float2 xf = y[(size_t)i * stride + c];
+// ---- S-meter dB, AGC log-magnitude and its sliding-window maximum; CTA per channel
+// dynamic smem: 2 x (kAgcBuf + max_n) doubles
+__global__ void __launch_bounds__(256) k_post_pre(PostBufs b, int n, int window)
+{
+    extern __shared__ double sm_d[];
+    const int c = blockIdx.x;
+    const int len_all = kAgcBuf + b.row;
+    double* A = sm_d;
+    double* B = sm_d + len_all;
+    const int hn = window - 1;
+    const int lo = kAgcBuf - hn;
+    const int mode = b.mode[c];
+    const float2* yrow = b.y + (size_t)c * b.y_row + kYHist;
+    for (int i = threadIdx.x; i < hn; i += blockDim.x) A[lo + i] = b.magh[(size_t)c * kAgcBuf + i];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const float2 xf = yrow[t];
         const double xr = xf.x, xi = xf.y;
-        // ---- CSMeter::ProcessData, dsp/smeter.cpp:71-92
-        if (mode != POST_AGC_ONLY) {
-            const double mag = 10.0 * log10((xr * xr + xi * xi) / (32767.0 * 32767.0) + 1e-50);
+        if (mode != POST_AGC_ONLY)     // dsp/smeter.cpp:76
+            b.smag[(size_t)c * b.row + t] = 10.0 * log10((xr * xr + xi * xi) / (32767.0 * 32767.0) + 1e-50);
+        double mag = fabs(xr);
+        const double mim = fabs(xi);
+        if (mim > mag) mag = mim;
+        A[kAgcBuf + t] = log10(mag + 3.2767e-4) - log10(32767.0);     // dsp/agc.cpp:197-201
+    }
+    __syncthreads();
+    // carry the last window-1 magnitudes for the next burst (everyone has read the old ones)
+    for (int i = threadIdx.x; i < hn; i += blockDim.x) b.magh[(size_t)c * kAgcBuf + i] = A[kAgcBuf + n - hn + i];
+    // doubling: after k passes src[i] = max over [max(lo, i-2^k+1), i]
+    double* src = A;
+    double* dst = B;
+    int len = 1;
+    const int hi = kAgcBuf + n;
+    while (len * 2 <= window) {
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const double a0 = src[i];
+            const int j = i - len;
+            dst[i] = (j >= lo) ? fmax(a0, src[j]) : a0;
+        }
+        __syncthreads();
+        double* tmp = src; src = dst; dst = tmp;
+        len <<= 1;
+    }
+    // window of `window` samples ending at i = two overlapping power-of-two windows
+    // (dsp/agc.cpp:210-231 keeps exactly this maximum: new sample vs current peak, rescan when the
+    // sample leaving the window was the peak)
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int i = kAgcBuf + t;
+        b.peak[(size_t)c * b.row + t] = fmax(src[i], src[i - window + len]);
+    }
+}
+
+// ---- sequential poles; thread per channel
+__global__ void __launch_bounds__(32) k_post_seq1(PostBufs b, int n, PostUniform u)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.nch) return;
+    const int mode = b.mode[c];
+    if (mode != POST_AGC_ONLY) {
+        // CSMeter::ProcessData, dsp/smeter.cpp:77-91
+        double sm_att = ST(S_SM_ATT), sm_dec = ST(S_SM_DEC), sm_ave = ST(S_SM_AVE), sm_peak = ST(S_SM_PEAK);
+        const double* row = b.smag + (size_t)c * b.row;
+        for (int t = 0; t < n; t++) {
+            const double mag = row[t];
             sm_att = (1.0 - u.sm_attack) * sm_att + u.sm_attack * mag;
             sm_dec = (1.0 - u.sm_decay) * sm_dec + u.sm_decay * mag;
             if (sm_att > sm_dec) { sm_ave = sm_att; sm_dec = sm_att; }
             else sm_ave = sm_dec;
             if (mag > sm_peak) sm_peak = mag;
         }
-        // ---- CAgc::ProcessData, dsp/agc.cpp:174-296
-        double outr, outi;
-        if (agc_on) {
-            const float2 dl = agc_delay[(size_t)dptr * stride + c];
-            agc_delay[(size_t)dptr * stride + c] = xf;
-            if (++dptr >= u.agc_delay) dptr = 0;
-            double mag = fabs(xr);
-            const double mim = fabs(xi);
-            if (mim > mag) mag = mim;
-            mag = log10(mag + 3.2767e-4) - log10(32767.0);
-            const double oldest = agc_mag[(size_t)mpos * stride + c];
-            agc_mag[(size_t)mpos * stride + c] = mag;
-            if (++mpos >= u.agc_window) mpos = 0;
-            if (mag > peak) peak = mag;
-            else if (oldest == peak) {
-                peak = -8.0;
-                for (int k = 0; k < u.agc_window; k++) {
-                    const double t = agc_mag[(size_t)k * stride + c];
-                    if (t > peak) peak = t;
-                }
-            }
+        ST(S_SM_ATT) = sm_att; ST(S_SM_DEC) = sm_dec; ST(S_SM_AVE) = sm_ave; ST(S_SM_PEAK) = sm_peak;
+    }
+    if (PAR(P_AGC_ON) != 0.0) {
+        // attack/decay averagers of CAgc::ProcessData, dsp/agc.cpp:235-276; row <- max(attack, decay)
+        const bool use_hang = PAR(P_AGC_HANG) != 0.0;
+        const double a_rise = PAR(P_A_RISE), a_fall = PAR(P_A_FALL), d_rise = PAR(P_D_RISE), d_fall = PAR(P_D_FALL);
+        const int hang_time = (int)PAR(P_HANG_TIME);
+        double att = ST(S_AGC_ATT), dec = ST(S_AGC_DEC);
+        int hang_timer = IST(I_AGC_HANGT);
+        double* row = b.peak + (size_t)c * b.row;
+        for (int t = 0; t < n; t++) {
+            const double peak = row[t];
             if (peak > att) att = (1.0 - a_rise) * att + a_rise * peak;
             else att = (1.0 - a_fall) * att + a_fall * peak;
             if (use_hang) {
@@ -181,103 +218,191 @@ __global__ void __launch_bounds__(64) k_post(const float2* __restrict__ y, int n
                 if (peak > dec) dec = (1.0 - d_rise) * dec + d_rise * peak;
                 else dec = (1.0 - d_fall) * dec + d_fall * peak;
             }
-            const double m = att > dec ? att : dec;
-            const double gain = (m <= knee) ? fixed_gain : 0.7 * pow(10.0, m * (gain_slope - 1.0));
-            outr = (double)dl.x * gain;
-            outi = (double)dl.y * gain;
-        } else {
-            outr = manual_gain * xr;
-            outi = manual_gain * xi;
+            row[t] = att > dec ? att : dec;
         }
-        if (tap3) tap3[(size_t)i * stride + c] = make_float2((float)outr, (float)outi);
-
-        // ---- demodulators (first, sample-recursive part)
-        if (mode == POST_AM) {
-            // dsp/amdemod.cpp:68-78: envelope then DC-removal IIR
-            const double mag = sqrt(outr * outr + outi * outi);
-            const double z0 = mag + (z1 * 0.99);
-            v[(size_t)(kHist + i) * stride + c] = z0 - z1;
-            z1 = z0;
-        } else if (mode == POST_SAM || mode == POST_FM) {
-            // second-order PLL, dsp/samdemod.cpp:81-105 / dsp/fmdemod.cpp:166-187. The SAM mono
-            // path mixes with (cos, -sin) and uses +atan2; FM mixes with (cos, sin) and uses -atan2.
-            double sn, cs;
-            sincos(phase, &sn, &cs);
-            if (mode == POST_SAM) sn = -sn;
-            const double tr = cs * outr - sn * outi;
-            const double ti = cs * outi + sn * outr;
-            double err = atan2(ti, tr);
-            if (mode == POST_FM) err = -err;
-            freq += (pll_beta * err);
-            if (freq > pll_hi) freq = pll_hi;
-            else if (freq < pll_lo) freq = pll_lo;
-            phase += (freq + pll_alpha * err);
-            // the reference wraps once per call (fmod after the loop); wrapping every sample is
-            // the same angle and keeps sincos in its accurate range
-            if (phase > kTwoPi) phase -= kTwoPi;
-            else if (phase < -kTwoPi) phase += kTwoPi;
-            if (mode == POST_SAM) {
-                const double z0 = tr + (z1 * 0.99);
-                if (aout) aout[i] = (float)(z0 - z1);
-                z1 = z0;
-            } else {
-                fm_dc = (1.0 - u.fm_dc_alpha) * fm_dc + u.fm_dc_alpha * freq;
-                v[(size_t)(kHist + i) * stride + c] = (freq - fm_dc) * u.fm_gain;
-            }
-        } else if (mode == POST_SSB) {
-            if (aout) aout[i] = (float)outr;       // dsp/ssbdemod.cpp:48-53
-        }
+        ST(S_AGC_ATT) = att; ST(S_AGC_DEC) = dec; IST(I_AGC_HANGT) = hang_timer;
     }
+}
 
-    // ---- second part: feed-forward FIRs and the squelch decision
-    if (mode == POST_AM) {
-        // Kaiser low-pass, dsp/amdemod.cpp:80 -> CFir::ProcessFilter, dsp/fir.cpp:72-91
-        for (int i = 0; i < n; i++) {
-            double acc = 0.0;
-            for (int k = 0; k < ntaps; k++) acc += taps[(size_t)k * stride + c] * v[(size_t)(kHist + i - k) * stride + c];
-            if (aout) aout[i] = (float)acc;
+// ---- gain law, delayed signal, per-mode pointwise front end; CTA per channel
+__global__ void __launch_bounds__(256) k_post_mid(PostBufs b, int n, int delay, float* __restrict__ audio, int audio_stride,
+                                                  int audio_off, const int* __restrict__ chan_map)
+{
+    const int c = blockIdx.x;
+    const int mode = b.mode[c];
+    const bool agc_on = PAR(P_AGC_ON) != 0.0;
+    const double knee = PAR(P_KNEE), gain_slope = PAR(P_GAIN_SLOPE), fixed_gain = PAR(P_FIXED_GAIN);
+    const double manual_gain = PAR(P_MANUAL_GAIN);
+    float2* yrow = b.y + (size_t)c * b.y_row;
+    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + audio_off : nullptr;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        double zr, zi;
+        if (agc_on) {
+            const double m = b.peak[(size_t)c * b.row + t];
+            const double gain = (m <= knee) ? fixed_gain : 0.7 * pow(10.0, m * (gain_slope - 1.0));   // dsp/agc.cpp:278-286
+            const float2 dl = yrow[kYHist + t - delay];            // m_SigDelayBuf: `delay` samples ago
+            zr = (double)dl.x * gain;
+            zi = (double)dl.y * gain;
+        } else {
+            const float2 xf = yrow[kYHist + t];
+            zr = manual_gain * (double)xf.x;                       // :288-294
+            zi = manual_gain * (double)xf.y;
         }
-    } else if (mode == POST_FM) {
-        // PerformNoiseSquelch, dsp/fmdemod.cpp:113-152: evaluated once per burst
-        double sq_ave = ST(S_SQ_AVE);
+        b.z[(size_t)c * b.row + t] = make_float2((float)zr, (float)zi);
+        if (mode == POST_AM) b.u[(size_t)c * b.row + t] = sqrt(zr * zr + zi * zi);          // dsp/amdemod.cpp:72
+        else if (mode == POST_SAM) {
+            b.u[(size_t)c * b.row + t] = sqrt(zr * zr + zi * zi);
+            b.th[(size_t)c * b.row + t] = atan2(zi, zr);
+        } else if (mode == POST_FM) b.th[(size_t)c * b.row + t] = atan2(zi, zr);
+        else if (mode == POST_SSB) { if (aout) aout[t] = (float)zr; }                       // dsp/ssbdemod.cpp:48-53
+    }
+    __syncthreads();
+    // the last kYHist samples of [history | burst] become the next burst's delay history
+    float2 keep[kYHist / 256];
+#pragma unroll
+    for (int q = 0; q < kYHist / 256; q++) keep[q] = yrow[n + threadIdx.x + q * 256];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kYHist / 256; q++) yrow[threadIdx.x + q * 256] = keep[q];
+}
+
+__device__ __forceinline__ double wrap_pi(double d)
+{
+    return d - kTwoPi * rint(d * (1.0 / kTwoPi));
+}
+
+// ---- DC blockers and PLLs; thread per channel
+__global__ void __launch_bounds__(32) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
+                                                  int audio_stride, int audio_off, const int* __restrict__ chan_map)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.nch) return;
+    const int mode = b.mode[c];
+    if (mode != POST_AM && mode != POST_SAM && mode != POST_FM) return;
+    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + audio_off : nullptr;
+    double* vrow = b.v + (size_t)c * b.v_row + kHist;
+    if (mode == POST_AM) {
+        // DC removal H(z) = (1 - z^-1)/(1 - .99 z^-1), dsp/amdemod.cpp:73-78
+        double z1 = ST(S_Z1);
+        const double* urow = b.u + (size_t)c * b.row;
+        for (int t = 0; t < n; t++) {
+            const double z0 = urow[t] + (z1 * 0.99);
+            vrow[t] = z0 - z1;
+            z1 = z0;
+        }
+        ST(S_Z1) = z1;
+        return;
+    }
+    double phase = ST(S_PHASE), freq = ST(S_FREQ);
+    const double* throw_ = b.th + (size_t)c * b.row;
+    if (mode == POST_SAM) {
+        // dsp/samdemod.cpp:81-105: tmp = x e^{-j phase}; err = atan2(tmp) = wrap(arg x - phase);
+        // tmp.re = |x| cos(err)
+        double z1 = ST(S_Z1);
+        const double* urow = b.u + (size_t)c * b.row;
+        for (int t = 0; t < n; t++) {
+            const double err = wrap_pi(throw_[t] - phase);
+            freq += (u.sam_beta * err);
+            if (freq > u.sam_hi) freq = u.sam_hi;
+            else if (freq < u.sam_lo) freq = u.sam_lo;
+            phase = wrap_pi(phase + (freq + u.sam_alpha * err));
+            const double z0 = urow[t] * cos(err) + (z1 * 0.99);
+            if (aout) aout[t] = (float)(z0 - z1);
+            z1 = z0;
+        }
+        ST(S_Z1) = z1;
+    } else {
+        // dsp/fmdemod.cpp:166-187: tmp = x e^{+j phase}; err = -atan2(tmp) = -wrap(arg x + phase)
+        double fm_dc = ST(S_FM_DC);
+        for (int t = 0; t < n; t++) {
+            const double err = -wrap_pi(throw_[t] + phase);
+            freq += (u.fm_beta * err);
+            if (freq > u.fm_hi) freq = u.fm_hi;
+            else if (freq < u.fm_lo) freq = u.fm_lo;
+            phase = wrap_pi(phase + (freq + u.fm_alpha * err));
+            fm_dc = (1.0 - u.fm_dc_alpha) * fm_dc + u.fm_dc_alpha * freq;
+            vrow[t] = (freq - fm_dc) * u.fm_gain;
+        }
+        ST(S_FM_DC) = fm_dc;
+    }
+    ST(S_PHASE) = phase; ST(S_FREQ) = freq;
+}
+
+// ---- Kaiser FIRs, squelch, biquad; CTA per channel. dynamic smem: (kHist + max_n + kFirMax) doubles
+__global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform u, float* __restrict__ audio, int audio_stride,
+                                                  int audio_off, const int* __restrict__ chan_map)
+{
+    extern __shared__ double sm_d[];
+    __shared__ double red[8];
+    __shared__ int s_squelched;
+    const int c = blockIdx.x;
+    const int mode = b.mode[c];
+    if (mode != POST_AM && mode != POST_FM) return;
+    double* v = sm_d;
+    double* h = sm_d + kHist + b.row;
+    const int ntaps = (int)PAR(P_NTAPS);
+    double* vrow = b.v + (size_t)c * b.v_row;
+    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + audio_off : nullptr;
+    for (int i = threadIdx.x; i < kHist + n; i += blockDim.x) v[i] = vrow[i];
+    for (int i = threadIdx.x; i < kFirMax; i += blockDim.x) h[i] = b.taps[(size_t)c * kFirMax + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHist; i += blockDim.x) vrow[i] = v[n + i];      // FIR history for the next burst
+    if (mode == POST_AM) {
+        // CFir::ProcessFilter, dsp/fir.cpp:72-91 (post filter of dsp/amdemod.cpp:80)
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            double acc = 0.0;
+            for (int k = 0; k < ntaps; k++) acc += h[k] * v[kHist + t - k];
+            if (aout) aout[t] = (float)acc;
+        }
+        return;
+    }
+    // FM: PerformNoiseSquelch, dsp/fmdemod.cpp:113-152. The squelch average is a one-pole over
+    // |high-passed audio|; only its value at the END of the burst is used, which is the weighted sum
+    //   (1-a)^n s0 + a * sum_t (1-a)^(n-1-t) |hp[t]|
+    double part = 0.0;
+    const double q = 1.0 - u.fm_sq_alpha;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < ntaps; k++) acc += h[k] * v[kHist + t - k];
+        part += fabs(acc) * pow(q, (double)(n - 1 - t));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < 8; w++) sum += red[w];
+        const double sq_ave = pow(q, (double)n) * ST(S_SQ_AVE) + u.fm_sq_alpha * sum;
+        ST(S_SQ_AVE) = sq_ave;
         int squelched = IST(I_SQUELCHED);
         const double sq_thresh = PAR(P_SQ_THRESH);
-        for (int i = 0; i < n; i++) {
-            double acc = 0.0;
-            for (int k = 0; k < ntaps; k++) acc += taps[(size_t)k * stride + c] * v[(size_t)(kHist + i - k) * stride + c];
-            sq_ave = (1.0 - u.fm_sq_alpha) * sq_ave + u.fm_sq_alpha * fabs(acc);
-        }
         if (0 == sq_thresh) squelched = 1;
         else if (squelched) { if (sq_ave < (sq_thresh - 100.0)) squelched = 0; }
         else { if (sq_ave >= (sq_thresh + 100.0)) squelched = 1; }
-        if (squelched) {
-            if (aout) for (int i = 0; i < n; i++) aout[i] = 0.f;
-        } else {
+        IST(I_SQUELCHED) = squelched;
+        s_squelched = squelched;
+        if (!squelched) {
+            // 3 kHz low-pass biquad only runs while the squelch is open, CIir::ProcessFilter dsp/iir.cpp:171-180
             double w1 = ST(S_LP_W1), w2 = ST(S_LP_W2);
-            for (int i = 0; i < n; i++) {       // CIir::ProcessFilter, dsp/iir.cpp:171-180
-                const double w0 = v[(size_t)(kHist + i) * stride + c] - u.lp_a1 * w1 - u.lp_a2 * w2;
-                if (aout) aout[i] = (float)(u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2);
+            for (int t = 0; t < n; t++) {
+                const double w0 = v[kHist + t] - u.lp_a1 * w1 - u.lp_a2 * w2;
+                v[kHist + t] = u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2;
                 w2 = w1;
                 w1 = w0;
             }
             ST(S_LP_W1) = w1; ST(S_LP_W2) = w2;
         }
-        ST(S_SQ_AVE) = sq_ave;
-        IST(I_SQUELCHED) = squelched;
     }
-    if (mode == POST_AM || mode == POST_FM) {
-        // keep the last kHist inputs of the FIR for the next burst
-        for (int i = 0; i < kHist; i++) v[(size_t)i * stride + c] = v[(size_t)(n + i) * stride + c];
+    __syncthreads();
+    if (aout) {
+        if (s_squelched) for (int t = threadIdx.x; t < n; t += blockDim.x) aout[t] = 0.f;
+        else for (int t = threadIdx.x; t < n; t += blockDim.x) aout[t] = (float)v[kHist + t];
     }
-
-    ST(S_SM_ATT) = sm_att; ST(S_SM_DEC) = sm_dec; ST(S_SM_AVE) = sm_ave; ST(S_SM_PEAK) = sm_peak;
-    ST(S_AGC_PEAK) = peak; ST(S_AGC_ATT) = att; ST(S_AGC_DEC) = dec;
-    IST(I_AGC_DPTR) = dptr; IST(I_AGC_MPOS) = mpos; IST(I_AGC_HANGT) = hang_timer;
-    ST(S_Z1) = z1; ST(S_PHASE) = phase; ST(S_FREQ) = freq; ST(S_FM_DC) = fm_dc;
+}
 #undef PAR
 #undef ST
 #undef IST
-}
 
 // ------------------------------------------------------------------------------------------
 // PostBank
@@ -285,13 +410,16 @@ __global__ void __launch_bounds__(64) k_post(const float2* __restrict__ y, int n
 PostBank::~PostBank()
 {
     cudaFree(d_par_); cudaFree(d_taps_); cudaFree(d_mode_); cudaFree(d_reset_); cudaFree(d_state_);
-    cudaFree(d_istate_); cudaFree(d_agc_delay_); cudaFree(d_agc_mag_); cudaFree(d_v_);
+    cudaFree(d_istate_); cudaFree(d_y_); cudaFree(d_magh_); cudaFree(d_smag_); cudaFree(d_peak_); cudaFree(d_z_);
+    cudaFree(d_u_); cudaFree(d_th_); cudaFree(d_v_);
 }
 
 int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream_t st, LaunchCounter* lc)
 {
     nch_ = nch; stride_ = stride; rate_ = rate; st_ = st; lc_ = lc;
     max_n_ = max_samples;
+    y_row_ = kYHist + max_n_;
+    v_row_ = round_up(kHist + max_n_, 2);
     // CSMeter, dsp/smeter.cpp:66-69
     uni_.sm_attack = (1.0 - exp(-1.0 / (rate * .01)));
     uni_.sm_decay = (1.0 - exp(-1.0 / (rate * .5)));
@@ -326,23 +454,36 @@ int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream
     h_par_.assign((size_t)P_COUNT * stride, 0.0);
     h_taps_.assign((size_t)kFirMax * stride, 0.0);
     h_mode_.assign(stride, POST_NONE);
-    h_reset_.assign(stride, R_AGC | R_DEMOD | R_FIR | R_SMETER);
+    h_reset_.assign(stride, 0);
     for (int i = 0; i < nch; i++) {
+        h_reset_[i] = R_AGC | R_DEMOD | R_FIR | R_SMETER;
         h_par_[(size_t)P_AGC_ON * stride + i] = 1.0;
         h_par_[(size_t)P_NTAPS * stride + i] = 1.0;
     }
+    const size_t rows = (size_t)stride;
     CSDR_CK(cudaMalloc(&d_par_, h_par_.size() * sizeof(double)));
     CSDR_CK(cudaMalloc(&d_taps_, h_taps_.size() * sizeof(double)));
     CSDR_CK(cudaMalloc(&d_mode_, stride * sizeof(int)));
     CSDR_CK(cudaMalloc(&d_reset_, stride * sizeof(int)));
     CSDR_CK(cudaMalloc(&d_state_, (size_t)S_COUNT * stride * sizeof(double)));
     CSDR_CK(cudaMalloc(&d_istate_, (size_t)I_COUNT * stride * sizeof(int)));
-    CSDR_CK(cudaMalloc(&d_agc_delay_, (size_t)kAgcBuf * stride * sizeof(float2)));
-    CSDR_CK(cudaMalloc(&d_agc_mag_, (size_t)kAgcBuf * stride * sizeof(double)));
-    CSDR_CK(cudaMalloc(&d_v_, (size_t)(kHist + max_n_) * stride * sizeof(double)));
+    CSDR_CK(cudaMalloc(&d_y_, rows * y_row_ * sizeof(float2)));
+    CSDR_CK(cudaMalloc(&d_magh_, rows * kAgcBuf * sizeof(double)));
+    CSDR_CK(cudaMalloc(&d_smag_, rows * max_n_ * sizeof(double)));
+    CSDR_CK(cudaMalloc(&d_peak_, rows * max_n_ * sizeof(double)));
+    CSDR_CK(cudaMalloc(&d_z_, rows * max_n_ * sizeof(float2)));
+    CSDR_CK(cudaMalloc(&d_u_, rows * max_n_ * sizeof(double)));
+    CSDR_CK(cudaMalloc(&d_th_, rows * max_n_ * sizeof(double)));
+    CSDR_CK(cudaMalloc(&d_v_, rows * v_row_ * sizeof(double)));
     CSDR_CK(cudaMemsetAsync(d_state_, 0, (size_t)S_COUNT * stride * sizeof(double), st_));
     CSDR_CK(cudaMemsetAsync(d_istate_, 0, (size_t)I_COUNT * stride * sizeof(int), st_));
-    CSDR_CK(cudaMemsetAsync(d_v_, 0, (size_t)(kHist + max_n_) * stride * sizeof(double), st_));
+    CSDR_CK(cudaMemsetAsync(d_y_, 0, rows * y_row_ * sizeof(float2), st_));
+    CSDR_CK(cudaMemsetAsync(d_v_, 0, rows * v_row_ * sizeof(double), st_));
+    const size_t smem_pre = 2 * (size_t)(kAgcBuf + max_n_) * sizeof(double);
+    const size_t smem_fir = (size_t)(kHist + max_n_ + kFirMax) * sizeof(double);
+    if (smem_pre > 200 * 1024) { set_error("post: burst capacity %d too large", max_n_); return CUTESDR_E_ARG; }
+    CSDR_CK(cudaFuncSetAttribute(k_post_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pre));
+    CSDR_CK(cudaFuncSetAttribute(k_post_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_fir, 1024)));
     dirty_ = true;
     return CUTESDR_OK;
 }
@@ -396,7 +537,7 @@ void PostBank::set_am_bandwidth(int i, double bw)
 {
     double coef[kFirMax];
     int n = design_kaiser_lp(1.0, 50.0, bw, bw * 1.8, rate_, coef);
-    for (int k = 0; k < kFirMax; k++) h_taps_[(size_t)k * stride_ + i] = k < n ? coef[k] : 0.0;
+    for (int k = 0; k < kFirMax; k++) h_taps_[(size_t)i * kFirMax + k] = k < n ? coef[k] : 0.0;
     h_par_[(size_t)P_NTAPS * stride_ + i] = n;
     h_reset_[i] |= R_FIR;
     dirty_ = true;
@@ -409,7 +550,7 @@ void PostBank::set_fm(int i, int squelch_value, double fm_bw)
         fm_bw_[i] = fm_bw;
         double coef[kFirMax];
         int n = design_kaiser_hp(1.0, 50.0, fm_bw, fm_bw * .6, rate_, coef);
-        for (int k = 0; k < kFirMax; k++) h_taps_[(size_t)k * stride_ + i] = k < n ? coef[k] : 0.0;
+        for (int k = 0; k < kFirMax; k++) h_taps_[(size_t)i * kFirMax + k] = k < n ? coef[k] : 0.0;
         h_par_[(size_t)P_NTAPS * stride_ + i] = n;
         h_reset_[i] |= R_FIR;
     }
@@ -422,26 +563,41 @@ int PostBank::upload()
     CSDR_CK(cudaMemcpyAsync(d_par_, h_par_.data(), h_par_.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
     CSDR_CK(cudaMemcpyAsync(d_taps_, h_taps_.data(), h_taps_.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
     CSDR_CK(cudaMemcpyAsync(d_mode_, h_mode_.data(), stride_ * sizeof(int), cudaMemcpyHostToDevice, st_));
-    // Reset flags: the host copy holds every flag raised since the last upload; the kernel clears
-    // a device flag after acting on it, and every upload is followed by a run (upload() is only
-    // called from run()), so no stale flag can survive.
-    CSDR_CK(cudaMemcpyAsync(d_reset_, h_reset_.data(), stride_ * sizeof(int), cudaMemcpyHostToDevice, st_));
-    CSDR_CK(cudaStreamSynchronize(st_));      // host vectors are reused below / by the next setter
-    std::fill(h_reset_.begin(), h_reset_.end(), 0);
+    bool any_reset = false;
+    for (int r : h_reset_) any_reset |= (r != 0);
+    if (any_reset) CSDR_CK(cudaMemcpyAsync(d_reset_, h_reset_.data(), stride_ * sizeof(int), cudaMemcpyHostToDevice, st_));
+    CSDR_CK(cudaStreamSynchronize(st_));      // the host vectors may be edited again right away
+    if (any_reset) {
+        std::fill(h_reset_.begin(), h_reset_.end(), 0);
+        need_reset_kernel_ = true;
+    }
     dirty_ = false;
     return CUTESDR_OK;
 }
 
-int PostBank::run(const float2* d_y, int n, float* d_audio, int audio_stride, int audio_off, const int* d_chan_map,
-                  float2* d_tap3)
+int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const int* d_chan_map)
 {
     if (n <= 0) return CUTESDR_OK;
     if (n > max_n_) { set_error("PostBank::run: %d samples exceed capacity %d", n, max_n_); return CUTESDR_E_ARG; }
     CSDR_TRY(upload());
-    k_post<<<(nch_ + 63) / 64, 64, 0, st_>>>(d_y, n, nch_, stride_, uni_, d_par_, d_taps_, d_mode_, d_reset_, d_state_,
-                                             d_istate_, d_agc_delay_, d_agc_mag_, d_v_, d_audio, audio_stride, audio_off,
-                                             d_chan_map, d_tap3);
-    lc_->n++;
+    PostBufs b;
+    b.y = d_y_; b.y_row = y_row_; b.magh = d_magh_; b.smag = d_smag_; b.peak = d_peak_; b.z = d_z_; b.u = d_u_; b.th = d_th_;
+    b.row = max_n_; b.v = d_v_; b.v_row = v_row_; b.par = d_par_; b.taps = d_taps_; b.mode = d_mode_; b.reset = d_reset_;
+    b.state = d_state_; b.istate = d_istate_; b.nch = nch_; b.stride = stride_;
+    if (need_reset_kernel_) {
+        k_post_reset<<<nch_, 128, 0, st_>>>(b);
+        lc_->n++;
+        need_reset_kernel_ = false;
+    }
+    const size_t smem_pre = 2 * (size_t)(kAgcBuf + max_n_) * sizeof(double);
+    const size_t smem_fir = (size_t)(kHist + max_n_ + kFirMax) * sizeof(double);
+    const int seq_blocks = (nch_ + 31) / 32;
+    k_post_pre<<<nch_, 256, smem_pre, st_>>>(b, n, uni_.agc_window);
+    k_post_seq1<<<seq_blocks, 32, 0, st_>>>(b, n, uni_);
+    k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, d_audio, audio_stride, audio_off, d_chan_map);
+    k_post_seq2<<<seq_blocks, 32, 0, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
+    k_post_fir<<<nch_, 256, smem_fir, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
+    lc_->n += 5;
     CSDR_CK(cudaGetLastError());
     return CUTESDR_OK;
 }

@@ -11,6 +11,8 @@ namespace csdr {
 int design_kaiser_lp(double scale, double astop, double fpass, double fstop, double fs, double* coef);
 int design_kaiser_hp(double scale, double astop, double fpass, double fstop, double fs, double* coef);
 
+constexpr int kYHist = 2048;          // >= MAX_DELAY_BUF-1 samples of AGC signal delay
+
 enum PostMode { POST_NONE = -1, POST_AM = 0, POST_SAM = 1, POST_FM = 2, POST_SSB = 3, POST_AGC_ONLY = 100 };
 
 // values shared by every channel of a group (they depend on the sample rate only)
@@ -40,11 +42,16 @@ public:
     // CFmDemod::SetSquelch and the FmBW handed to ProcessData (m_DemodInfo.HiCut)
     void set_fm(int i, int squelch_value, double fm_bw);
 
-    // Run n samples (a burst is 1024). d_y: FIR output [t][stride] complex64. d_audio (float32) is
-    // indexed [chan_map[c]][audio_stride] + audio_off; d_tap3 (optional) receives the post-AGC
-    // complex stream [t][stride].
-    int run(const float2* d_y, int n, float* d_audio, int audio_stride, int audio_off, const int* d_chan_map,
-            float2* d_tap3);
+    // The FIR (or the caller) writes the burst's complex64 samples for channel c at
+    //   y_in() + c * y_stride()   (contiguous in time).
+    float2* y_in() { return d_y_ + kYHist; }
+    int y_stride() const { return y_row_; }
+    // Run n samples (a burst is 1024) already placed at y_in(). d_audio (float32) is indexed
+    // [chan_map[c]][audio_stride] + audio_off. tap3() then holds the post-AGC complex stream
+    // [c][tap3_stride()].
+    int run(int n, float* d_audio, int audio_stride, int audio_off, const int* d_chan_map);
+    const float2* tap3() const { return d_z_; }
+    int tap3_stride() const { return max_n_; }
     // S-meter readout for local channel i (synchronises the stream)
     int read_smeter(int i, double* peak, double* ave);
     double rate() const { return rate_; }
@@ -60,18 +67,25 @@ private:
     std::vector<AgcHost> agc_;
     std::vector<double> fm_bw_;
     std::vector<double> h_par_;     // [P_COUNT][stride]
-    std::vector<double> h_taps_;    // [kFirMax][stride]
+    std::vector<double> h_taps_;    // [stride][kFirMax]
     std::vector<int> h_mode_, h_reset_;
-    bool dirty_ = true;
+    bool dirty_ = true, need_reset_kernel_ = false;
     double* d_par_ = nullptr;
     double* d_taps_ = nullptr;
     int* d_mode_ = nullptr;
     int* d_reset_ = nullptr;
     double* d_state_ = nullptr;     // [S_COUNT][stride]
     int* d_istate_ = nullptr;       // [I_COUNT][stride]
-    float2* d_agc_delay_ = nullptr; // [kAgcBuf][stride]
-    double* d_agc_mag_ = nullptr;   // [kAgcBuf][stride]
-    double* d_v_ = nullptr;         // [(kFirMax-1)+max_n][stride] FIR work/history
+    // channel-major work rows (row c = channel c)
+    float2* d_y_ = nullptr;         // [nch][kYHist + max_n]   FIR output with the AGC delay history in front
+    double* d_magh_ = nullptr;      // [nch][kAgcBuf]          last window-1 AGC log-magnitudes
+    double* d_smag_ = nullptr;      // [nch][max_n]            S-meter dB values
+    double* d_peak_ = nullptr;      // [nch][max_n]            sliding-window peak, then max(attack,decay)
+    float2* d_z_ = nullptr;         // [nch][max_n]            AGC output (PROFILE_3 tap)
+    double* d_u_ = nullptr;         // [nch][max_n]            envelope (AM/SAM)
+    double* d_th_ = nullptr;        // [nch][max_n]            phase angle (SAM/FM)
+    double* d_v_ = nullptr;         // [nch][kHist + max_n]    FIR input with history (AM post filter / FM squelch)
+    int y_row_ = 0, v_row_ = 0;
 };
 
 }  // namespace csdr
