@@ -259,6 +259,7 @@ def run_ours(args):
         ev0.record(stream)
         for i in range(args.steps):
             produced += step_device(args.warmup + i)
+        bank.join()             # main stream waits for the burst side streams: ev1 covers all work
         ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -20,9 +20,13 @@ void set_error(const char* fmt, ...)
 
 Group::~Group()
 {
+    if (st_post) { cudaStreamSynchronize(st_post); }
+    if (ev_dec) cudaEventDestroy(ev_dec);
+    for (auto& e : ev_post) if (e) cudaEventDestroy(e);
     cudaFree(d_demod);
     cudaFree(d_chan_map);
     cudaFree(d_local_map);
+    if (st_post) cudaStreamDestroy(st_post);
 }
 
 static int block_limit(double in_rate, double out_rate)
@@ -43,6 +47,7 @@ cutesdr_bank::~cutesdr_bank()
     groups.clear();
     nb.reset();
     cudaFree(d_x);
+    cudaFree(d_halo_tmp);
     cudaFree(d_audio);
     if (h_stage) cudaFreeHost(h_stage);
     if (st) cudaStreamDestroy(st);
@@ -90,22 +95,27 @@ int cutesdr_bank::rebuild()
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr;
         CSDR_CK(cudaMalloc(&d_x, (size_t)(kHaloMax + L) * sizeof(float2)));
+        if (!d_halo_tmp) CSDR_CK(cudaMalloc(&d_halo_tmp, (size_t)kHaloMax * sizeof(float2)));
         CSDR_CK(cudaHostAlloc(&h_stage, (size_t)L * sizeof(float2), cudaHostAllocDefault));
         h_fill = 0;
     }
     // a rebuild re-creates every DSP object: the stream restarts from zero state
     CSDR_CK(cudaMemsetAsync(d_x, 0, (size_t)(kHaloMax + L) * sizeof(float2), st));
     stream_pos = 0;
+    block_index = 0;
     for (auto& kv : by_bw) {
         std::unique_ptr<Group> g(new Group());
         g->max_bw = kv.first;
         g->chans = kv.second;
         std::stable_sort(g->chans.begin(), g->chans.end(), [&](int a, int c2) { return ch[a].mode < ch[c2].mode; });
         const int n = (int)g->chans.size();
+        CSDR_CK(cudaStreamCreateWithFlags(&g->st_post, cudaStreamNonBlocking));
+        CSDR_CK(cudaEventCreateWithFlags(&g->ev_dec, cudaEventDisableTiming));
+        for (auto& e : g->ev_post) CSDR_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CSDR_TRY(g->dec.init(n, in_rate, g->max_bw, L, st, &lc));
         const int stride = g->dec.stride();
-        CSDR_TRY(g->fir.init(n, stride, st, &lc));
-        CSDR_TRY(g->post.init(n, stride, g->dec.out_rate(), kMaxBurstSamples, st, &lc));
+        CSDR_TRY(g->fir.init(n, stride, g->st_post, &lc));
+        CSDR_TRY(g->post.init(n, stride, g->dec.out_rate(), kMaxBurstSamples, g->st_post, &lc));
         CSDR_CK(cudaMalloc(&g->d_chan_map, stride * sizeof(int)));
         CSDR_CK(cudaMalloc(&g->d_local_map, stride * sizeof(int)));
         std::vector<int> map(stride, 0), ident(stride, 0);
@@ -114,7 +124,7 @@ int cutesdr_bank::rebuild()
         CSDR_CK(cudaMemcpy(g->d_local_map, ident.data(), stride * sizeof(int), cudaMemcpyHostToDevice));
         if (audio_rate > 0.0) {
             g->rs.reset(new ResamplerBank());
-            CSDR_TRY(g->rs->init(n, kMaxBurstSamples, st, &lc));
+            CSDR_TRY(g->rs->init(n, kMaxBurstSamples, g->st_post, &lc));
         }
         const int gi = (int)groups.size();
         for (int i = 0; i < n; i++) { ch[g->chans[i]].group = gi; ch[g->chans[i]].local = i; }
@@ -140,6 +150,15 @@ int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_strid
     std::fill(blk_nout.begin(), blk_nout.end(), 0);
     for (size_t gi = 0; gi < groups.size(); gi++) {
         Group& g = *groups[gi];
+        // The decimator may run ahead of the burst chain by two blocks, not more: the FIR window of
+        // a burst must not be overwritten in the 4096-sample ring (3 blocks of <= 1200 samples fit
+        // in the 2048 samples of slack).
+        for (size_t k = 0; k < g.pending.size();) {
+            if (g.pending[k].block <= block_index - 2) {
+                CSDR_CK(cudaStreamWaitEvent(st, g.pending[k].ev, 0));
+                g.pending.erase(g.pending.begin() + k);
+            } else k++;
+        }
         CSDR_TRY(g.dec.run_block(d_block));
         const long long total = g.dec.total_out();
         const int nbursts = (int)(total / kBurst - g.bursts_done);
@@ -147,6 +166,8 @@ int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_strid
         if (nbursts <= 0) continue;
         const int n = nbursts * kBurst;
         if (n > kMaxBurstSamples) { set_error("more than %d FIR bursts in one DSP block", kMaxBurstSamples / kBurst); return CUTESDR_E_STATE; }
+        CSDR_CK(cudaEventRecord(g.ev_dec, st));
+        CSDR_CK(cudaStreamWaitEvent(g.st_post, g.ev_dec, 0));
         CSDR_TRY(g.fir.run(g.dec.ring(), g.bursts_done, nbursts, g.post.y_in(), g.post.y_stride()));
         g.bursts_done += nbursts;
         g.last_fir_n = n;
@@ -168,13 +189,35 @@ int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_strid
             }
             CSDR_TRY(g.post.run(n, d_audio_out, audio_stride, off, g.d_chan_map));
         }
+        cudaEvent_t done = g.ev_post[g.post_launches++ & 7];
+        CSDR_CK(cudaEventRecord(done, g.st_post));
+        g.pending.push_back({done, block_index});
         for (int c : g.chans) blk_nout[c] = produced;
         nmax = std::max(nmax, produced);
     }
-    // keep the tail of this block in front of the next one (CIC halo of kernel 1)
-    CSDR_CK(cudaMemcpyAsync(d_block - kHaloMax, d_block + (L - kHaloMax), kHaloMax * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    // keep the tail of this block in front of the next one (halo of kernel 1): the last kHaloMax
+    // samples of [old halo | block], staged through a scratch buffer because the ranges may overlap
+    CSDR_CK(cudaMemcpyAsync(d_halo_tmp, d_block + (L - kHaloMax), kHaloMax * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    CSDR_CK(cudaMemcpyAsync(d_block - kHaloMax, d_halo_tmp, kHaloMax * sizeof(float2), cudaMemcpyDeviceToDevice, st));
     stream_pos += L;
+    block_index++;
     if (n_out_max) *n_out_max = nmax;
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank::join()
+{
+    for (auto& g : groups) {
+        for (auto& p : g->pending) CSDR_CK(cudaStreamWaitEvent(st, p.ev, 0));
+        g->pending.clear();
+    }
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank::sync_all()
+{
+    CSDR_TRY(join());
+    CSDR_CK(cudaStreamSynchronize(st));
     return CUTESDR_OK;
 }
 
@@ -184,7 +227,7 @@ int cutesdr_bank::collect_taps()
     bool any = false;
     for (auto& g : groups) any |= g->any_tap;
     if (!any) return CUTESDR_OK;
-    CSDR_CK(cudaStreamSynchronize(st));
+    CSDR_TRY(sync_all());
     for (auto& gp : groups) {
         Group& g = *gp;
         if (!g.any_tap) continue;
@@ -413,6 +456,7 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
             if (produced > 0 && audio) {
                 // PROFILE_4 tap = the audio rows themselves
                 for (int c : g.chans) if (b->ch[c].tap_mask & 16u) {
+                    CSDR_TRY(b->sync_all());
                     std::vector<float> tmp(produced);
                     CSDR_CK(cudaMemcpyAsync(tmp.data(), b->d_audio + (size_t)c * b->audio_cap + goff[gi], produced * sizeof(float), cudaMemcpyDeviceToHost, b->st));
                     CSDR_CK(cudaStreamSynchronize(b->st));
@@ -427,6 +471,7 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
         // the staging buffer (or the caller's memory) must not change until the copy is done
         CSDR_CK(cudaStreamSynchronize(b->st));
     }
+    CSDR_TRY(b->join());
     if (audio && nmax > 0) {
         CSDR_CK(cudaMemcpy2DAsync(audio, (size_t)audio_stride * sizeof(float), b->d_audio, (size_t)b->audio_cap * sizeof(float),
                                   (size_t)nmax * sizeof(float), b->nch, cudaMemcpyDeviceToHost, b->st));
@@ -454,8 +499,17 @@ int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, voi
 int cutesdr_bank_synchronize(cutesdr_bank* b)
 {
     if (!b) { set_error("synchronize: bad handle"); return CUTESDR_E_ARG; }
-    CSDR_CK(cudaStreamSynchronize(b->st));
-    return CUTESDR_OK;
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    return b->sync_all();
+}
+
+int cutesdr_bank_join(cutesdr_bank* b)
+{
+    if (!b) { set_error("join: bad handle"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    return b->join();
 }
 
 int cutesdr_bank_stream(cutesdr_bank* b, void** stream)

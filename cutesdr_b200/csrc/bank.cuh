@@ -37,6 +37,14 @@ struct Group {
     int* d_local_map = nullptr;          // identity map (for resampler input rows)
     long long bursts_done = 0;
     int last_fir_n = 0;                  // FIR samples produced by the last block
+    // The burst stages (FIR, AGC/demod, resampler) run on their own stream so the small sequential
+    // kernels overlap the next blocks' decimation instead of idling the GPU.
+    cudaStream_t st_post = 0;
+    cudaEvent_t ev_dec = nullptr;        // decimator output of the current block is in the ring
+    cudaEvent_t ev_post[8] = {};         // completion of recent burst chains (round robin)
+    long long post_launches = 0;
+    struct Pending { cudaEvent_t ev; long long block; };
+    std::vector<Pending> pending;        // burst chains the main stream has not been ordered after yet
     bool any_tap = false;
     ~Group();
 };
@@ -57,9 +65,11 @@ struct cutesdr_bank {
     bool layout_dirty = true;
     int L = 0;                           // m_InBufLimit
     float2* d_x = nullptr;               // [kHaloMax | L]
+    float2* d_halo_tmp = nullptr;        // [kHaloMax]
     float2* h_stage = nullptr;           // pinned staging of one block
     int h_fill = 0;
     long long stream_pos = 0;
+    long long block_index = 0;
     float* d_audio = nullptr;            // [nch][audio_cap]
     int audio_cap = 0;
     double audio_rate = 0.0;             // > 0: CFractResampler to this rate
@@ -71,5 +81,7 @@ struct cutesdr_bank {
     int rebuild();
     int run_block(float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);
     int collect_taps();
+    int join();                          // order the main stream after every outstanding burst chain
+    int sync_all();
     ~cutesdr_bank();
 };

@@ -90,22 +90,68 @@ __device__ __forceinline__ float2 seed_osc(unsigned long long ph)
     return make_float2(c, s);
 }
 
-struct CicSt { float2 xodd, xeven; };
+constexpr int kFuseHb = 1;
 
-template <int NCIC> struct K1Cfg {
-    static constexpr int G = 1 << NCIC;                    // input samples per final CIC output
+static int k1_body(int ncic) { int g = 1 << ncic; return g < 32 ? 32 : g; }
+static int k1_halo(int ncic, int nhb)
+{
+    const int g = 1 << ncic, b = k1_body(ncic);
+    const int need = (ncic == 0 ? 0 : (2 << ncic)) + 10 * g * ((1 << nhb) - 1);
+    const int q = std::max(g << nhb, b);
+    return (need + q - 1) / q * q;
+}
+
+struct CicSt { float2 xodd, xeven; };
+struct Hb11St { float2 e[5]; float2 o[3]; };     // e[0] = most recent even-indexed input, o[0] = most recent odd
+
+// NCIC CIC3 stages followed by NHB fused 11-tap half-bands
+template <int NCIC, int NHB> struct K1Cfg {
+    static constexpr int G = 1 << NCIC;                    // input samples per CIC-chain output
     static constexpr int B = G < 32 ? 32 : G;              // unrolled body length
-    static constexpr int H = NCIC == 0 ? 0 : (NCIC <= 4 ? 32 : (2 << NCIC));   // halo >= 2^(ncic+1)-2
+    static constexpr int Hcic = NCIC == 0 ? 0 : (2 << NCIC);                  // >= 2^(ncic+1)-2 samples re-prime the CICs
+    static constexpr int Hneed = Hcic + 10 * G * ((1 << NHB) - 1);            // + 10 inputs of history per half-band
+    static constexpr int Q = (G << NHB) > B ? (G << NHB) : B;                 // tiles start on output boundaries
+    static constexpr int H = (Hneed + Q - 1) / Q * Q;
 };
+
+struct EmitCtx {
+    OutDesc od;
+    long long row_lo;     // first output row this tile owns (rows before it belong to the halo)
+    int c;
+    float scale;
+    float h0, h2, h4;     // HB11 taps 0/2/4 (= 10/8/6); centre tap is 0.5
+};
+
+// 11-tap half-band decimate-by-2 in direct form on a register delay line
+// (y[m] = sum_j h[j] x[2m-10+j], dsp/downconvert.cpp:348-423): an output is complete when the
+// even-indexed input x[2m] arrives; odd-indexed inputs only feed the centre tap three outputs later.
+// q = block-relative index of v at this stage (may be negative inside the halo).
+template <int NHB, int J>
+__device__ __forceinline__ void hb_feed(float2 v, long long q, Hb11St* hs, const EmitCtx& em)
+{
+    if constexpr (J == NHB) {
+        if (q >= em.row_lo) store_out(em.od, q, em.c, make_float2(v.x * em.scale, v.y * em.scale));
+    } else {
+        Hb11St& s = hs[J];
+        if ((q & 1) == 0) {
+            float2 y;
+            y.x = fmaf(em.h0, s.e[4].x + v.x, fmaf(em.h2, s.e[3].x + s.e[0].x, fmaf(em.h4, s.e[2].x + s.e[1].x, 0.5f * s.o[2].x)));
+            y.y = fmaf(em.h0, s.e[4].y + v.y, fmaf(em.h2, s.e[3].y + s.e[0].y, fmaf(em.h4, s.e[2].y + s.e[1].y, 0.5f * s.o[2].y)));
+            s.e[4] = s.e[3]; s.e[3] = s.e[2]; s.e[2] = s.e[1]; s.e[1] = s.e[0]; s.e[0] = v;
+            hb_feed<NHB, J + 1>(y, q >> 1, hs, em);
+        } else {
+            s.o[2] = s.o[1]; s.o[1] = s.o[0]; s.o[0] = v;
+        }
+    }
+}
 
 // CIC3 decimate-by-2, scale .125 folded into the kernel's output scale
 // (y = odd + Xeven + 3*(Xodd + even), dsp/downconvert.cpp:450-455).
-template <int NCIC, int S, int IDX>
-__device__ __forceinline__ void cic_feed(float2 v, CicSt* st, float2* ev, bool emit, const OutDesc& od,
-                                         long long row0, int c, float scale)
+template <int NCIC, int NHB, int S, int IDX>
+__device__ __forceinline__ void cic_feed(float2 v, CicSt* st, float2* ev, Hb11St* hs, long long q0, const EmitCtx& em)
 {
     if constexpr (S == NCIC) {
-        if (emit) store_out(od, row0 + IDX, c, make_float2(v.x * scale, v.y * scale));
+        hb_feed<NHB, 0>(v, q0 + IDX, hs, em);
     } else if constexpr ((IDX & 1) == 0) {
         ev[S] = v;
     } else {
@@ -114,37 +160,38 @@ __device__ __forceinline__ void cic_feed(float2 v, CicSt* st, float2* ev, bool e
         r.y = (v.y + st[S].xeven.y) + 3.0f * (st[S].xodd.y + e.y);
         st[S].xodd = v;
         st[S].xeven = e;
-        cic_feed<NCIC, S + 1, (IDX >> 1)>(r, st, ev, emit, od, row0, c, scale);
+        cic_feed<NCIC, NHB, S + 1, (IDX >> 1)>(r, st, ev, hs, q0, em);
     }
 }
 
-template <int NCIC, int K, int B> struct Body {
-    static __device__ __forceinline__ void run(const float2* t, float2& o, float2 w, CicSt* st, float2* ev,
-                                               bool emit, const OutDesc& od, long long row0, int c, float scale)
+template <int NCIC, int NHB, int K, int B> struct Body {
+    static __device__ __forceinline__ void run(const float2* t, float2& o, float2 w, CicSt* st, float2* ev, Hb11St* hs,
+                                               long long q0, const EmitCtx& em)
     {
         float2 xv = t[K];                 // all lanes read the same address: broadcast LDS
         float2 y = cmul(xv, o);           // mixer, dsp/downconvert.cpp:238-239
         if (K + 1 < B) o = cmul(o, w);    // oscillator step, :211-212
-        cic_feed<NCIC, 0, K>(y, st, ev, emit, od, row0, c, scale);
-        Body<NCIC, K + 1, B>::run(t, o, w, st, ev, emit, od, row0, c, scale);
+        cic_feed<NCIC, NHB, 0, K>(y, st, ev, hs, q0, em);
+        Body<NCIC, NHB, K + 1, B>::run(t, o, w, st, ev, hs, q0, em);
     }
 };
-template <int NCIC, int B> struct Body<NCIC, B, B> {
-    static __device__ __forceinline__ void run(const float2*, float2&, float2, CicSt*, float2*, bool,
-                                               const OutDesc&, long long, int, float) {}
+template <int NCIC, int NHB, int B> struct Body<NCIC, NHB, B, B> {
+    static __device__ __forceinline__ void run(const float2*, float2&, float2, CicSt*, float2*, Hb11St*, long long,
+                                               const EmitCtx&) {}
 };
 
 // ------------------------------------------------------------------------------------------
-// K1: fused NCO mix + NCIC x CIC3
+// K1: fused NCO mix + NCIC x CIC3 + NHB x HB11
 // ------------------------------------------------------------------------------------------
-template <int NCIC>
+template <int NCIC, int NHB>
 __global__ void __launch_bounds__(256) k_mix_cic(const float2* __restrict__ x, int L, int tile_len,
                                                  const NcoDev* __restrict__ nco,
                                                  const unsigned long long* __restrict__ phase_cur,
                                                  unsigned long long* __restrict__ phase_next, int nch,
                                                  OutDesc od, float scale)
 {
-    constexpr int G = K1Cfg<NCIC>::G, B = K1Cfg<NCIC>::B, H = K1Cfg<NCIC>::H;
+    typedef K1Cfg<NCIC, NHB> Cfg;
+    constexpr int G = Cfg::G, B = Cfg::B, H = Cfg::H;
     extern __shared__ float4 smem4[];
     const int t0 = blockIdx.x * tile_len;
     const int n_tile = min(tile_len, L - t0);
@@ -167,44 +214,68 @@ __global__ void __launch_bounds__(256) k_mix_cic(const float2* __restrict__ x, i
 
     CicSt st[NCIC > 0 ? NCIC : 1];
     float2 ev[NCIC > 0 ? NCIC : 1];
+    Hb11St hs[NHB > 0 ? NHB : 1];
 #pragma unroll
     for (int s = 0; s < (NCIC > 0 ? NCIC : 1); s++) {
         st[s].xodd = make_float2(0.f, 0.f);
         st[s].xeven = make_float2(0.f, 0.f);
         ev[s] = make_float2(0.f, 0.f);
     }
+#pragma unroll
+    for (int s = 0; s < (NHB > 0 ? NHB : 1); s++) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) hs[s].e[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 3; k++) hs[s].o[k] = make_float2(0.f, 0.f);
+    }
+    EmitCtx em;
+    em.od = od;
+    em.row_lo = (long long)(t0 / (G << NHB));
+    em.c = c;
+    em.scale = scale;
+    em.h0 = c_hb_taps[0]; em.h2 = c_hb_taps[1]; em.h4 = c_hb_taps[2];
+
     const float2* tile = reinterpret_cast<const float2*>(smem4);
     const int nbody = n_load / B;
     float2 S = make_float2(1.f, 0.f);
+    long long q0 = (long long)((t0 - H) / G);          // index of the body's first CIC-chain output (exact: G | t0-H)
     for (int b = 0; b < nbody; b++) {
-        if ((b & 7) == 0) S = seed_osc(ph);        // exact re-seed: bounds recursion drift
+        if ((b & 7) == 0) S = seed_osc(ph);            // exact re-seed: bounds recursion drift
         float2 o = S;
-        const bool emit = b >= (H / B);
-        const long long row0 = (long long)(t0 / G) + (long long)(b - H / B) * (B / G);
-        Body<NCIC, 0, B>::run(tile + b * B, o, w1, st, ev, emit, od, row0, c, scale);
+        Body<NCIC, NHB, 0, B>::run(tile + b * B, o, w1, st, ev, hs, q0, em);
         S = cmul(S, wg);
         ph += ph_step;
+        q0 += B / G;
     }
 }
 
-// Slow generic path for block lengths that are not a multiple of 32 (single-object API with odd
-// sizes). Same math, run-time stage count, one tile.
-__global__ void k_mix_cic_generic(const float2* __restrict__ x, int L, int ncic, const NcoDev* __restrict__ nco,
+// Slow generic path for block lengths that are not a multiple of the unrolled body (single-object
+// API with odd sizes). Same math, run-time stage counts, one tile.
+__global__ void k_mix_cic_generic(const float2* __restrict__ x, int L, int ncic, int nhb, const NcoDev* __restrict__ nco,
                                   const unsigned long long* __restrict__ phase_cur,
                                   unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nch) return;
-    const int H = ncic == 0 ? 0 : (2 << ncic);
+    const int G = 1 << ncic;
+    const int q_align = G << nhb;
+    int H = (ncic == 0 ? 0 : (2 << ncic)) + 10 * G * ((1 << nhb) - 1);
+    H = (H + q_align - 1) / q_align * q_align;
     const NcoDev p = nco[c];
     const unsigned long long ph0 = phase_cur[c];
     phase_next[c] = ph0 + (unsigned long long)L * p.inc;
     const float2 w1 = make_float2(p.w1c, p.w1s);
+    const float h0 = c_hb_taps[0], h2 = c_hb_taps[1], h4 = c_hb_taps[2];
     float2 xo[8], xe[8], ev[8];
     int par[8];
+    Hb11St hs[2];
     for (int s = 0; s < 8; s++) { xo[s] = xe[s] = ev[s] = make_float2(0.f, 0.f); par[s] = 0; }
+    for (int s = 0; s < 2; s++) {
+        for (int k = 0; k < 5; k++) hs[s].e[k] = make_float2(0.f, 0.f);
+        for (int k = 0; k < 3; k++) hs[s].o[k] = make_float2(0.f, 0.f);
+    }
     float2 o = make_float2(1.f, 0.f);
-    long long row = -(long long)(H >> ncic);
+    long long q = -(long long)(H >> ncic);
     for (int i = -H; i < L; i++) {
         if (((i + H) & 31) == 0) o = seed_osc(ph0 + (unsigned long long)(long long)(i + 1) * p.inc);
         float2 v = cmul(x[i], o);
@@ -219,10 +290,20 @@ __global__ void k_mix_cic_generic(const float2* __restrict__ x, int L, int ncic,
             v = r;
             s++;
         }
-        if (s == ncic) {
-            if (row >= 0) store_out(od, row, c, make_float2(v.x * scale, v.y * scale));
-            row++;
+        if (s < ncic) continue;
+        long long qq = q++;
+        int j = 0;
+        for (; j < nhb; j++) {
+            Hb11St& hh = hs[j];
+            if (qq & 1) { hh.o[2] = hh.o[1]; hh.o[1] = hh.o[0]; hh.o[0] = v; break; }
+            float2 y;
+            y.x = fmaf(h0, hh.e[4].x + v.x, fmaf(h2, hh.e[3].x + hh.e[0].x, fmaf(h4, hh.e[2].x + hh.e[1].x, 0.5f * hh.o[2].x)));
+            y.y = fmaf(h0, hh.e[4].y + v.y, fmaf(h2, hh.e[3].y + hh.e[0].y, fmaf(h4, hh.e[2].y + hh.e[1].y, 0.5f * hh.o[2].y)));
+            hh.e[4] = hh.e[3]; hh.e[3] = hh.e[2]; hh.e[2] = hh.e[1]; hh.e[1] = hh.e[0]; hh.e[0] = v;
+            v = y;
+            qq >>= 1;
         }
+        if (j == nhb && qq >= 0) store_out(od, qq, c, make_float2(v.x * scale, v.y * scale));
     }
 }
 
@@ -350,6 +431,9 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     }
     ncic_ = 0;
     while (ncic_ < (int)lens_.size() && lens_[ncic_] == 3 && ncic_ < 6) ncic_++;
+    // up to kFuseHb 11-tap half-bands that follow the CICs run inside kernel 1 as well
+    nhbf_ = 0;
+    while (nhbf_ < kFuseHb && ncic_ + nhbf_ < (int)lens_.size() && lens_[ncic_ + nhbf_] == 11) nhbf_++;
     n_out_ = block_len >> lens_.size();
     if (n_out_ > kDecRing - kFirFft) { set_error("decimated block of %d samples exceeds the FIR ring", n_out_); return CUTESDR_E_ARG; }
     CSDR_TRY(upload_taps());
@@ -360,9 +444,9 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
         CSDR_CK(cudaMalloc(&d_phase_[k], stride_ * sizeof(unsigned long long)));
         CSDR_CK(cudaMemsetAsync(d_phase_[k], 0, stride_ * sizeof(unsigned long long), st_));
     }
-    const int nhb = (int)lens_.size() - ncic_;
+    const int nhb = (int)lens_.size() - k1_stages();
     for (int s = 0; s < nhb; s++) {
-        int n_rows = block_len >> (ncic_ + s);             // rows this ring receives per block
+        int n_rows = block_len >> (k1_stages() + s);       // rows this ring receives per block
         int rows = next_pow2((long long)n_rows + 64);
         float2* p = nullptr;
         size_t bytes = (size_t)rows * stride_ * sizeof(float2);
@@ -376,17 +460,19 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     CSDR_CK(cudaMalloc(&d_ring_, rbytes));
     CSDR_CK(cudaMemsetAsync(d_ring_, 0, rbytes, st_));
 
-    // time tile: enough CTAs to fill 148 SMs several times over, tile >= 16 halos
-    constexpr int Bs[7] = {32, 32, 32, 32, 32, 32, 64};
-    const int B = Bs[ncic_];
+    // time tile: enough CTAs to fill 148 SMs several times over, tile >= ~16 halos
+    const int B = k1_body(ncic_);
+    const int Q = std::max((1 << ncic_) << nhbf_, B);
+    const int H = k1_halo(ncic_, nhbf_);
+    if (H > kHaloMax) { set_error("kernel-1 halo %d exceeds kHaloMax", H); return CUTESDR_E_ARG; }
     const int cta_threads = std::min(256, round_up(stride_, 32));
     const int chan_blocks = (stride_ + cta_threads - 1) / cta_threads;
     int tiles_target = (148 * 8 + chan_blocks - 1) / chan_blocks;
     int tl = block_len / std::max(1, tiles_target);
-    tl = std::max(tl, 512);
+    tl = std::max(tl, std::max(512, 16 * H));
     tl = std::min(tl, 4096);
-    tl = tl / B * B;
-    tile_len_ = std::max(tl, B);
+    tl = tl / Q * Q;
+    tile_len_ = std::max(tl, Q);
     dirty_ = true;
     return CUTESDR_OK;
 }
@@ -398,8 +484,7 @@ void Decimator::set_frequency(int i, double nco_freq)
     long double turns = (long double)nco_freq / (long double)in_rate_;
     turns -= floorl(turns);
     unsigned long long inc = (unsigned long long)(turns * 18446744073709551616.0L);
-    constexpr int Bs[7] = {32, 32, 32, 32, 32, 32, 64};
-    const int B = Bs[ncic_];
+    const int B = k1_body(ncic_);
     const double a1 = kTwoPi * (double)((long double)inc / 18446744073709551616.0L);
     const unsigned long long incB = inc * (unsigned long long)B;
     const double aB = kTwoPi * (double)((long double)incB / 18446744073709551616.0L);
@@ -420,12 +505,28 @@ int Decimator::upload_dirty()
     return CUTESDR_OK;
 }
 
-template <int NCIC>
+template <int NCIC, int NHB>
 static void launch_k1(dim3 grid, int threads, size_t smem, cudaStream_t st, const float2* x, int L, int tile_len,
                       const NcoDev* nco, const unsigned long long* pc, unsigned long long* pn, int nch, OutDesc od,
                       float scale)
 {
-    k_mix_cic<NCIC><<<grid, threads, smem, st>>>(x, L, tile_len, nco, pc, pn, nch, od, scale);
+    k_mix_cic<NCIC, NHB><<<grid, threads, smem, st>>>(x, L, tile_len, nco, pc, pn, nch, od, scale);
+}
+
+template <int NHB>
+static void launch_k1_n(int ncic, dim3 grid, int threads, size_t smem, cudaStream_t st, const float2* x, int L, int tile_len,
+                        const NcoDev* nco, const unsigned long long* pc, unsigned long long* pn, int nch, OutDesc od,
+                        float scale)
+{
+    switch (ncic) {
+    case 0: launch_k1<0, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
+    case 1: launch_k1<1, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
+    case 2: launch_k1<2, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
+    case 3: launch_k1<3, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
+    case 4: launch_k1<4, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
+    case 5: launch_k1<5, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
+    default: launch_k1<6, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
+    }
 }
 
 int Decimator::run_block(const float2* d_x, int L)
@@ -437,7 +538,7 @@ int Decimator::run_block(const float2* d_x, int L)
         set_error("Decimator::run_block: length %d (capacity %d, must be a multiple of %d)", L, block_len_, 1 << lens_.size());
         return CUTESDR_E_ARG;
     }
-    const int nhb = (int)lens_.size() - ncic_;
+    const int nhb = (int)lens_.size() - k1_stages();
     OutDesc od;
     if (nhb > 0) {
         od.p = d_stage_[0];
@@ -469,22 +570,16 @@ int Decimator::run_block(const float2* d_x, int L)
         ev_used_++;
         CSDR_CK(cudaEventRecord(ev_a, st_));
     }
-    if (L % 32 == 0 && (ncic_ < 6 || L % 64 == 0)) {
+    const int Q = std::max((1 << ncic_) << nhbf_, k1_body(ncic_));
+    if (L % Q == 0) {
         const int threads = std::min(256, round_up(stride_, 32));
         dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);
-        const int H = ncic_ == 0 ? 0 : (ncic_ <= 4 ? 32 : (2 << ncic_));
+        const int H = k1_halo(ncic_, nhbf_);
         size_t smem = (size_t)(tile_len_ + H) * sizeof(float2);
-        switch (ncic_) {
-        case 0: launch_k1<0>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
-        case 1: launch_k1<1>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
-        case 2: launch_k1<2>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
-        case 3: launch_k1<3>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
-        case 4: launch_k1<4>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
-        case 5: launch_k1<5>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
-        default: launch_k1<6>(grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale); break;
-        }
+        if (nhbf_ == 0) launch_k1_n<0>(ncic_, grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale);
+        else launch_k1_n<1>(ncic_, grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale);
     } else {
-        k_mix_cic_generic<<<(stride_ + 63) / 64, 64, 0, st_>>>(d_x, L, ncic_, d_nco_, pc, pn, stride_, od, scale);
+        k_mix_cic_generic<<<(stride_ + 63) / 64, 64, 0, st_>>>(d_x, L, ncic_, nhbf_, d_nco_, pc, pn, stride_, od, scale);
     }
     lc_->n++;
     CSDR_CK(cudaGetLastError());
@@ -492,8 +587,8 @@ int Decimator::run_block(const float2* d_x, int L)
     phase_cur_ ^= 1;
 
     for (int s = 0; s < nhb; s++) {
-        const int N = lens_[ncic_ + s];
-        const int n_in = L >> (ncic_ + s);
+        const int N = lens_[k1_stages() + s];
+        const int n_in = L >> (k1_stages() + s);
         const int n_out = n_in >> 1;
         OutDesc o2;
         if (s + 1 < nhb) {

@@ -56,7 +56,8 @@ public:
 
 private:
     int upload_dirty();
-    int nch_ = 0, stride_ = 0, block_len_ = 0, ncic_ = 0, n_out_ = 0, tile_len_ = 0;
+    int nch_ = 0, stride_ = 0, block_len_ = 0, ncic_ = 0, nhbf_ = 0, n_out_ = 0, tile_len_ = 0;
+    int k1_stages() const { return ncic_ + nhbf_; }     // stages fused into kernel 1
     double in_rate_ = 0, out_rate_ = 0;
     std::vector<int> lens_;
     cudaStream_t st_ = 0;

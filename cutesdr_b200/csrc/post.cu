@@ -178,50 +178,90 @@ __global__ void __launch_bounds__(256) k_post_pre(PostBufs b, int n, int window)
     }
 }
 
-// ---- sequential poles; thread per channel
-__global__ void __launch_bounds__(32) k_post_seq1(PostBufs b, int n, PostUniform u)
+// Row access for the sequential kernels: every lane walks its own channel row, so a plain
+// `row[t]` load per step would expose the full memory latency 1024 times. Rows are read in
+// 16-sample chunks (one 128-byte line per lane) with the next chunk in flight while the current
+// one is consumed from registers.
+__device__ __forceinline__ void load16(const double* __restrict__ p, double* v)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const double2 d = q[i]; v[2 * i] = d.x; v[2 * i + 1] = d.y; }
+}
+__device__ __forceinline__ void store16(double* __restrict__ p, const double* v)
+{
+    double2* q = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = make_double2(v[2 * i], v[2 * i + 1]);
+}
+
+// ---- sequential poles; 64-thread CTA = 32 channels x {AGC averagers (warp 0), S-meter (warp 1)}
+__global__ void __launch_bounds__(64) k_post_seq1(PostBufs b, int n, PostUniform u)
+{
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const bool smeter_warp = threadIdx.x >= 32;
     if (c >= b.nch) return;
     const int mode = b.mode[c];
-    if (mode != POST_AGC_ONLY) {
+    const int n16 = n & ~15;
+    if (smeter_warp) {
+        if (mode == POST_AGC_ONLY) return;
         // CSMeter::ProcessData, dsp/smeter.cpp:77-91
         double sm_att = ST(S_SM_ATT), sm_dec = ST(S_SM_DEC), sm_ave = ST(S_SM_AVE), sm_peak = ST(S_SM_PEAK);
         const double* row = b.smag + (size_t)c * b.row;
-        for (int t = 0; t < n; t++) {
-            const double mag = row[t];
-            sm_att = (1.0 - u.sm_attack) * sm_att + u.sm_attack * mag;
-            sm_dec = (1.0 - u.sm_decay) * sm_dec + u.sm_decay * mag;
+        const double qa = 1.0 - u.sm_attack, qd = 1.0 - u.sm_decay;
+        auto step = [&](double mag) {
+            sm_att = qa * sm_att + u.sm_attack * mag;
+            sm_dec = qd * sm_dec + u.sm_decay * mag;
             if (sm_att > sm_dec) { sm_ave = sm_att; sm_dec = sm_att; }
             else sm_ave = sm_dec;
             if (mag > sm_peak) sm_peak = mag;
+        };
+        double cur[16], nxt[16];
+        if (n16 > 0) load16(row, cur);
+        for (int t0 = 0; t0 < n16; t0 += 16) {
+            if (t0 + 16 < n16) load16(row + t0 + 16, nxt);
+#pragma unroll
+            for (int k = 0; k < 16; k++) step(cur[k]);
+#pragma unroll
+            for (int k = 0; k < 16; k++) cur[k] = nxt[k];
         }
+        for (int t = n16; t < n; t++) step(row[t]);
         ST(S_SM_ATT) = sm_att; ST(S_SM_DEC) = sm_dec; ST(S_SM_AVE) = sm_ave; ST(S_SM_PEAK) = sm_peak;
+        return;
     }
-    if (PAR(P_AGC_ON) != 0.0) {
-        // attack/decay averagers of CAgc::ProcessData, dsp/agc.cpp:235-276; row <- max(attack, decay)
-        const bool use_hang = PAR(P_AGC_HANG) != 0.0;
-        const double a_rise = PAR(P_A_RISE), a_fall = PAR(P_A_FALL), d_rise = PAR(P_D_RISE), d_fall = PAR(P_D_FALL);
-        const int hang_time = (int)PAR(P_HANG_TIME);
-        double att = ST(S_AGC_ATT), dec = ST(S_AGC_DEC);
-        int hang_timer = IST(I_AGC_HANGT);
-        double* row = b.peak + (size_t)c * b.row;
-        for (int t = 0; t < n; t++) {
-            const double peak = row[t];
-            if (peak > att) att = (1.0 - a_rise) * att + a_rise * peak;
-            else att = (1.0 - a_fall) * att + a_fall * peak;
-            if (use_hang) {
-                if (peak > dec) { dec = (1.0 - d_rise) * dec + d_rise * peak; hang_timer = 0; }
-                else if (hang_timer < hang_time) hang_timer++;
-                else dec = (1.0 - d_fall) * dec + d_fall * peak;
-            } else {
-                if (peak > dec) dec = (1.0 - d_rise) * dec + d_rise * peak;
-                else dec = (1.0 - d_fall) * dec + d_fall * peak;
-            }
-            row[t] = att > dec ? att : dec;
+    if (PAR(P_AGC_ON) == 0.0) return;
+    // attack/decay averagers of CAgc::ProcessData, dsp/agc.cpp:235-276; row <- max(attack, decay)
+    const bool use_hang = PAR(P_AGC_HANG) != 0.0;
+    const double a_rise = PAR(P_A_RISE), a_fall = PAR(P_A_FALL), d_rise = PAR(P_D_RISE), d_fall = PAR(P_D_FALL);
+    const int hang_time = (int)PAR(P_HANG_TIME);
+    double att = ST(S_AGC_ATT), dec = ST(S_AGC_DEC);
+    int hang_timer = IST(I_AGC_HANGT);
+    double* row = b.peak + (size_t)c * b.row;
+    auto step = [&](double peak) -> double {
+        if (peak > att) att = (1.0 - a_rise) * att + a_rise * peak;
+        else att = (1.0 - a_fall) * att + a_fall * peak;
+        if (use_hang) {
+            if (peak > dec) { dec = (1.0 - d_rise) * dec + d_rise * peak; hang_timer = 0; }
+            else if (hang_timer < hang_time) hang_timer++;
+            else dec = (1.0 - d_fall) * dec + d_fall * peak;
+        } else {
+            if (peak > dec) dec = (1.0 - d_rise) * dec + d_rise * peak;
+            else dec = (1.0 - d_fall) * dec + d_fall * peak;
         }
-        ST(S_AGC_ATT) = att; ST(S_AGC_DEC) = dec; IST(I_AGC_HANGT) = hang_timer;
+        return att > dec ? att : dec;
+    };
+    double cur[16], nxt[16];
+    if (n16 > 0) load16(row, cur);
+    for (int t0 = 0; t0 < n16; t0 += 16) {
+        if (t0 + 16 < n16) load16(row + t0 + 16, nxt);
+#pragma unroll
+        for (int k = 0; k < 16; k++) cur[k] = step(cur[k]);
+        store16(row + t0, cur);
+#pragma unroll
+        for (int k = 0; k < 16; k++) cur[k] = nxt[k];
     }
+    for (int t = n16; t < n; t++) row[t] = step(row[t]);
+    ST(S_AGC_ATT) = att; ST(S_AGC_DEC) = dec; IST(I_AGC_HANGT) = hang_timer;
 }
 
 // ---- gain law, delayed signal, per-mode pointwise front end; CTA per channel
@@ -281,15 +321,27 @@ __global__ void __launch_bounds__(32) k_post_seq2(PostBufs b, int n, PostUniform
     if (mode != POST_AM && mode != POST_SAM && mode != POST_FM) return;
     float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + audio_off : nullptr;
     double* vrow = b.v + (size_t)c * b.v_row + kHist;
+    const int n16 = n & ~15;
+    double cur[16], nxt[16];
     if (mode == POST_AM) {
         // DC removal H(z) = (1 - z^-1)/(1 - .99 z^-1), dsp/amdemod.cpp:73-78
         double z1 = ST(S_Z1);
         const double* urow = b.u + (size_t)c * b.row;
-        for (int t = 0; t < n; t++) {
-            const double z0 = urow[t] + (z1 * 0.99);
-            vrow[t] = z0 - z1;
+        auto step = [&](double mag) -> double {
+            const double z0 = mag + (z1 * 0.99);
+            const double o = z0 - z1;
             z1 = z0;
+            return o;
+        };
+        if (n16 > 0) load16(urow, cur);
+        for (int t0 = 0; t0 < n16; t0 += 16) {
+            if (t0 + 16 < n16) load16(urow + t0 + 16, nxt);
+#pragma unroll
+            for (int k = 0; k < 16; k++) vrow[t0 + k] = step(cur[k]);     // vrow is only 8-byte aligned (kHist offset)
+#pragma unroll
+            for (int k = 0; k < 16; k++) cur[k] = nxt[k];
         }
+        for (int t = n16; t < n; t++) vrow[t] = step(urow[t]);
         ST(S_Z1) = z1;
         return;
     }
@@ -300,29 +352,50 @@ __global__ void __launch_bounds__(32) k_post_seq2(PostBufs b, int n, PostUniform
         // tmp.re = |x| cos(err)
         double z1 = ST(S_Z1);
         const double* urow = b.u + (size_t)c * b.row;
-        for (int t = 0; t < n; t++) {
-            const double err = wrap_pi(throw_[t] - phase);
+        double ucur[16], unxt[16];
+        auto step = [&](double th, double mag) -> float {
+            const double err = wrap_pi(th - phase);
             freq += (u.sam_beta * err);
             if (freq > u.sam_hi) freq = u.sam_hi;
             else if (freq < u.sam_lo) freq = u.sam_lo;
             phase = wrap_pi(phase + (freq + u.sam_alpha * err));
-            const double z0 = urow[t] * cos(err) + (z1 * 0.99);
-            if (aout) aout[t] = (float)(z0 - z1);
+            const double z0 = mag * cos(err) + (z1 * 0.99);
+            const float o = (float)(z0 - z1);
             z1 = z0;
+            return o;
+        };
+        if (n16 > 0) { load16(throw_, cur); load16(urow, ucur); }
+        for (int t0 = 0; t0 < n16; t0 += 16) {
+            if (t0 + 16 < n16) { load16(throw_ + t0 + 16, nxt); load16(urow + t0 + 16, unxt); }
+#pragma unroll
+            for (int k = 0; k < 16; k++) { const float o = step(cur[k], ucur[k]); if (aout) aout[t0 + k] = o; }
+#pragma unroll
+            for (int k = 0; k < 16; k++) { cur[k] = nxt[k]; ucur[k] = unxt[k]; }
         }
+        for (int t = n16; t < n; t++) { const float o = step(throw_[t], urow[t]); if (aout) aout[t] = o; }
         ST(S_Z1) = z1;
     } else {
         // dsp/fmdemod.cpp:166-187: tmp = x e^{+j phase}; err = -atan2(tmp) = -wrap(arg x + phase)
         double fm_dc = ST(S_FM_DC);
-        for (int t = 0; t < n; t++) {
-            const double err = -wrap_pi(throw_[t] + phase);
+        const double qdc = 1.0 - u.fm_dc_alpha;
+        auto step = [&](double th) -> double {
+            const double err = -wrap_pi(th + phase);
             freq += (u.fm_beta * err);
             if (freq > u.fm_hi) freq = u.fm_hi;
             else if (freq < u.fm_lo) freq = u.fm_lo;
             phase = wrap_pi(phase + (freq + u.fm_alpha * err));
-            fm_dc = (1.0 - u.fm_dc_alpha) * fm_dc + u.fm_dc_alpha * freq;
-            vrow[t] = (freq - fm_dc) * u.fm_gain;
+            fm_dc = qdc * fm_dc + u.fm_dc_alpha * freq;
+            return (freq - fm_dc) * u.fm_gain;
+        };
+        if (n16 > 0) load16(throw_, cur);
+        for (int t0 = 0; t0 < n16; t0 += 16) {
+            if (t0 + 16 < n16) load16(throw_ + t0 + 16, nxt);
+#pragma unroll
+            for (int k = 0; k < 16; k++) vrow[t0 + k] = step(cur[k]);
+#pragma unroll
+            for (int k = 0; k < 16; k++) cur[k] = nxt[k];
         }
+        for (int t = n16; t < n; t++) vrow[t] = step(throw_[t]);
         ST(S_FM_DC) = fm_dc;
     }
     ST(S_PHASE) = phase; ST(S_FREQ) = freq;
@@ -593,7 +666,7 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
     const size_t smem_fir = (size_t)(kHist + max_n_ + kFirMax) * sizeof(double);
     const int seq_blocks = (nch_ + 31) / 32;
     k_post_pre<<<nch_, 256, smem_pre, st_>>>(b, n, uni_.agc_window);
-    k_post_seq1<<<seq_blocks, 32, 0, st_>>>(b, n, uni_);
+    k_post_seq1<<<seq_blocks, 64, 0, st_>>>(b, n, uni_);
     k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_seq2<<<seq_blocks, 32, 0, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_fir<<<nch_, 256, smem_fir, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);

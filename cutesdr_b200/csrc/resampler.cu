@@ -51,6 +51,15 @@ __global__ void __launch_bounds__(128) k_resample(const float* __restrict__ w, i
     }
 }
 
+// The output time sequence, stepped exactly like the reference's accumulator (same IEEE double adds
+// as ResampleClock::advance on the host, which supplies the start time and the count).
+__global__ void k_resample_times(double t0, double rate, int m, double* __restrict__ times)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double t = t0;
+    for (int k = 0; k < m; k++) { times[k] = t; t += rate; }
+}
+
 // carry the last 28 inputs of every row to the row's front (dsp/fractresampler.cpp:180-182)
 __global__ void k_resample_carry(float* w, int row_len, int nrows, int n_in)
 {
@@ -67,7 +76,6 @@ ResamplerBank::~ResamplerBank()
     cudaFree(d_w_);
     cudaFree(d_sinc_);
     cudaFree(d_times_);
-    if (h_times_) cudaFreeHost(h_times_);
 }
 
 int ResamplerBank::init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc)
@@ -96,21 +104,19 @@ int ResamplerBank::run(int n_in, double rate, float* d_out, int out_stride, int 
                        int* n_out, int16_t* d_out16, double gain, int interleave16)
 {
     if (n_in < 0 || n_in > max_in_ || !(rate > 0)) { set_error("resampler: bad length %d / rate %g", n_in, rate); return CUTESDR_E_ARG; }
+    const double t0 = clk_.now();
     clk_.advance(n_in, rate, times_);
     const int m = (int)times_.size();
     if (n_out) *n_out = m;
     if (m > 0) {
         if (m > times_cap_) {
+            CSDR_CK(cudaStreamSynchronize(st_));
             cudaFree(d_times_);
-            if (h_times_) cudaFreeHost(h_times_);
             times_cap_ = std::max(m, 2 * times_cap_) + 64;
             CSDR_CK(cudaMalloc(&d_times_, times_cap_ * sizeof(double)));
-            CSDR_CK(cudaHostAlloc(&h_times_, times_cap_ * sizeof(double), cudaHostAllocDefault));
         }
-        // the pinned buffer is rewritten every call: wait for the previous call's copy first
-        CSDR_CK(cudaStreamSynchronize(st_));
-        memcpy(h_times_, times_.data(), m * sizeof(double));
-        CSDR_CK(cudaMemcpyAsync(d_times_, h_times_, m * sizeof(double), cudaMemcpyHostToDevice, st_));
+        k_resample_times<<<1, 32, 0, st_>>>(t0, rate, m, d_times_);
+        lc_->n++;
         if (d_out || d_out16) {
             dim3 grid((m + 127) / 128, nrows_);
             k_resample<<<grid, 128, 0, st_>>>(d_w_, row_len_, nrows_, d_times_, m, d_sinc_, d_out, out_stride, out_off,

@@ -16,6 +16,7 @@ constexpr int kRsLen = kRsPeriods * kRsPts + 1;
 class ResampleClock {
 public:
     void reset() { t_ = 0.0; }
+    double now() const { return t_; }
     // fills times with the fractional input time of every output produced for n_in inputs
     void advance(int n_in, double rate, std::vector<double>& times);
 private:
@@ -50,7 +51,6 @@ private:
     float* d_w_ = nullptr;        // [nrows][28 + max_in] : 28 carried inputs, then the new ones
     float* d_sinc_ = nullptr;     // [kRsLen]
     double* d_times_ = nullptr;
-    double* h_times_ = nullptr;   // pinned
     int times_cap_ = 0;
     std::vector<double> times_;
 };

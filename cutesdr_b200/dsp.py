@@ -129,6 +129,9 @@ class ReceiverBank:
     def synchronize(self):
         check(self.L.cutesdr_bank_synchronize(self.h))
 
+    def join(self):
+        check(self.L.cutesdr_bank_join(self.h))
+
     # --- processing
     def ProcessData(self, iq, audio=None, audio_stride=None):
         """iq: complex64 host array (any length). Returns (audio[n_channels, stride] float32, n_out[n_channels])."""

@@ -101,7 +101,12 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
  * stream; *n_out_max is known on return (burst timing is deterministic). */
 int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, void* d_audio, int audio_stride,
                                 int* n_out_max);
+/* process_device queues work on the bank's main stream (decimation) and on internal side streams
+ * (FIR / AGC / demodulator bursts, which overlap the next blocks' decimation). synchronize waits
+ * for all of it; join only orders the main stream after all queued burst work, so that an event
+ * recorded on the main stream afterwards covers everything (used for device timing). */
 int cutesdr_bank_synchronize(cutesdr_bank* b);
+int cutesdr_bank_join(cutesdr_bank* b);
 /* cudaStream_t of the bank, as void* (for event timing on the launching stream) */
 int cutesdr_bank_stream(cutesdr_bank* b, void** stream);
 /* kernels launched by this bank so far */
