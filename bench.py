@@ -314,7 +314,12 @@ def run_ours(args):
             per_launch_s = (k1_ms / k1_n) * 1e-3
             groups = max(1, round(k1_n / max(1, args.steps)))
             ach = (k1_bytes / groups) / per_launch_s / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[args.workload]["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "kernel": "k_mix_cic", "launch_ms": k1_ms / k1_n, "launches": k1_n, "peak_source": peak_src,
                     "note": "per-channel streaming model (8 B per sample*channel); real DRAM traffic is far lower "
                             "because every channel re-uses the staged tile -- the kernel is FP32-issue bound"}
