@@ -3,6 +3,7 @@
 #include "bank.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace csdr {
 
@@ -47,7 +48,8 @@ cutesdr_bank::~cutesdr_bank()
     groups.clear();
     nb.reset();
     cudaFree(d_x);
-    cudaFree(d_halo_tmp);
+    cudaFree(d_halo[0]);
+    cudaFree(d_halo[1]);
     cudaFree(d_audio);
     if (h_stage) cudaFreeHost(h_stage);
     if (st) cudaStreamDestroy(st);
@@ -94,13 +96,14 @@ int cutesdr_bank::rebuild()
         d_x = nullptr;
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr;
-        CSDR_CK(cudaMalloc(&d_x, (size_t)(kHaloMax + L) * sizeof(float2)));
-        if (!d_halo_tmp) CSDR_CK(cudaMalloc(&d_halo_tmp, (size_t)kHaloMax * sizeof(float2)));
+        CSDR_CK(cudaMalloc(&d_x, (size_t)L * sizeof(float2)));
+        for (int k = 0; k < 2; k++) if (!d_halo[k]) CSDR_CK(cudaMalloc(&d_halo[k], (size_t)kHaloMax * sizeof(float2)));
         CSDR_CK(cudaHostAlloc(&h_stage, (size_t)L * sizeof(float2), cudaHostAllocDefault));
         h_fill = 0;
     }
     // a rebuild re-creates every DSP object: the stream restarts from zero state
-    CSDR_CK(cudaMemsetAsync(d_x, 0, (size_t)(kHaloMax + L) * sizeof(float2), st));
+    for (int k = 0; k < 2; k++) CSDR_CK(cudaMemsetAsync(d_halo[k], 0, (size_t)kHaloMax * sizeof(float2), st));
+    halo_cur = 0;
     stream_pos = 0;
     block_index = 0;
     for (auto& kv : by_bw) {
@@ -113,6 +116,7 @@ int cutesdr_bank::rebuild()
         CSDR_CK(cudaEventCreateWithFlags(&g->ev_dec, cudaEventDisableTiming));
         for (auto& e : g->ev_post) CSDR_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CSDR_TRY(g->dec.init(n, in_rate, g->max_bw, L, st, &lc));
+        CSDR_TRY(g->dec.set_overlap(getenv("CUTESDR_OVERLAP_K2") != nullptr));   // measured: no gain
         const int stride = g->dec.stride();
         CSDR_TRY(g->fir.init(n, stride, g->st_post, &lc));
         CSDR_TRY(g->post.init(n, stride, g->dec.out_rate(), kMaxBurstSamples, g->st_post, &lc));
@@ -143,9 +147,8 @@ int cutesdr_bank::rebuild()
 
 // One DSP block. d_block points at the block's first sample (kHaloMax history in front).
 // audio_off[group] = samples already written for that group's channels in d_audio_out.
-int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max)
+int cutesdr_bank::run_block(const float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max)
 {
-    CSDR_TRY(apply_nco_startup_gain(d_block, stream_pos, L, st, &lc));
     int nmax = 0;
     std::fill(blk_nout.begin(), blk_nout.end(), 0);
     for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -155,19 +158,18 @@ int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_strid
         // in the 2048 samples of slack).
         for (size_t k = 0; k < g.pending.size();) {
             if (g.pending[k].block <= block_index - 2) {
-                CSDR_CK(cudaStreamWaitEvent(st, g.pending[k].ev, 0));
+                CSDR_TRY(g.dec.wait_before_output(g.pending[k].ev));
                 g.pending.erase(g.pending.begin() + k);
             } else k++;
         }
-        CSDR_TRY(g.dec.run_block(d_block));
+        CSDR_TRY(g.dec.run_block(d_block, d_halo[halo_cur], d_halo[halo_cur ^ 1]));
         const long long total = g.dec.total_out();
         const int nbursts = (int)(total / kBurst - g.bursts_done);
         g.last_fir_n = 0;
         if (nbursts <= 0) continue;
         const int n = nbursts * kBurst;
         if (n > kMaxBurstSamples) { set_error("more than %d FIR bursts in one DSP block", kMaxBurstSamples / kBurst); return CUTESDR_E_STATE; }
-        CSDR_CK(cudaEventRecord(g.ev_dec, st));
-        CSDR_CK(cudaStreamWaitEvent(g.st_post, g.ev_dec, 0));
+        CSDR_CK(cudaStreamWaitEvent(g.st_post, g.dec.done_event(), 0));
         CSDR_TRY(g.fir.run(g.dec.ring(), g.bursts_done, nbursts, g.post.y_in(), g.post.y_stride()));
         g.bursts_done += nbursts;
         g.last_fir_n = n;
@@ -195,10 +197,7 @@ int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_strid
         for (int c : g.chans) blk_nout[c] = produced;
         nmax = std::max(nmax, produced);
     }
-    // keep the tail of this block in front of the next one (halo of kernel 1): the last kHaloMax
-    // samples of [old halo | block], staged through a scratch buffer because the ranges may overlap
-    CSDR_CK(cudaMemcpyAsync(d_halo_tmp, d_block + (L - kHaloMax), kHaloMax * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-    CSDR_CK(cudaMemcpyAsync(d_block - kHaloMax, d_halo_tmp, kHaloMax * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    halo_cur ^= 1;      // kernel 1 saved this block's tail into the other halo buffer
     stream_pos += L;
     block_index++;
     if (n_out_max) *n_out_max = nmax;
@@ -208,6 +207,7 @@ int cutesdr_bank::run_block(float2* d_block, float* d_audio_out, int audio_strid
 int cutesdr_bank::join()
 {
     for (auto& g : groups) {
+        CSDR_TRY(g->dec.join_main());
         for (auto& p : g->pending) CSDR_CK(cudaStreamWaitEvent(st, p.ev, 0));
         g->pending.clear();
     }
@@ -405,19 +405,32 @@ static int ensure_audio(cutesdr_bank* b, int stride)
     return CUTESDR_OK;
 }
 
-// wideband pre-processing shared by all channels: the noise blanker writes the block buffer
-static int stage_block(cutesdr_bank* b, const float2* src, cudaMemcpyKind kind)
+// Wideband pre-processing shared by all channels. Returns (in *blk) the device block kernel 1 reads:
+// the caller's own device buffer when nothing has to touch it, else the bank's staging buffer
+// (host input, the noise blanker's output, or the first block of a stream whose first samples get the
+// oscillator's start-up amplitude).
+static int stage_block(cutesdr_bank* b, const float2* src, cudaMemcpyKind kind, const float2** blk)
 {
-    float2* dst = b->d_x + kHaloMax;
-    if (b->nb && b->nb->on()) {
+    const bool nb_on = b->nb && b->nb->on();
+    const bool startup = b->stream_pos < kNcoStartup;
+    if (kind == cudaMemcpyDeviceToDevice && !nb_on && !startup) { *blk = src; return CUTESDR_OK; }
+    float2* dst = b->d_x;
+    if (nb_on) {
         float2* raw = nullptr;
-        CSDR_CK(cudaMallocAsync(&raw, (size_t)b->L * sizeof(float2), b->st));
-        CSDR_CK(cudaMemcpyAsync(raw, src, (size_t)b->L * sizeof(float2), kind, b->st));
-        int rc = b->nb->run(raw, dst, b->L);
-        CSDR_CK(cudaFreeAsync(raw, b->st));
-        return rc;
+        const float2* in = src;
+        if (kind != cudaMemcpyDeviceToDevice) {
+            CSDR_CK(cudaMallocAsync(&raw, (size_t)b->L * sizeof(float2), b->st));
+            CSDR_CK(cudaMemcpyAsync(raw, src, (size_t)b->L * sizeof(float2), kind, b->st));
+            in = raw;
+        }
+        int rc = b->nb->run(in, dst, b->L);
+        if (raw) CSDR_CK(cudaFreeAsync(raw, b->st));
+        if (rc < 0) return rc;
+    } else {
+        CSDR_CK(cudaMemcpyAsync(dst, src, (size_t)b->L * sizeof(float2), kind, b->st));
     }
-    CSDR_CK(cudaMemcpyAsync(dst, src, (size_t)b->L * sizeof(float2), kind, b->st));
+    if (startup) CSDR_TRY(apply_nco_startup_gain(dst, b->stream_pos, b->L, b->st, &b->lc));
+    *blk = dst;
     return CUTESDR_OK;
 }
 
@@ -446,9 +459,10 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
             blk = b->h_stage;
             b->h_fill = 0;
         }
-        CSDR_TRY(stage_block(b, blk, cudaMemcpyHostToDevice));
+        const float2* dblk = nullptr;
+        CSDR_TRY(stage_block(b, blk, cudaMemcpyHostToDevice, &dblk));
         int m = 0;
-        CSDR_TRY(b->run_block(b->d_x + kHaloMax, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
+        CSDR_TRY(b->run_block(dblk, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
         for (size_t gi = 0; gi < b->groups.size(); gi++) {
             Group& g = *b->groups[gi];
             if (g.chans.empty()) continue;
@@ -488,9 +502,10 @@ int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, voi
     CSDR_CK(cudaSetDevice(b->device));
     if (b->layout_dirty) CSDR_TRY(b->rebuild());
     if (n_in != b->L) { set_error("bank_process_device: n_in %d must equal the block length %d", n_in, b->L); return CUTESDR_E_ARG; }
-    CSDR_TRY(stage_block(b, reinterpret_cast<const float2*>(d_iq), cudaMemcpyDeviceToDevice));
+    const float2* dblk = nullptr;
+    CSDR_TRY(stage_block(b, reinterpret_cast<const float2*>(d_iq), cudaMemcpyDeviceToDevice, &dblk));
     int m = 0;
-    CSDR_TRY(b->run_block(b->d_x + kHaloMax, reinterpret_cast<float*>(d_audio), audio_stride, nullptr, &m));
+    CSDR_TRY(b->run_block(dblk, reinterpret_cast<float*>(d_audio), audio_stride, nullptr, &m));
     CSDR_TRY(b->collect_taps());
     if (n_out_max) *n_out_max = m;
     return m;

@@ -64,8 +64,9 @@ struct cutesdr_bank {
     std::vector<std::unique_ptr<csdr::Group>> groups;
     bool layout_dirty = true;
     int L = 0;                           // m_InBufLimit
-    float2* d_x = nullptr;               // [kHaloMax | L]
-    float2* d_halo_tmp = nullptr;        // [kHaloMax]
+    float2* d_x = nullptr;               // [L] staging of host / blanked blocks
+    float2* d_halo[2] = {nullptr, nullptr};   // [kHaloMax] tail of the previous block (double buffer)
+    int halo_cur = 0;
     float2* h_stage = nullptr;           // pinned staging of one block
     int h_fill = 0;
     long long stream_pos = 0;
@@ -79,7 +80,7 @@ struct cutesdr_bank {
     std::vector<int> blk_nout;           // per channel, samples produced by the last block
 
     int rebuild();
-    int run_block(float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);
+    int run_block(const float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);
     int collect_taps();
     int join();                          // order the main stream after every outstanding burst chain
     int sync_all();

@@ -17,6 +17,7 @@
 // Reference: CDownConvert::ProcessData and the three DecBy2 classes, dsp/downconvert.cpp:186-460.
 #include "decimator.cuh"
 #include "halfband_tables.h"
+#include <stdlib.h>
 
 namespace csdr {
 
@@ -90,7 +91,7 @@ __device__ __forceinline__ float2 seed_osc(unsigned long long ph)
     return make_float2(c, s);
 }
 
-constexpr int kFuseHb = 1;
+constexpr int kFuseHb = 1;      // a second fused stage costs kernel 1 more (registers, halo) than it saves in kernel 2
 
 static int k1_body(int ncic) { int g = 1 << ncic; return g < 32 ? 32 : g; }
 static int k1_halo(int ncic, int nhb)
@@ -99,6 +100,17 @@ static int k1_halo(int ncic, int nhb)
     const int need = (ncic == 0 ? 0 : (2 << ncic)) + 10 * g * ((1 << nhb) - 1);
     const int q = std::max(g << nhb, b);
     return (need + q - 1) / q * q;
+}
+
+// The last kHaloMax samples of [previous halo | this block] become the next block's halo
+// (written to the other half of a double buffer, so concurrent readers of halo_cur are safe).
+__device__ __forceinline__ void save_halo(const float2* __restrict__ x, const float2* __restrict__ halo_cur,
+                                          float2* __restrict__ halo_next, int L)
+{
+    for (int i = threadIdx.x; i < kHaloMax; i += blockDim.x) {
+        const int j = L - kHaloMax + i;
+        halo_next[i] = j >= 0 ? x[j] : halo_cur[kHaloMax + j];
+    }
 }
 
 struct CicSt { float2 xodd, xeven; };
@@ -184,7 +196,8 @@ template <int NCIC, int NHB, int B> struct Body<NCIC, NHB, B, B> {
 // K1: fused NCO mix + NCIC x CIC3 + NHB x HB11
 // ------------------------------------------------------------------------------------------
 template <int NCIC, int NHB>
-__global__ void __launch_bounds__(256) k_mix_cic(const float2* __restrict__ x, int L, int tile_len,
+__global__ void __launch_bounds__(256, 3) k_mix_cic(const float2* __restrict__ x, const float2* __restrict__ halo_cur,
+                                                 float2* __restrict__ halo_next, int L, int tile_len,
                                                  const NcoDev* __restrict__ nco,
                                                  const unsigned long long* __restrict__ phase_cur,
                                                  unsigned long long* __restrict__ phase_next, int nch,
@@ -197,9 +210,14 @@ __global__ void __launch_bounds__(256) k_mix_cic(const float2* __restrict__ x, i
     const int n_tile = min(tile_len, L - t0);
     const int n_load = n_tile + H;
     {
+        // samples before the block start (first tile's halo) come from the saved tail of the
+        // previous block: halo_cur[kHaloMax + j] for j < 0
         const float4* src = reinterpret_cast<const float4*>(x + (t0 - H));
-        for (int i = threadIdx.x; i < (n_load >> 1); i += blockDim.x) smem4[i] = __ldg(src + i);
+        const float4* hsrc = reinterpret_cast<const float4*>(halo_cur + (kHaloMax + t0 - H));
+        const int n_neg = t0 < H ? ((H - t0) >> 1) : 0;
+        for (int i = threadIdx.x; i < (n_load >> 1); i += blockDim.x) smem4[i] = i < n_neg ? __ldg(hsrc + i) : __ldg(src + i);
     }
+    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == 0) save_halo(x, halo_cur, halo_next, L);
     __syncthreads();
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= nch) return;
@@ -251,10 +269,12 @@ __global__ void __launch_bounds__(256) k_mix_cic(const float2* __restrict__ x, i
 
 // Slow generic path for block lengths that are not a multiple of the unrolled body (single-object
 // API with odd sizes). Same math, run-time stage counts, one tile.
-__global__ void k_mix_cic_generic(const float2* __restrict__ x, int L, int ncic, int nhb, const NcoDev* __restrict__ nco,
+__global__ void k_mix_cic_generic(const float2* __restrict__ x, const float2* __restrict__ halo_cur,
+                                  float2* __restrict__ halo_next, int L, int ncic, int nhb, const NcoDev* __restrict__ nco,
                                   const unsigned long long* __restrict__ phase_cur,
                                   unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
 {
+    if (blockIdx.x == 0) save_halo(x, halo_cur, halo_next, L);
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nch) return;
     const int G = 1 << ncic;
@@ -278,7 +298,7 @@ __global__ void k_mix_cic_generic(const float2* __restrict__ x, int L, int ncic,
     long long q = -(long long)(H >> ncic);
     for (int i = -H; i < L; i++) {
         if (((i + H) & 31) == 0) o = seed_osc(ph0 + (unsigned long long)(long long)(i + 1) * p.inc);
-        float2 v = cmul(x[i], o);
+        float2 v = cmul(i >= 0 ? x[i] : halo_cur[kHaloMax + i], o);
         o = cmul(o, w1);
         int s = 0;
         while (s < ncic) {
@@ -307,12 +327,96 @@ __global__ void k_mix_cic_generic(const float2* __restrict__ x, int L, int ncic,
     }
 }
 
+typedef void (*K1Fn)(const float2*, const float2*, float2*, int, int, const NcoDev*, const unsigned long long*,
+                     unsigned long long*, int, OutDesc, float);
+
+static K1Fn k1_kernel(int ncic, int nhb)
+{
+    static const K1Fn table[7][3] = {
+        {k_mix_cic<0, 0>, k_mix_cic<0, 1>, k_mix_cic<0, 2>}, {k_mix_cic<1, 0>, k_mix_cic<1, 1>, k_mix_cic<1, 2>},
+        {k_mix_cic<2, 0>, k_mix_cic<2, 1>, k_mix_cic<2, 2>}, {k_mix_cic<3, 0>, k_mix_cic<3, 1>, k_mix_cic<3, 2>},
+        {k_mix_cic<4, 0>, k_mix_cic<4, 1>, k_mix_cic<4, 2>}, {k_mix_cic<5, 0>, k_mix_cic<5, 1>, k_mix_cic<5, 2>},
+        {k_mix_cic<6, 0>, k_mix_cic<6, 1>, k_mix_cic<6, 2>}};
+    return table[ncic][nhb];
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a: NS consecutive 11-tap half-band stages in ONE pass over HBM (the stages right after
+// kernel 1 carry most of kernel 2's traffic). Lane = channel, sequential over a time tile with the
+// delay lines in registers; a body is 2^NS input rows (loaded up front: 2^NS independent coalesced
+// 256-byte row reads in flight per warp), so every stage's even/odd phase is a compile-time constant.
+// Tiles overlap by 10*(2^NS-1) input rows (rounded up to a body) that re-prime the delay lines.
+// ------------------------------------------------------------------------------------------
+template <int NS, int J, int IDX>
+__device__ __forceinline__ void hbc_feed(float2 v, Hb11St* hs, float h0, float h2, float h4, float2& out, bool& have)
+{
+    if constexpr (J == NS) {
+        out = v;
+        have = true;
+    } else {
+        Hb11St& s = hs[J];
+        if constexpr ((IDX & 1) == 0) {
+            float2 y;
+            y.x = fmaf(h0, s.e[4].x + v.x, fmaf(h2, s.e[3].x + s.e[0].x, fmaf(h4, s.e[2].x + s.e[1].x, 0.5f * s.o[2].x)));
+            y.y = fmaf(h0, s.e[4].y + v.y, fmaf(h2, s.e[3].y + s.e[0].y, fmaf(h4, s.e[2].y + s.e[1].y, 0.5f * s.o[2].y)));
+            s.e[4] = s.e[3]; s.e[3] = s.e[2]; s.e[2] = s.e[1]; s.e[1] = s.e[0]; s.e[0] = v;
+            hbc_feed<NS, J + 1, (IDX >> 1)>(y, hs, h0, h2, h4, out, have);
+        } else {
+            s.o[2] = s.o[1]; s.o[1] = s.o[0]; s.o[0] = v;
+        }
+    }
+}
+
+template <int NS, int K> struct HbcBody {
+    static __device__ __forceinline__ void run(const float2* x, Hb11St* hs, float h0, float h2, float h4, float2& out, bool& have)
+    {
+        hbc_feed<NS, 0, K>(x[K], hs, h0, h2, h4, out, have);
+        HbcBody<NS, K + 1>::run(x, hs, h0, h2, h4, out, have);
+    }
+};
+template <int NS> struct HbcBody<NS, (1 << NS)> {
+    static __device__ __forceinline__ void run(const float2*, Hb11St*, float, float, float, float2&, bool&) {}
+};
+
+template <int NS>
+__global__ void __launch_bounds__(128) k_hb11_chain(const float2* __restrict__ in, unsigned in_mask, long long in_base, int stride,
+                                                    int n_out, int tile_out, OutDesc od)
+{
+    constexpr int R = 1 << NS;
+    constexpr int HALO = (10 * (R - 1) + R - 1) / R * R;        // input rows, whole bodies
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= stride) return;
+    const int o0 = blockIdx.x * tile_out;
+    const int o1 = min(o0 + tile_out, n_out);
+    const float h0 = c_hb_taps[0], h2 = c_hb_taps[1], h4 = c_hb_taps[2];
+    Hb11St hs[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) hs[s].e[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 3; k++) hs[s].o[k] = make_float2(0.f, 0.f);
+    }
+    // output o is complete when input row o*R arrives (newest tap of every stage is an even index):
+    // bodies are aligned so that row o*R is a body's FIRST row
+    for (int o = o0 - HALO / R; o < o1; o++) {
+        const long long row0 = in_base + (long long)o * R;
+        float2 x[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) x[k] = in[(size_t)((row0 + k) & in_mask) * stride + c];
+        float2 y = make_float2(0.f, 0.f);
+        bool have = false;
+        HbcBody<NS, 0>::run(x, hs, h0, h2, h4, y, have);
+        if (have && o >= o0) store_out(od, o, c, y);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K2: one decimate-by-2 stage, thread per (output row m, channel c)
 //   half-band : y[m] = sum_j h[j] x[2m-(N-1)+j]            (dsp/downconvert.cpp:286-320, 348-423)
 //   N == 3    : CIC3, y[m] = .125 (x[2m+1] + 3x[2m] + 3x[2m-1] + x[2m-2])          (:444-460)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_halfband(const float2* __restrict__ in, unsigned in_mask, long long in_base,
+__global__ void __launch_bounds__(128) k_halfband(const float2* __restrict__ in, unsigned in_mask, long long in_base,
                                                   int stride, int n_out, int N, int tap_off, OutDesc od)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,12 +487,20 @@ int apply_nco_startup_gain(float2* d_x, long long stream_pos, int n, cudaStream_
 int Decimator::read_timing(double* ms_total, long long* launches)
 {
     CSDR_CK(cudaStreamSynchronize(st_));
+    double gap = 0.0;
     for (size_t i = 0; i < ev_used_; i++) {
         float ms = 0.f;
         CSDR_CK(cudaEventElapsedTime(&ms, ev_pool_[i].first, ev_pool_[i].second));
         k1_ms_ += ms;
         k1_n_++;
+        if (i + 1 < ev_used_) {
+            CSDR_CK(cudaEventElapsedTime(&ms, ev_pool_[i].second, ev_pool_[i + 1].first));
+            gap += ms;
+        }
     }
+    if (getenv("CUTESDR_DEBUG_TIMING") && ev_used_ > 1)
+        fprintf(stderr, "[cutesdr] kernel-1: %zu launches, mean %.3f ms, mean gap to next launch %.3f ms\n", ev_used_,
+                k1_ms_ / (double)k1_n_, gap / (double)(ev_used_ - 1));
     ev_used_ = 0;
     if (ms_total) *ms_total = k1_ms_;
     if (launches) *launches = k1_n_;
@@ -397,8 +509,37 @@ int Decimator::read_timing(double* ms_total, long long* launches)
     return CUTESDR_OK;
 }
 
+int Decimator::set_overlap(bool on)
+{
+    if (on && !st_hb_) {
+        int lo = 0, hi = 0;
+        CSDR_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CSDR_CK(cudaStreamCreateWithPriority(&st_hb_, cudaStreamNonBlocking, hi));
+        for (auto& e : ev_k2_) CSDR_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    overlap_ = on && (int)lens_.size() > k1_stages() && !getenv("CUTESDR_NO_OVERLAP");
+    return CUTESDR_OK;
+}
+
+int Decimator::wait_before_output(cudaEvent_t ev)
+{
+    cudaStream_t s = (overlap_ && st_hb_) ? st_hb_ : st_;
+    CSDR_CK(cudaStreamWaitEvent(s, ev, 0));
+    return CUTESDR_OK;
+}
+
+int Decimator::join_main()
+{
+    if (overlap_ && blocks_run_ > 0) CSDR_CK(cudaStreamWaitEvent(st_, ev_done_, 0));
+    return CUTESDR_OK;
+}
+
 Decimator::~Decimator()
 {
+    if (st_hb_) { cudaStreamSynchronize(st_hb_); cudaStreamDestroy(st_hb_); }
+    if (ev_k1_) cudaEventDestroy(ev_k1_);
+    if (ev_done_) cudaEventDestroy(ev_done_);
+    for (auto& e : ev_k2_) if (e) cudaEventDestroy(e);
     for (auto& p : ev_pool_) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaFree(d_nco_);
     cudaFree(d_phase_[0]);
@@ -433,7 +574,9 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     while (ncic_ < (int)lens_.size() && lens_[ncic_] == 3 && ncic_ < 6) ncic_++;
     // up to kFuseHb 11-tap half-bands that follow the CICs run inside kernel 1 as well
     nhbf_ = 0;
-    while (nhbf_ < kFuseHb && ncic_ + nhbf_ < (int)lens_.size() && lens_[ncic_ + nhbf_] == 11) nhbf_++;
+    int fuse_max = kFuseHb;
+    if (const char* e = getenv("CUTESDR_FUSE_HB")) fuse_max = std::max(0, std::min(2, atoi(e)));     // tuning aid
+    while (nhbf_ < fuse_max && ncic_ + nhbf_ < (int)lens_.size() && lens_[ncic_ + nhbf_] == 11) nhbf_++;
     n_out_ = block_len >> lens_.size();
     if (n_out_ > kDecRing - kFirFft) { set_error("decimated block of %d samples exceeds the FIR ring", n_out_); return CUTESDR_E_ARG; }
     CSDR_TRY(upload_taps());
@@ -447,7 +590,8 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     const int nhb = (int)lens_.size() - k1_stages();
     for (int s = 0; s < nhb; s++) {
         int n_rows = block_len >> (k1_stages() + s);       // rows this ring receives per block
-        int rows = next_pow2((long long)n_rows + 64);
+        // ring 0 keeps two blocks so kernel 1 of block k+1 can fill it while kernel 2 still reads block k
+        int rows = next_pow2((long long)n_rows * (s == 0 ? 2 : 1) + 64);
         float2* p = nullptr;
         size_t bytes = (size_t)rows * stride_ * sizeof(float2);
         CSDR_CK(cudaMalloc(&p, bytes));
@@ -459,20 +603,60 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     size_t rbytes = (size_t)stride_ * kDecRing * sizeof(float2);
     CSDR_CK(cudaMalloc(&d_ring_, rbytes));
     CSDR_CK(cudaMemsetAsync(d_ring_, 0, rbytes, st_));
+    CSDR_CK(cudaEventCreateWithFlags(&ev_k1_, cudaEventDisableTiming));
+    CSDR_CK(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
 
-    // time tile: enough CTAs to fill 148 SMs several times over, tile >= ~16 halos
+    // Time tile. Every CTA costs ~(tile + halo) samples per lane, and the grid runs in waves of
+    // (SMs x resident CTAs): pick the tile count that minimises waves x (tile + halo), i.e. avoid a
+    // mostly-empty last wave and keep the halo small, within the shared memory that still allows the
+    // same residency.
     const int B = k1_body(ncic_);
     const int Q = std::max((1 << ncic_) << nhbf_, B);
     const int H = k1_halo(ncic_, nhbf_);
     if (H > kHaloMax) { set_error("kernel-1 halo %d exceeds kHaloMax", H); return CUTESDR_E_ARG; }
     const int cta_threads = std::min(256, round_up(stride_, 32));
     const int chan_blocks = (stride_ + cta_threads - 1) / cta_threads;
-    int tiles_target = (148 * 8 + chan_blocks - 1) / chan_blocks;
-    int tl = block_len / std::max(1, tiles_target);
-    tl = std::max(tl, std::max(512, 16 * H));
-    tl = std::min(tl, 4096);
-    tl = tl / Q * Q;
-    tile_len_ = std::max(tl, Q);
+    int dev = 0, sms = 148;
+    CSDR_CK(cudaGetDevice(&dev));
+    CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    K1Fn fn = k1_kernel(ncic_, nhbf_);
+    CSDR_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    double best_cost = 1e300;
+    int best_tl = Q;
+    std::map<int, int> occ_cache;       // smem KB -> resident CTAs per SM
+    const int max_tiles = std::max(1, block_len / std::max(Q, 4 * H));
+    for (int tiles = 1; tiles <= max_tiles; tiles++) {
+        int tl = (block_len + tiles - 1) / tiles;
+        tl = (tl + Q - 1) / Q * Q;
+        const size_t smem = (size_t)(tl + H) * sizeof(float2);
+        if (smem > 200 * 1024) continue;
+        const int real_tiles = (block_len + tl - 1) / tl;
+        const int key = (int)(smem >> 10);
+        int occ;
+        auto it = occ_cache.find(key);
+        if (it != occ_cache.end()) occ = it->second;
+        else {
+            CSDR_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cta_threads, smem));
+            occ_cache[key] = occ;
+        }
+        if (occ < 1) continue;
+        const long long grid = (long long)real_tiles * chan_blocks;
+        const long long slots = (long long)sms * occ;
+        const long long waves = (grid + slots - 1) / slots;
+        // fewer resident warps hide latency worse: charge a residency penalty below 16 warps/SM
+        const double warps = (double)std::min<long long>(grid, slots) / sms * (cta_threads / 32.0);
+        const double penalty = warps >= 16.0 ? 1.0 : (16.0 / std::max(warps, 1.0));
+        const double cost = (double)waves * (tl + H) * (warps >= 16.0 ? 1.0 : std::min(penalty, 4.0) * 0.5 + 0.5);
+        if (cost < best_cost * 0.999) { best_cost = cost; best_tl = tl; }
+    }
+    tile_len_ = best_tl;
+    if (const char* e = getenv("CUTESDR_TILE")) tile_len_ = std::max(Q, atoi(e) / Q * Q);                    // tuning aid
+    if (getenv("CUTESDR_DEBUG_TIMING")) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cta_threads, (size_t)(tile_len_ + H) * sizeof(float2));
+        fprintf(stderr, "[cutesdr] kernel-1 <%d,%d>: tile %d + halo %d, grid %d x %d, %d CTAs/SM\n", ncic_, nhbf_, tile_len_, H,
+                (block_len + tile_len_ - 1) / tile_len_, chan_blocks, occ);
+    }
     dirty_ = true;
     return CUTESDR_OK;
 }
@@ -505,31 +689,7 @@ int Decimator::upload_dirty()
     return CUTESDR_OK;
 }
 
-template <int NCIC, int NHB>
-static void launch_k1(dim3 grid, int threads, size_t smem, cudaStream_t st, const float2* x, int L, int tile_len,
-                      const NcoDev* nco, const unsigned long long* pc, unsigned long long* pn, int nch, OutDesc od,
-                      float scale)
-{
-    k_mix_cic<NCIC, NHB><<<grid, threads, smem, st>>>(x, L, tile_len, nco, pc, pn, nch, od, scale);
-}
-
-template <int NHB>
-static void launch_k1_n(int ncic, dim3 grid, int threads, size_t smem, cudaStream_t st, const float2* x, int L, int tile_len,
-                        const NcoDev* nco, const unsigned long long* pc, unsigned long long* pn, int nch, OutDesc od,
-                        float scale)
-{
-    switch (ncic) {
-    case 0: launch_k1<0, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
-    case 1: launch_k1<1, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
-    case 2: launch_k1<2, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
-    case 3: launch_k1<3, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
-    case 4: launch_k1<4, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
-    case 5: launch_k1<5, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
-    default: launch_k1<6, NHB>(grid, threads, smem, st, x, L, tile_len, nco, pc, pn, nch, od, scale); break;
-    }
-}
-
-int Decimator::run_block(const float2* d_x, int L)
+int Decimator::run_block(const float2* d_x, const float2* halo_cur, float2* halo_next, int L)
 {
     CSDR_TRY(upload_dirty());
     if (L < 0) L = block_len_;
@@ -557,6 +717,7 @@ int Decimator::run_block(const float2* d_x, int L)
     const float scale = (float)(sqrt(0.95) * ldexp(1.0, -3 * ncic_));
     const unsigned long long* pc = d_phase_[phase_cur_];
     unsigned long long* pn = d_phase_[phase_cur_ ^ 1];
+    if (overlap_ && blocks_run_ >= 2) CSDR_CK(cudaStreamWaitEvent(st_, ev_k2_[(blocks_run_ - 2) & 3], 0));
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     if (timing_ && ev_used_ < 8192) {
         if (ev_used_ == ev_pool_.size()) {
@@ -576,17 +737,61 @@ int Decimator::run_block(const float2* d_x, int L)
         dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);
         const int H = k1_halo(ncic_, nhbf_);
         size_t smem = (size_t)(tile_len_ + H) * sizeof(float2);
-        if (nhbf_ == 0) launch_k1_n<0>(ncic_, grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale);
-        else launch_k1_n<1>(ncic_, grid, threads, smem, st_, d_x, L, tile_len_, d_nco_, pc, pn, stride_, od, scale);
+        k1_kernel(ncic_, nhbf_)<<<grid, threads, smem, st_>>>(d_x, halo_cur, halo_next, L, tile_len_, d_nco_, pc, pn, stride_, od,
+                                                               scale);
     } else {
-        k_mix_cic_generic<<<(stride_ + 63) / 64, 64, 0, st_>>>(d_x, L, ncic_, nhbf_, d_nco_, pc, pn, stride_, od, scale);
+        k_mix_cic_generic<<<(stride_ + 63) / 64, 64, 0, st_>>>(d_x, halo_cur, halo_next, L, ncic_, nhbf_, d_nco_, pc, pn, stride_, od, scale);
     }
     lc_->n++;
     CSDR_CK(cudaGetLastError());
     if (ev_b) CSDR_CK(cudaEventRecord(ev_b, st_));
     phase_cur_ ^= 1;
+    cudaStream_t s2 = st_;
+    if (overlap_) {
+        CSDR_CK(cudaEventRecord(ev_k1_, st_));
+        CSDR_CK(cudaStreamWaitEvent(st_hb_, ev_k1_, 0));
+        s2 = st_hb_;
+    }
 
-    for (int s = 0; s < nhb; s++) {
+    int s_first = 0;
+    {
+        // leading run of 11-tap stages -> one fused pass
+        int nchain = 0;
+        while (nchain < 3 && nchain < nhb && lens_[k1_stages() + nchain] == 11) nchain++;
+        if (nchain >= 2 && !getenv("CUTESDR_NO_HBCHAIN")) {
+            const int n_in = L >> k1_stages();
+            const int n_out = n_in >> nchain;
+            OutDesc o2;
+            if (nchain < nhb) {
+                o2.p = d_stage_[nchain];
+                o2.mask = (unsigned)(stage_rows_[nchain] - 1);
+                o2.stride = stride_;
+                o2.transposed = 0;
+                o2.base = stage_base_[nchain];
+            } else {
+                o2.p = d_ring_;
+                o2.mask = 0;
+                o2.stride = stride_;
+                o2.transposed = 1;
+                o2.base = total_out_;
+            }
+            const int threads = std::min(128, round_up(stride_, 32));
+            const int chan_blocks = (stride_ + threads - 1) / threads;
+            // ~16 CTAs per SM in flight; tiles no shorter than ~8 halos
+            const int halo_out = (10 * ((1 << nchain) - 1) + (1 << nchain) - 1) >> nchain;
+            int tiles = std::max(1, (148 * 16) / chan_blocks);
+            int tile_out = std::max((n_out + tiles - 1) / tiles, 8 * halo_out);
+            dim3 grid((n_out + tile_out - 1) / tile_out, chan_blocks);
+            const unsigned mask0 = (unsigned)(stage_rows_[0] - 1);
+            if (nchain == 2) k_hb11_chain<2><<<grid, threads, 0, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, tile_out, o2);
+            else k_hb11_chain<3><<<grid, threads, 0, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, tile_out, o2);
+            lc_->n++;
+            CSDR_CK(cudaGetLastError());
+            for (int s = 0; s < nchain; s++) stage_base_[s] += (L >> (k1_stages() + s));
+            s_first = nchain;
+        }
+    }
+    for (int s = s_first; s < nhb; s++) {
         const int N = lens_[k1_stages() + s];
         const int n_in = L >> (k1_stages() + s);
         const int n_out = n_in >> 1;
@@ -605,13 +810,16 @@ int Decimator::run_block(const float2* d_x, int L)
             o2.base = total_out_;
         }
         long long work = (long long)n_out * stride_;
-        int blocks = (int)((work + 255) / 256);
-        k_halfband<<<blocks, 256, 0, st_>>>(d_stage_[s], (unsigned)(stage_rows_[s] - 1), stage_base_[s], stride_, n_out, N,
-                                            tap_offset_for(N), o2);
+        int blocks = (int)((work + 127) / 128);      // small CTAs slot in beside kernel 1's resident CTAs
+        k_halfband<<<blocks, 128, 0, s2>>>(d_stage_[s], (unsigned)(stage_rows_[s] - 1), stage_base_[s], stride_, n_out, N,
+                                           tap_offset_for(N), o2);
         lc_->n++;
         CSDR_CK(cudaGetLastError());
         stage_base_[s] += n_in;
     }
+    if (overlap_) CSDR_CK(cudaEventRecord(ev_k2_[blocks_run_ & 3], s2));
+    CSDR_CK(cudaEventRecord(ev_done_, s2));
+    blocks_run_++;
     total_out_ += L >> lens_.size();
     return CUTESDR_OK;
 }

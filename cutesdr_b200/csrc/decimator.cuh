@@ -36,11 +36,22 @@ public:
     // CDownConvert::SetFrequency for local channel i (freq already includes the CW offset)
     void set_frequency(int i, double nco_freq);
 
-    // Run one block of L <= block_len samples (L a multiple of 2^stages). d_x points at the first
-    // sample of the block inside a buffer that keeps kHaloMax samples of the previous block in
-    // front of it. L < 0 means the full block length.
-    int run_block(const float2* d_x, int L = -1);
+    // Run one block of L <= block_len samples (L a multiple of 2^stages; L < 0 = the full block).
+    // d_x: the block (device, complex64, 16-byte aligned). halo_cur: kHaloMax samples that preceded
+    // it in the stream (zeros at stream start); halo_next (a different buffer) receives the last
+    // kHaloMax samples of [halo_cur | block] for the next call -- kernel 1 writes it itself, so the
+    // caller's block is read in place and no copy node sits between consecutive launches.
+    int run_block(const float2* d_x, const float2* halo_cur, float2* halo_next, int L = -1);
     int block_len() const { return block_len_; }
+    // Overlap mode (used by the bank): the HBM-bound half-band stages (kernel 2) run on an internal
+    // second stream so they execute under the FP32-bound kernel 1 of the NEXT block. The first stage
+    // ring then holds two blocks. done_event() is recorded after the last kernel that writes the
+    // decimated ring; wait_before_output(ev) orders that last writer after `ev` (ring-reuse guard).
+    // Without overlap everything is ordered on the caller's stream.
+    int set_overlap(bool on);
+    cudaEvent_t done_event() const { return ev_done_; }
+    int wait_before_output(cudaEvent_t ev);
+    int join_main();          // order the caller's stream after all internal work queued so far
     // CUDA-event timing of kernel 1 on the launching stream (bench.py's roofline line)
     void enable_timing(bool on) { timing_ = on; }
     int read_timing(double* ms_total, long long* launches);
@@ -73,6 +84,11 @@ private:
     std::vector<float2*> d_stage_;
     std::vector<int> stage_rows_;      // power of two
     float2* d_ring_ = nullptr;
+    bool overlap_ = false;
+    cudaStream_t st_hb_ = 0;
+    cudaEvent_t ev_k1_ = nullptr, ev_done_ = nullptr;
+    cudaEvent_t ev_k2_[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long blocks_run_ = 0;
     bool timing_ = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool_;
     size_t ev_used_ = 0;

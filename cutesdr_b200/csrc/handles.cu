@@ -64,8 +64,9 @@ struct cutesdr_downconvert : HandleBase {
     Stager in;
     long long stream_pos = 0;
     int chunk = 0;
-    float2* d_tmp = nullptr;
-    ~cutesdr_downconvert() { if (st) cudaStreamSynchronize(st); dec.reset(); cudaFree(d_tmp); close(); }
+    float2* d_halo[2] = {nullptr, nullptr};
+    int halo_cur = 0;
+    ~cutesdr_downconvert() { if (st) cudaStreamSynchronize(st); dec.reset(); cudaFree(d_halo[0]); cudaFree(d_halo[1]); close(); }
 
     int build()
     {
@@ -76,9 +77,12 @@ struct cutesdr_downconvert : HandleBase {
         dec.reset(new Decimator());
         CSDR_TRY(dec->init(1, in_rate, max_bw, chunk, st, &lc));
         dec->set_frequency(0, nco_freq);
-        CSDR_TRY(in.ensure(chunk, kHaloMax));
-        if (!d_tmp) CSDR_CK(cudaMalloc(&d_tmp, kHaloMax * sizeof(float2)));
-        CSDR_CK(cudaMemsetAsync(in.d, 0, (size_t)(kHaloMax + in.cap) * sizeof(float2), st));
+        CSDR_TRY(in.ensure(chunk, 0));
+        for (int k = 0; k < 2; k++) {
+            if (!d_halo[k]) CSDR_CK(cudaMalloc(&d_halo[k], kHaloMax * sizeof(float2)));
+            CSDR_CK(cudaMemsetAsync(d_halo[k], 0, kHaloMax * sizeof(float2), st));
+        }
+        halo_cur = 0;
         return CUTESDR_OK;
     }
 
@@ -97,10 +101,8 @@ struct cutesdr_downconvert : HandleBase {
             for (int i = 0; i < m; i++) in.h[i] = make_float2((float)src[2 * (done + i)], (float)src[2 * (done + i) + 1]);
             CSDR_CK(cudaMemcpyAsync(in.data(), in.h, (size_t)m * sizeof(float2), cudaMemcpyHostToDevice, st));
             CSDR_TRY(apply_nco_startup_gain(in.data(), stream_pos, m, st, &lc));
-            CSDR_TRY(dec->run_block(in.data(), m));
-            // the last kHaloMax samples of [old halo | data] become the next call's halo
-            CSDR_CK(cudaMemcpyAsync(d_tmp, in.d + m, (size_t)kHaloMax * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-            CSDR_CK(cudaMemcpyAsync(in.d, d_tmp, (size_t)kHaloMax * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+            CSDR_TRY(dec->run_block(in.data(), d_halo[halo_cur], d_halo[halo_cur ^ 1], m));
+            halo_cur ^= 1;
             stream_pos += m;
             const int k = m / dec_by;
             tmp.resize(k);

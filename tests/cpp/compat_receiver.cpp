@@ -35,10 +35,12 @@ int main(int argc, char** argv)
     const double freq = atof(argv[6]);
     const int fftsize = atoi(argv[7]);
 
-    CNoiseProc m_NoiseProc;
-    CFft m_Fft;
-    CDemodulator m_Demodulator;
-    CFractResampler m_OutResampler;
+    // static storage = zero-initialised before construction: the reference's CDemodulator leaves
+    // m_pFmDemod (and others) uninitialised and deletes it in SetDemod (dsp/demodulator.cpp:47-60,80-81)
+    static CNoiseProc m_NoiseProc;
+    static CFft m_Fft;
+    static CDemodulator m_Demodulator;
+    static CFractResampler m_OutResampler;
 
     m_NoiseProc.SetupBlanker(false, 50.0, 2.0, fs);
     m_Fft.SetFFTParams(fftsize, false, 0.0, fs);
