@@ -198,6 +198,7 @@ int cutesdr_bank::run_block(const float2* d_block, float* d_audio_out, int audio
         nmax = std::max(nmax, produced);
     }
     halo_cur ^= 1;      // kernel 1 saved this block's tail into the other halo buffer
+    last_block = d_block;
     stream_pos += L;
     block_index++;
     if (n_out_max) *n_out_max = nmax;
@@ -525,6 +526,15 @@ int cutesdr_bank_join(cutesdr_bank* b)
     std::lock_guard<std::mutex> lk(b->mu);
     CSDR_CK(cudaSetDevice(b->device));
     return b->join();
+}
+
+int cutesdr_bank_last_block(cutesdr_bank* b, const void** d_block, int* n)
+{
+    if (!b || !d_block) { set_error("last_block: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    *d_block = b->last_block;
+    if (n) *n = b->L;
+    return b->last_block ? CUTESDR_OK : CUTESDR_E_STATE;
 }
 
 int cutesdr_bank_stream(cutesdr_bank* b, void** stream)

@@ -67,6 +67,7 @@ struct cutesdr_bank {
     float2* d_x = nullptr;               // [L] staging of host / blanked blocks
     float2* d_halo[2] = {nullptr, nullptr};   // [kHaloMax] tail of the previous block (double buffer)
     int halo_cur = 0;
+    const float2* last_block = nullptr;  // device block of the most recent DSP block (after the blanker)
     float2* h_stage = nullptr;           // pinned staging of one block
     int h_fill = 0;
     long long stream_pos = 0;

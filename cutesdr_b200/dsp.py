@@ -121,6 +121,12 @@ class ReceiverBank:
         check(self.L.cutesdr_bank_kernel_time(self.h, int(which), C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def last_block(self):
+        """(device pointer, length) of the most recent DSP block after the noise blanker."""
+        p, n = C.c_void_p(), C.c_int()
+        check(self.L.cutesdr_bank_last_block(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
     def stream(self):
         s = C.c_void_p()
         check(self.L.cutesdr_bank_stream(self.h, C.byref(s)))

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "cutesdr_bank_process_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_synchronize": (C.c_int, [_vp]),
     "cutesdr_bank_join": (C.c_int, [_vp]),
+    "cutesdr_bank_last_block": (C.c_int, [_vp, _pp, _ip]),
     "cutesdr_bank_stream": (C.c_int, [_vp, _pp]),
     "cutesdr_bank_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "cutesdr_bank_kernel_timing": (C.c_int, [_vp, C.c_int]),

@@ -107,6 +107,11 @@ int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, voi
  * recorded on the main stream afterwards covers everything (used for device timing). */
 int cutesdr_bank_synchronize(cutesdr_bank* b);
 int cutesdr_bank_join(cutesdr_bank* b);
+/* Device pointer (complex64[n]) of the most recent DSP block as the channels saw it, i.e. after the
+ * noise blanker -- the samples CSdrInterface::ProcessIQData hands to the display FFT
+ * (interface/sdrinterface.cpp:884-909). Feed slices of it to cutesdr_fft_put_device. Valid until the
+ * next process call. */
+int cutesdr_bank_last_block(cutesdr_bank* b, const void** d_block, int* n);
 /* cudaStream_t of the bank, as void* (for event timing on the launching stream) */
 int cutesdr_bank_stream(cutesdr_bank* b, void** stream);
 /* kernels launched by this bank so far */

@@ -412,3 +412,64 @@ def test_bank_nbfm_resampled_100msps_config4_slice(lib, orc):
     iq = syn_iq(fs, 24 * 1001472, modes, carriers, seed=20264)
     _bank_vs_oracle(orc, fs, modes, carriers, infos, iq, check=[0, 7, 15], audio_rate=48000.0,
                     skip_by_mode={M.DEMOD_FM: 7 * 1024})
+
+
+def test_bank_config5_slice_blanker_spectrum_200msps(lib, orc):
+    # BASELINE config 5 shape on the "200 Msps" stream (200 294 400 sps): mixed AM/SAM/FM/USB with AGC
+    # (every 8th channel hang), noise blanker on (Thr 50, 50 us) with injected impulses, and a concurrent
+    # 65536-point averaged spectrum taken from the blanked block on the device. 8 channels / 16 blocks so
+    # the CPU oracle stays within about a minute.
+    fs = 200294400.0
+    nch = 8
+    L = 2002944
+    nblk = 16
+    modes = [[M.DEMOD_AM, M.DEMOD_SAM, M.DEMOD_FM, M.DEMOD_USB][c % 4] for c in range(nch)]
+    carriers = carrier_grid(nch, 39000.0) + 5.0e6
+    infos = [M.demod_info(m, HiCut=2800, LowCut=100, AgcHangOn=(c == 3)) if m == M.DEMOD_USB else
+             M.demod_info(m, AgcHangOn=(c % 8 == 0)) for c, m in enumerate(modes)]
+    iq = syn_iq(fs, nblk * L, modes, carriers, seed=20265)
+    imp = (np.arange(20) * (nblk * L // 21) + 12345).astype(np.int64)
+    iq[imp] += np.complex64(30000.0)
+    # ---- oracle: blanker -> (display FFT, N x CDemodulator), interface/sdrinterface.cpp:878-922
+    nb = orc.NoiseProc()
+    nb.SetupBlanker(True, 50.0, 50.0, fs)
+    blanked = nb.ProcessBlanker(iq.astype(np.complex128)).astype(np.complex64)
+    assert np.sum(blanked == 0) >= 20 * 4096          # width clamps at MAX_WIDTH 4096 samples
+    fa = orc.Fft()
+    fa.SetFFTParams(65536, False, 0.0, fs)
+    fa.SetFFTAve(4)
+    # ---- GPU bank
+    bank = cs.ReceiverBank(nch, fs)
+    bank.SetupNoiseProc(True, 50.0, 50.0)
+    for c in range(nch):
+        bank.SetDemod(c, modes[c], infos[c])
+        bank.SetDemodFreq(c, -carriers[c])
+    assert bank.block_length() == L
+    fb = cs.CFft()
+    fb.SetFFTParams(65536, False, 0.0, fs)
+    fb.SetFFTAve(4)
+    outs = [[] for _ in range(nch)]
+    for k in range(nblk):
+        audio, n_out = bank.ProcessData(iq[k * L:(k + 1) * L])
+        for c in range(nch):
+            outs[c].append(audio[c, :n_out[c]].copy())
+        # one spectrum frame per block from the block the channels saw
+        ptr, n = bank.last_block()
+        assert n == L
+        fb.put_device(ptr + 8 * 100000, 65536)
+        fa.PutInDisplayFFT(blanked[k * L + 100000:k * L + 100000 + 65536].astype(np.complex128))
+        for args in [(255, 1024, 0.0, -140.0, int(-fs / 2), int(fs / 2)), (600, 800, 0.0, -140.0, 4800000, 5200000)]:
+            ova, ya = fa.GetScreenIntegerFFTData(*args)
+            ovb, yb = fb.GetScreenIntegerFFTData(*args)
+            assert ova == ovb and np.max(np.abs(ya - yb)) <= 1
+    skip = {M.DEMOD_SAM: 3 * 1024, M.DEMOD_FM: 5 * 1024}
+    for c in range(nch):
+        a = orc.Demodulator()
+        a.SetInputSampleRate(fs)
+        a.SetDemod(modes[c], infos[c])
+        a.SetDemodFreq(-carriers[c])
+        ya = a.run(blanked)
+        yb = np.concatenate(outs[c])
+        assert len(ya) == len(yb) >= 7 * 1024, (len(ya), len(yb))
+        s = snr_db(ya[skip.get(modes[c], 0):], yb[skip.get(modes[c], 0):])
+        assert s > SNR_MIN, "channel %d mode %d: %.1f dB" % (c, modes[c], s)
