@@ -77,9 +77,11 @@ __device__ __forceinline__ void store_out(const OutDesc& od, long long row, int 
         od.p[(size_t)((od.base + row) & od.mask) * od.stride + c] = v;
 }
 
+// Explicit rounding/contraction: every inlined copy must round identically, otherwise the oscillator
+// (and with it every output bit) would depend on which code path produced it.
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return make_float2(__fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y)), __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
 }
 
 // exact oscillator seed from the 64-bit phase (turns * 2^64): angle = pi * (hi32 / 2^31)
@@ -255,10 +257,17 @@ __global__ void __launch_bounds__(256, 3) k_mix_cic(const float2* __restrict__ x
 
     const float2* tile = reinterpret_cast<const float2*>(smem4);
     const int nbody = n_load / B;
-    float2 S = make_float2(1.f, 0.f);
+    // The oscillator is re-seeded exactly (sincospi of the 64-bit phase) at ABSOLUTE body indices that
+    // are multiples of 8 (every 256 samples of the block) and rotated in float32 in between, so its
+    // values -- and therefore every output bit -- do not depend on how the block is cut into tiles
+    // (nor on the number of channels or GPUs that decided the tiling).
+    const int body0 = (t0 - H) / B;                                  // exact: B divides t0 and H; may be negative
+    const int lead = ((body0 % 8) + 8) % 8;                          // bodies since the last absolute seed point
+    float2 S = seed_osc(ph - (unsigned long long)lead * ph_step);
+    for (int i = 0; i < lead; i++) S = cmul(S, wg);
     long long q0 = (long long)((t0 - H) / G);          // index of the body's first CIC-chain output (exact: G | t0-H)
     for (int b = 0; b < nbody; b++) {
-        if ((b & 7) == 0) S = seed_osc(ph);            // exact re-seed: bounds recursion drift
+        if (((body0 + b) & 7) == 0) S = seed_osc(ph);
         float2 o = S;
         Body<NCIC, NHB, 0, B>::run(tile + b * B, o, w1, st, ev, hs, q0, em);
         S = cmul(S, wg);
@@ -297,7 +306,7 @@ __global__ void k_mix_cic_generic(const float2* __restrict__ x, const float2* __
     float2 o = make_float2(1.f, 0.f);
     long long q = -(long long)(H >> ncic);
     for (int i = -H; i < L; i++) {
-        if (((i + H) & 31) == 0) o = seed_osc(ph0 + (unsigned long long)(long long)(i + 1) * p.inc);
+        if ((i & 31) == 0 || i == -H) o = seed_osc(ph0 + (unsigned long long)(long long)(i + 1) * p.inc);
         float2 v = cmul(i >= 0 ? x[i] : halo_cur[kHaloMax + i], o);
         o = cmul(o, w1);
         int s = 0;

@@ -473,3 +473,87 @@ def test_bank_config5_slice_blanker_spectrum_200msps(lib, orc):
         assert len(ya) == len(yb) >= 7 * 1024, (len(ya), len(yb))
         s = snr_db(ya[skip.get(modes[c], 0):], yb[skip.get(modes[c], 0):])
         assert s > SNR_MIN, "channel %d mode %d: %.1f dB" % (c, modes[c], s)
+
+
+# ------------------------------------------------------------------------------------------------
+# Full BASELINE sizes: size-independent properties (the CPU oracle cannot run 1024-4096 channels)
+# ------------------------------------------------------------------------------------------------
+def _cheap_wideband(L, nblocks, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = L * nblocks
+    x = (300.0 * (rng.standard_normal(n, dtype=np.float32) + 1j * rng.standard_normal(n, dtype=np.float32))).astype(np.complex64)
+    t = np.arange(n, dtype=np.float64)
+    for k in range(6):
+        x += (1500.0 * np.exp(2j * np.pi * ((k - 2.5) * 0.0437) * t)).astype(np.complex64)
+    return x
+
+
+@pytest.mark.parametrize("fs,nch,nblk,spacing", [(100147200.0, 1024, 7, 78125.0), (200294400.0, 4096, 5, 39000.0),
+                                                 (20000000.0, 256, 12, 62500.0)])
+def test_full_size_bank_equals_independent_receivers(lib, fs, nch, nblk, spacing):
+    """A bank of N channels must give, per channel, exactly what N independent CDemodulator objects fed
+    the same IQ would: a channel's arithmetic does not depend on its neighbours, so the audio of
+    a channel inside the full-size bank is BIT-IDENTICAL to the same channel run alone."""
+    pick = [M.DEMOD_AM, M.DEMOD_SAM, M.DEMOD_FM, M.DEMOD_USB]
+    if fs == 20000000.0:
+        modes = [M.DEMOD_USB if c % 2 == 0 else M.DEMOD_LSB for c in range(nch)]
+    elif nch == 1024:
+        modes = [M.DEMOD_FM] * nch
+    else:
+        modes = [pick[c % 4] for c in range(nch)]
+    carriers = carrier_grid(nch, spacing)
+
+    def info(m):
+        if m == M.DEMOD_USB:
+            return M.demod_info(m, HiCut=2800, LowCut=100)
+        if m == M.DEMOD_LSB:
+            return M.demod_info(m, HiCut=-100, LowCut=-2800)
+        return M.demod_info(m)
+
+    bank = cs.ReceiverBank(nch, fs)
+    for c in range(nch):
+        bank.SetDemod(c, modes[c], info(modes[c]))
+        bank.SetDemodFreq(c, -carriers[c])
+    L = bank.block_length()
+    iq = _cheap_wideband(L, nblk, seed=31)
+    check = sorted(set(int(v) for v in np.random.default_rng(5).integers(0, nch, 6)) | {0, nch - 1})
+    big = {c: [] for c in check}
+    total = 0
+    for k in range(nblk):
+        audio, n_out = bank.ProcessData(iq[k * L:(k + 1) * L])
+        assert np.all((n_out == 0) | (n_out == 1024) | (n_out == 2048))
+        total += int(n_out.max())
+        for c in check:
+            big[c].append(audio[c, :n_out[c]].copy())
+    assert total >= 2048
+    del bank
+    for c in check:
+        one = cs.ReceiverBank(1, fs)
+        one.SetDemod(0, modes[c], info(modes[c]))
+        one.SetDemodFreq(0, -carriers[c])
+        audio, n_out = one.ProcessData(iq)
+        ya = np.concatenate(big[c])
+        yb = audio[0, :n_out[0]]
+        assert len(ya) == len(yb) > 0
+        assert np.array_equal(ya, yb), "channel %d differs between the %d-channel bank and a bank of one" % (c, nch)
+        assert np.all(np.isfinite(ya))
+
+
+def test_full_size_linearity_of_the_front_end(lib):
+    """NCO mix + CIC/half-band cascade + FFT band-pass are linear: scaling the input by a power of two
+    scales the PROFILE_2 tap by exactly that factor (bit-exact in float32), at the full 1 001 472-sample block."""
+    fs = 100147200.0
+    outs = []
+    for scale in (1.0, 0.25):
+        bank = cs.ReceiverBank(2, fs)
+        for c in range(2):
+            bank.SetDemod(c, M.DEMOD_FM, M.demod_info(M.DEMOD_FM))
+            bank.SetDemodFreq(c, -1.0e6 * (c + 1))
+        bank.tap_enable(1, (2,))
+        L = bank.block_length()
+        iq = _cheap_wideband(L, 6, seed=32)
+        # skip the oscillator start-up window (its amplitude factors are not powers of two)
+        bank.ProcessData((iq * np.float32(scale)).astype(np.complex64))
+        outs.append(bank.tap_read(1, 2))
+    assert len(outs[0]) == len(outs[1]) >= 2048
+    assert np.array_equal(outs[0][1024:] * np.float32(0.25), outs[1][1024:])
