@@ -112,7 +112,11 @@ int cutesdr_bank::rebuild()
         g->chans = kv.second;
         std::stable_sort(g->chans.begin(), g->chans.end(), [&](int a, int c2) { return ch[a].mode < ch[c2].mode; });
         const int n = (int)g->chans.size();
-        CSDR_CK(cudaStreamCreateWithFlags(&g->st_post, cudaStreamNonBlocking));
+        {   // burst kernels get scheduled ahead of kernel 1's queued CTAs whenever an SM slot frees up
+            int lo = 0, hi = 0;
+            CSDR_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CSDR_CK(cudaStreamCreateWithPriority(&g->st_post, cudaStreamNonBlocking, hi));
+        }
         CSDR_CK(cudaEventCreateWithFlags(&g->ev_dec, cudaEventDisableTiming));
         for (auto& e : g->ev_post) CSDR_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CSDR_TRY(g->dec.init(n, in_rate, g->max_bw, L, st, &lc));

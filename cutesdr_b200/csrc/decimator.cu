@@ -351,72 +351,54 @@ static K1Fn k1_kernel(int ncic, int nhb)
 
 // ------------------------------------------------------------------------------------------
 // K2a: NS consecutive 11-tap half-band stages in ONE pass over HBM (the stages right after
-// kernel 1 carry most of kernel 2's traffic). Lane = channel, sequential over a time tile with the
-// delay lines in registers; a body is 2^NS input rows (loaded up front: 2^NS independent coalesced
-// 256-byte row reads in flight per warp), so every stage's even/odd phase is a compile-time constant.
-// Tiles overlap by 10*(2^NS-1) input rows (rounded up to a body) that re-prime the delay lines.
+// kernel 1 carry most of kernel 2's traffic). A CTA owns 32 channels x T final outputs: it stages
+// the 2^NS*T + halo input rows in shared memory (all 8 warps issue whole-row 256-byte loads, ~30 in
+// flight per warp), then runs the stages time-parallel out of shared memory (lane = channel, so a
+// warp reads one row per LDS.64, conflict-free), each stage writing the next stage's rows, the last
+// one writing HBM. Only the first stage's input and the last stage's output touch HBM.
+// Row counts: c[NS] = T, c[j] = 2 c[j+1] + 9 (an output needs inputs 2m-10 .. 2m).
 // ------------------------------------------------------------------------------------------
-template <int NS, int J, int IDX>
-__device__ __forceinline__ void hbc_feed(float2 v, Hb11St* hs, float h0, float h2, float h4, float2& out, bool& have)
-{
-    if constexpr (J == NS) {
-        out = v;
-        have = true;
-    } else {
-        Hb11St& s = hs[J];
-        if constexpr ((IDX & 1) == 0) {
-            float2 y;
-            y.x = fmaf(h0, s.e[4].x + v.x, fmaf(h2, s.e[3].x + s.e[0].x, fmaf(h4, s.e[2].x + s.e[1].x, 0.5f * s.o[2].x)));
-            y.y = fmaf(h0, s.e[4].y + v.y, fmaf(h2, s.e[3].y + s.e[0].y, fmaf(h4, s.e[2].y + s.e[1].y, 0.5f * s.o[2].y)));
-            s.e[4] = s.e[3]; s.e[3] = s.e[2]; s.e[2] = s.e[1]; s.e[1] = s.e[0]; s.e[0] = v;
-            hbc_feed<NS, J + 1, (IDX >> 1)>(y, hs, h0, h2, h4, out, have);
-        } else {
-            s.o[2] = s.o[1]; s.o[1] = s.o[0]; s.o[0] = v;
-        }
-    }
-}
-
-template <int NS, int K> struct HbcBody {
-    static __device__ __forceinline__ void run(const float2* x, Hb11St* hs, float h0, float h2, float h4, float2& out, bool& have)
-    {
-        hbc_feed<NS, 0, K>(x[K], hs, h0, h2, h4, out, have);
-        HbcBody<NS, K + 1>::run(x, hs, h0, h2, h4, out, have);
-    }
-};
-template <int NS> struct HbcBody<NS, (1 << NS)> {
-    static __device__ __forceinline__ void run(const float2*, Hb11St*, float, float, float, float2&, bool&) {}
+template <int NS, int T> struct HbcCfg {
+    static constexpr int c(int j) { return j >= NS ? T : 2 * c(j + 1) + 9; }
+    static constexpr int smem_rows() { return NS == 2 ? c(0) + c(1) : c(0) + c(1) + c(2); }
 };
 
-template <int NS>
-__global__ void __launch_bounds__(128) k_hb11_chain(const float2* __restrict__ in, unsigned in_mask, long long in_base, int stride,
-                                                    int n_out, int tile_out, OutDesc od)
+template <int NS, int T>
+__global__ void __launch_bounds__(256) k_hb11_chain(const float2* __restrict__ in, unsigned in_mask, long long in_base, int stride,
+                                                    int n_out, OutDesc od)
 {
-    constexpr int R = 1 << NS;
-    constexpr int HALO = (10 * (R - 1) + R - 1) / R * R;        // input rows, whole bodies
-    const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    if (c >= stride) return;
-    const int o0 = blockIdx.x * tile_out;
-    const int o1 = min(o0 + tile_out, n_out);
+    typedef HbcCfg<NS, T> Cfg;
+    extern __shared__ float2 sm_rows[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + lane;
+    const bool live = c < stride;
+    const int o0 = blockIdx.x * T;
     const float h0 = c_hb_taps[0], h2 = c_hb_taps[1], h4 = c_hb_taps[2];
-    Hb11St hs[NS];
+    // first input row of every stage for this tile: lo[NS] = o0, lo[j] = 2 lo[j+1] - 10
+    long long lo0 = o0;
 #pragma unroll
-    for (int s = 0; s < NS; s++) {
+    for (int j = 0; j < NS; j++) lo0 = 2 * lo0 - 10;
+    float2* buf = sm_rows;
+    if (live)
+        for (int r = warp; r < Cfg::c(0); r += 8) buf[r * 32 + lane] = in[(size_t)((in_base + lo0 + r) & in_mask) * stride + c];
+    __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 5; k++) hs[s].e[k] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 3; k++) hs[s].o[k] = make_float2(0.f, 0.f);
-    }
-    // output o is complete when input row o*R arrives (newest tap of every stage is an even index):
-    // bodies are aligned so that row o*R is a body's FIRST row
-    for (int o = o0 - HALO / R; o < o1; o++) {
-        const long long row0 = in_base + (long long)o * R;
-        float2 x[R];
-#pragma unroll
-        for (int k = 0; k < R; k++) x[k] = in[(size_t)((row0 + k) & in_mask) * stride + c];
-        float2 y = make_float2(0.f, 0.f);
-        bool have = false;
-        HbcBody<NS, 0>::run(x, hs, h0, h2, h4, y, have);
-        if (have && o >= o0) store_out(od, o, c, y);
+    for (int j = 0; j < NS; j++) {
+        const int n_j = Cfg::c(j + 1);             // outputs of this stage
+        float2* nxt = buf + Cfg::c(j) * 32;
+        if (live) {
+            for (int i = warp; i < n_j; i += 8) {
+                const float2* x = buf + (2 * i) * 32 + lane;
+                const float2 a0 = x[0], a2 = x[2 * 32], a4 = x[4 * 32], a5 = x[5 * 32], a6 = x[6 * 32], a8 = x[8 * 32], a10 = x[10 * 32];
+                float2 y;
+                y.x = fmaf(h0, a0.x + a10.x, fmaf(h2, a2.x + a8.x, fmaf(h4, a4.x + a6.x, 0.5f * a5.x)));
+                y.y = fmaf(h0, a0.y + a10.y, fmaf(h2, a2.y + a8.y, fmaf(h4, a4.y + a6.y, 0.5f * a5.y)));
+                if (j + 1 < NS) nxt[i * 32 + lane] = y;
+                else if (o0 + i < n_out) store_out(od, o0 + i, c, y);
+            }
+        }
+        if (j + 1 < NS) __syncthreads();
+        buf = nxt;
     }
 }
 
@@ -784,16 +766,23 @@ int Decimator::run_block(const float2* d_x, const float2* halo_cur, float2* halo
                 o2.transposed = 1;
                 o2.base = total_out_;
             }
-            const int threads = std::min(128, round_up(stride_, 32));
-            const int chan_blocks = (stride_ + threads - 1) / threads;
-            // ~16 CTAs per SM in flight; tiles no shorter than ~8 halos
-            const int halo_out = (10 * ((1 << nchain) - 1) + (1 << nchain) - 1) >> nchain;
-            int tiles = std::max(1, (148 * 16) / chan_blocks);
-            int tile_out = std::max((n_out + tiles - 1) / tiles, 8 * halo_out);
-            dim3 grid((n_out + tile_out - 1) / tile_out, chan_blocks);
             const unsigned mask0 = (unsigned)(stage_rows_[0] - 1);
-            if (nchain == 2) k_hb11_chain<2><<<grid, threads, 0, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, tile_out, o2);
-            else k_hb11_chain<3><<<grid, threads, 0, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, tile_out, o2);
+            const int chan_blocks = (stride_ + 31) / 32;
+            if (nchain == 2) {
+                constexpr int T = 48;
+                const size_t smem = (size_t)HbcCfg<2, T>::smem_rows() * 32 * sizeof(float2);
+                static bool attr2 = false;
+                if (!attr2) { CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr2 = true; }
+                dim3 grid((n_out + T - 1) / T, chan_blocks);
+                k_hb11_chain<2, T><<<grid, 256, smem, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, o2);
+            } else {
+                constexpr int T = 24;
+                const size_t smem = (size_t)HbcCfg<3, T>::smem_rows() * 32 * sizeof(float2);
+                static bool attr3 = false;
+                if (!attr3) { CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<3, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr3 = true; }
+                dim3 grid((n_out + T - 1) / T, chan_blocks);
+                k_hb11_chain<3, T><<<grid, 256, smem, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, o2);
+            }
             lc_->n++;
             CSDR_CK(cudaGetLastError());
             for (int s = 0; s < nchain; s++) stage_base_[s] += (L >> (k1_stages() + s));

@@ -96,6 +96,7 @@ struct PostBufs {
     double* smag; double* peak; float2* z; double* u; double* th; int row;   // [c][max_n]
     double* v; int v_row;          // [c][kHist + max_n]
     const double* par; const double* taps; const int* mode; int* reset;
+    const double* qpow;            // [max_n + 1] powers of (1 - squelch alpha)
     double* state; int* istate;
     int nch, stride;
 };
@@ -195,11 +196,13 @@ __device__ __forceinline__ void store16(double* __restrict__ p, const double* v)
     for (int i = 0; i < 8; i++) q[i] = make_double2(v[2 * i], v[2 * i + 1]);
 }
 
-// ---- sequential poles; 64-thread CTA = 32 channels x {AGC averagers (warp 0), S-meter (warp 1)}
-__global__ void __launch_bounds__(64) k_post_seq1(PostBufs b, int n, PostUniform u)
+// ---- sequential poles; one warp per CTA: even CTAs run the AGC averagers of 32 channels, odd CTAs
+// the S-meter of the same channels. 32 threads x <= 128 registers = 4096 registers, which is what is
+// left beside kernel 1's three resident CTAs, so these latency-bound loops run UNDER kernel 1.
+__global__ void __maxnreg__(128) k_post_seq1(PostBufs b, int n, PostUniform u)
 {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const bool smeter_warp = threadIdx.x >= 32;
+    const int c = (blockIdx.x >> 1) * 32 + threadIdx.x;
+    const bool smeter_warp = (blockIdx.x & 1) != 0;
     if (c >= b.nch) return;
     const int mode = b.mode[c];
     const int n16 = n & ~15;
@@ -312,7 +315,7 @@ __device__ __forceinline__ double wrap_pi(double d)
 }
 
 // ---- DC blockers and PLLs; thread per channel
-__global__ void __launch_bounds__(32) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
+__global__ void __maxnreg__(128) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
                                                   int audio_stride, int audio_off, const int* __restrict__ chan_map)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -433,11 +436,10 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
     // |high-passed audio|; only its value at the END of the burst is used, which is the weighted sum
     //   (1-a)^n s0 + a * sum_t (1-a)^(n-1-t) |hp[t]|
     double part = 0.0;
-    const double q = 1.0 - u.fm_sq_alpha;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
         double acc = 0.0;
         for (int k = 0; k < ntaps; k++) acc += h[k] * v[kHist + t - k];
-        part += fabs(acc) * pow(q, (double)(n - 1 - t));
+        part += fabs(acc) * b.qpow[n - 1 - t];
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
     if (threadIdx.x == 0) {
         double sum = 0.0;
         for (int w = 0; w < 8; w++) sum += red[w];
-        const double sq_ave = pow(q, (double)n) * ST(S_SQ_AVE) + u.fm_sq_alpha * sum;
+        const double sq_ave = b.qpow[n] * ST(S_SQ_AVE) + u.fm_sq_alpha * sum;
         ST(S_SQ_AVE) = sq_ave;
         int squelched = IST(I_SQUELCHED);
         const double sq_thresh = PAR(P_SQ_THRESH);
@@ -458,9 +460,25 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
         if (!squelched) {
             // 3 kHz low-pass biquad only runs while the squelch is open, CIir::ProcessFilter dsp/iir.cpp:171-180
             double w1 = ST(S_LP_W1), w2 = ST(S_LP_W2);
-            for (int t = 0; t < n; t++) {
-                const double w0 = v[kHist + t] - u.lp_a1 * w1 - u.lp_a2 * w2;
-                v[kHist + t] = u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2;
+            double* vv = v + kHist;
+            int t = 0;
+            for (; t + 8 <= n; t += 8) {        // 8 samples per trip in registers: the loop is one dependent chain
+                double r[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) r[k] = vv[t + k];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const double w0 = r[k] - u.lp_a1 * w1 - u.lp_a2 * w2;
+                    r[k] = u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2;
+                    w2 = w1;
+                    w1 = w0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) vv[t + k] = r[k];
+            }
+            for (; t < n; t++) {
+                const double w0 = vv[t] - u.lp_a1 * w1 - u.lp_a2 * w2;
+                vv[t] = u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2;
                 w2 = w1;
                 w1 = w0;
             }
@@ -484,7 +502,7 @@ PostBank::~PostBank()
 {
     cudaFree(d_par_); cudaFree(d_taps_); cudaFree(d_mode_); cudaFree(d_reset_); cudaFree(d_state_);
     cudaFree(d_istate_); cudaFree(d_y_); cudaFree(d_magh_); cudaFree(d_smag_); cudaFree(d_peak_); cudaFree(d_z_);
-    cudaFree(d_u_); cudaFree(d_th_); cudaFree(d_v_);
+    cudaFree(d_u_); cudaFree(d_th_); cudaFree(d_v_); cudaFree(d_qpow_);
 }
 
 int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream_t st, LaunchCounter* lc)
@@ -548,6 +566,14 @@ int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream
     CSDR_CK(cudaMalloc(&d_u_, rows * max_n_ * sizeof(double)));
     CSDR_CK(cudaMalloc(&d_th_, rows * max_n_ * sizeof(double)));
     CSDR_CK(cudaMalloc(&d_v_, rows * v_row_ * sizeof(double)));
+    {
+        std::vector<double> qp(max_n_ + 1);
+        const double q = 1.0 - uni_.fm_sq_alpha;
+        qp[0] = 1.0;
+        for (int j = 1; j <= max_n_; j++) qp[j] = qp[j - 1] * q;
+        CSDR_CK(cudaMalloc(&d_qpow_, qp.size() * sizeof(double)));
+        CSDR_CK(cudaMemcpy(d_qpow_, qp.data(), qp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     CSDR_CK(cudaMemsetAsync(d_state_, 0, (size_t)S_COUNT * stride * sizeof(double), st_));
     CSDR_CK(cudaMemsetAsync(d_istate_, 0, (size_t)I_COUNT * stride * sizeof(int), st_));
     CSDR_CK(cudaMemsetAsync(d_y_, 0, rows * y_row_ * sizeof(float2), st_));
@@ -656,7 +682,7 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
     PostBufs b;
     b.y = d_y_; b.y_row = y_row_; b.magh = d_magh_; b.smag = d_smag_; b.peak = d_peak_; b.z = d_z_; b.u = d_u_; b.th = d_th_;
     b.row = max_n_; b.v = d_v_; b.v_row = v_row_; b.par = d_par_; b.taps = d_taps_; b.mode = d_mode_; b.reset = d_reset_;
-    b.state = d_state_; b.istate = d_istate_; b.nch = nch_; b.stride = stride_;
+    b.state = d_state_; b.istate = d_istate_; b.nch = nch_; b.stride = stride_; b.qpow = d_qpow_;
     if (need_reset_kernel_) {
         k_post_reset<<<nch_, 128, 0, st_>>>(b);
         lc_->n++;
@@ -666,7 +692,7 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
     const size_t smem_fir = (size_t)(kHist + max_n_ + kFirMax) * sizeof(double);
     const int seq_blocks = (nch_ + 31) / 32;
     k_post_pre<<<nch_, 256, smem_pre, st_>>>(b, n, uni_.agc_window);
-    k_post_seq1<<<seq_blocks, 64, 0, st_>>>(b, n, uni_);
+    k_post_seq1<<<2 * seq_blocks, 32, 0, st_>>>(b, n, uni_);
     k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_seq2<<<seq_blocks, 32, 0, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_fir<<<nch_, 256, smem_fir, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);

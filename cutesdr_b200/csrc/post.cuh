@@ -85,6 +85,7 @@ private:
     double* d_u_ = nullptr;         // [nch][max_n]            envelope (AM/SAM)
     double* d_th_ = nullptr;        // [nch][max_n]            phase angle (SAM/FM)
     double* d_v_ = nullptr;         // [nch][kHist + max_n]    FIR input with history (AM post filter / FM squelch)
+    double* d_qpow_ = nullptr;      // [max_n+1] powers of (1 - squelch alpha)
     int y_row_ = 0, v_row_ = 0;
 };
 

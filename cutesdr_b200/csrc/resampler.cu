@@ -21,25 +21,48 @@ void ResampleClock::advance(int n_in, double rate, std::vector<double>& times)
     t_ -= (double)n_in;
 }
 
-// w: [nrows][row_len], row = 28 carried samples then the new inputs.
+// Pass 1 (one small launch): every row of a bank shares the output times, hence the truncated table
+// indices and the 28 weights of every output. They are looked up ONCE into wts[k][28] (+ the integer
+// input position), turning the per-row work of pass 2 into a dense 28-tap dot product without gathers.
+__global__ void __launch_bounds__(128) k_resample_weights(const double* __restrict__ times, int n_out,
+                                                          const float* __restrict__ sinc, float* __restrict__ wts,
+                                                          int* __restrict__ pos)
+{
+    const int k = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int i = (threadIdx.x & 31) + 1;
+    if (k >= n_out) return;
+    const double t = times[k];
+    const int it = (int)t;
+    if (i == 1) pos[k] = it;
+    if (i <= kRsPeriods) {
+        const int j = it + i;
+        const int s = (int)(((double)j - t) * (double)kRsPts);      // dsp/fractresampler.cpp:168
+        wts[(size_t)k * kRsPeriods + (i - 1)] = __ldg(sinc + s);
+    }
+}
+
+// Pass 2: w: [nrows][row_len], row = 28 carried samples then the new inputs. Thread per (output, row);
+// consecutive lanes take consecutive outputs of one row (inputs and weights stream, no table access).
 __global__ void __launch_bounds__(128) k_resample(const float* __restrict__ w, int row_len, int nrows,
-                                                  const double* __restrict__ times, int n_out,
-                                                  const float* __restrict__ sinc, float* __restrict__ out, int out_stride,
+                                                  const float* __restrict__ wts, const int* __restrict__ pos, int n_out,
+                                                  float* __restrict__ out, int out_stride,
                                                   int out_off, const int* __restrict__ row_map,
                                                   int16_t* __restrict__ out16, float gain, int interleave16)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (k >= n_out) return;
-    const double t = times[k];
-    const int it = (int)t;
-    const float* x = w + (size_t)r * row_len;
+    const float* x = w + (size_t)r * row_len + pos[k];
+    const float4* c4 = reinterpret_cast<const float4*>(wts + (size_t)k * kRsPeriods);
     float acc = 0.f;
-#pragma unroll 4
-    for (int i = 1; i <= kRsPeriods; i++) {
-        const int j = it + i;
-        const int s = (int)(((double)j - t) * (double)kRsPts);      // dsp/fractresampler.cpp:168
-        acc = fmaf(x[j], __ldg(sinc + s), acc);
+#pragma unroll
+    for (int q = 0; q < kRsPeriods / 4; q++) {
+        const float4 c = __ldg(c4 + q);
+        // same accumulation order as the reference loop i = 1..28
+        acc = fmaf(x[4 * q + 1], c.x, acc);
+        acc = fmaf(x[4 * q + 2], c.y, acc);
+        acc = fmaf(x[4 * q + 3], c.z, acc);
+        acc = fmaf(x[4 * q + 4], c.w, acc);
     }
     if (out16) {
         float v = acc * gain;                                       // :228-239 gain, clip, truncate
@@ -76,6 +99,8 @@ ResamplerBank::~ResamplerBank()
     cudaFree(d_w_);
     cudaFree(d_sinc_);
     cudaFree(d_times_);
+    cudaFree(d_wts_);
+    cudaFree(d_pos_);
 }
 
 int ResamplerBank::init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc)
@@ -112,16 +137,21 @@ int ResamplerBank::run(int n_in, double rate, float* d_out, int out_stride, int 
         if (m > times_cap_) {
             CSDR_CK(cudaStreamSynchronize(st_));
             cudaFree(d_times_);
+            cudaFree(d_wts_);
+            cudaFree(d_pos_);
             times_cap_ = std::max(m, 2 * times_cap_) + 64;
             CSDR_CK(cudaMalloc(&d_times_, times_cap_ * sizeof(double)));
+            CSDR_CK(cudaMalloc(&d_wts_, (size_t)times_cap_ * kRsPeriods * sizeof(float)));
+            CSDR_CK(cudaMalloc(&d_pos_, times_cap_ * sizeof(int)));
         }
         k_resample_times<<<1, 32, 0, st_>>>(t0, rate, m, d_times_);
         lc_->n++;
         if (d_out || d_out16) {
             dim3 grid((m + 127) / 128, nrows_);
-            k_resample<<<grid, 128, 0, st_>>>(d_w_, row_len_, nrows_, d_times_, m, d_sinc_, d_out, out_stride, out_off,
+            k_resample_weights<<<(m + 3) / 4, 128, 0, st_>>>(d_times_, m, d_sinc_, d_wts_, d_pos_);
+            k_resample<<<grid, 128, 0, st_>>>(d_w_, row_len_, nrows_, d_wts_, d_pos_, m, d_out, out_stride, out_off,
                                               d_row_map, d_out16, (float)gain, interleave16);
-            lc_->n++;
+            lc_->n += 2;
             CSDR_CK(cudaGetLastError());
         }
     }

@@ -51,6 +51,8 @@ private:
     float* d_w_ = nullptr;        // [nrows][28 + max_in] : 28 carried inputs, then the new ones
     float* d_sinc_ = nullptr;     // [kRsLen]
     double* d_times_ = nullptr;
+    float* d_wts_ = nullptr;      // [outputs][28] weights shared by all rows
+    int* d_pos_ = nullptr;        // [outputs] integer input position
     int times_cap_ = 0;
     std::vector<double> times_;
 };
