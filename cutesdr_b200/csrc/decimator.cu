@@ -379,8 +379,19 @@ __global__ void __launch_bounds__(256) k_hb11_chain(const float2* __restrict__ i
 #pragma unroll
     for (int j = 0; j < NS; j++) lo0 = 2 * lo0 - 10;
     float2* buf = sm_rows;
-    if (live)
-        for (int r = warp; r < Cfg::c(0); r += 8) buf[r * 32 + lane] = in[(size_t)((in_base + lo0 + r) & in_mask) * stride + c];
+    {
+        // stage the input rows with cp.async (LDGSTS): 16 bytes = 2 channels per lane, two rows per
+        // warp instruction, no registers held -- the whole tile (c(0) x 256 B) is in flight at once
+        const int half = lane >> 4, l16 = lane & 15;
+        const int cbase = blockIdx.y * 32 + 2 * l16;
+        for (int r = 2 * warp + half; r < Cfg::c(0); r += 16) {
+            const float2* g = in + (size_t)((in_base + lo0 + r) & in_mask) * stride + cbase;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + r * 32 + 2 * l16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < NS; j++) {
@@ -391,8 +402,9 @@ __global__ void __launch_bounds__(256) k_hb11_chain(const float2* __restrict__ i
                 const float2* x = buf + (2 * i) * 32 + lane;
                 const float2 a0 = x[0], a2 = x[2 * 32], a4 = x[4 * 32], a5 = x[5 * 32], a6 = x[6 * 32], a8 = x[8 * 32], a10 = x[10 * 32];
                 float2 y;
-                y.x = fmaf(h0, a0.x + a10.x, fmaf(h2, a2.x + a8.x, fmaf(h4, a4.x + a6.x, 0.5f * a5.x)));
-                y.y = fmaf(h0, a0.y + a10.y, fmaf(h2, a2.y + a8.y, fmaf(h4, a4.y + a6.y, 0.5f * a5.y)));
+                // same operation order as k_halfband, so a stage gives identical bits on either path
+                y.x = fmaf(h4, a4.x + a6.x, fmaf(h2, a2.x + a8.x, fmaf(h0, a0.x + a10.x, 0.5f * a5.x)));
+                y.y = fmaf(h4, a4.y + a6.y, fmaf(h2, a2.y + a8.y, fmaf(h0, a0.y + a10.y, 0.5f * a5.y)));
                 if (j + 1 < NS) nxt[i * 32 + lane] = y;
                 else if (o0 + i < n_out) store_out(od, o0 + i, c, y);
             }
@@ -749,7 +761,7 @@ int Decimator::run_block(const float2* d_x, const float2* halo_cur, float2* halo
         // leading run of 11-tap stages -> one fused pass
         int nchain = 0;
         while (nchain < 3 && nchain < nhb && lens_[k1_stages() + nchain] == 11) nchain++;
-        if (nchain >= 2 && !getenv("CUTESDR_NO_HBCHAIN")) {
+        if (nchain >= 2 && stride_ % 32 == 0 && !getenv("CUTESDR_NO_HBCHAIN")) {
             const int n_in = L >> k1_stages();
             const int n_out = n_in >> nchain;
             OutDesc o2;
