@@ -159,13 +159,33 @@ __device__ __forceinline__ void hb_feed(float2 v, long long q, Hb11St* hs, const
     }
 }
 
+// First fused half-band when a body carries an EVEN number of CIC outputs (B/G >= 2): tiles start on
+// multiples of 2G, so the body's CIC output IDX is even-indexed iff IDX is even -- a compile-time
+// fact, no branch, and the compiler can keep the delay line in fixed registers.
+template <int NHB, int IDX>
+__device__ __forceinline__ void hb_feed_static(float2 v, int q0, Hb11St* hs, const EmitCtx& em)
+{
+    Hb11St& s = hs[0];
+    if constexpr ((IDX & 1) == 0) {
+        float2 y;
+        y.x = fmaf(em.h0, s.e[4].x + v.x, fmaf(em.h2, s.e[3].x + s.e[0].x, fmaf(em.h4, s.e[2].x + s.e[1].x, 0.5f * s.o[2].x)));
+        y.y = fmaf(em.h0, s.e[4].y + v.y, fmaf(em.h2, s.e[3].y + s.e[0].y, fmaf(em.h4, s.e[2].y + s.e[1].y, 0.5f * s.o[2].y)));
+        s.e[4] = s.e[3]; s.e[3] = s.e[2]; s.e[2] = s.e[1]; s.e[1] = s.e[0]; s.e[0] = v;
+        hb_feed<NHB, 1>(y, (long long)((q0 + IDX) >> 1), hs, em);
+    } else {
+        s.o[2] = s.o[1]; s.o[1] = s.o[0]; s.o[0] = v;
+    }
+}
+
 // CIC3 decimate-by-2, scale .125 folded into the kernel's output scale
 // (y = odd + Xeven + 3*(Xodd + even), dsp/downconvert.cpp:450-455).
 template <int NCIC, int NHB, int S, int IDX>
 __device__ __forceinline__ void cic_feed(float2 v, CicSt* st, float2* ev, Hb11St* hs, long long q0, const EmitCtx& em)
 {
     if constexpr (S == NCIC) {
-        hb_feed<NHB, 0>(v, q0 + IDX, hs, em);
+        constexpr int G = 1 << NCIC, B = G < 32 ? 32 : G;
+        if constexpr (NHB >= 1 && (B / G) >= 2) hb_feed_static<NHB, IDX>(v, (int)q0, hs, em);
+        else hb_feed<NHB, 0>(v, q0 + IDX, hs, em);
     } else if constexpr ((IDX & 1) == 0) {
         ev[S] = v;
     } else {
