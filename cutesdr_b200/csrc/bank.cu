@@ -48,6 +48,14 @@ cutesdr_bank::~cutesdr_bank()
     groups.clear();
     nb.reset();
     cudaFree(d_x);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(d_xs[k]);
+        if (ev_h2d[k]) cudaEventDestroy(ev_h2d[k]);
+        if (ev_free[k]) cudaEventDestroy(ev_free[k]);
+    }
+    if (ev_d2h) cudaEventDestroy(ev_d2h);
+    if (st_h2d) { cudaStreamSynchronize(st_h2d); cudaStreamDestroy(st_h2d); }
+    if (st_d2h) { cudaStreamSynchronize(st_d2h); cudaStreamDestroy(st_d2h); }
     cudaFree(d_halo[0]);
     cudaFree(d_halo[1]);
     cudaFree(d_audio);
@@ -97,6 +105,7 @@ int cutesdr_bank::rebuild()
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr;
         CSDR_CK(cudaMalloc(&d_x, (size_t)L * sizeof(float2)));
+        for (int k = 0; k < 2; k++) { cudaFree(d_xs[k]); d_xs[k] = nullptr; }
         for (int k = 0; k < 2; k++) if (!d_halo[k]) CSDR_CK(cudaMalloc(&d_halo[k], (size_t)kHaloMax * sizeof(float2)));
         CSDR_CK(cudaHostAlloc(&h_stage, (size_t)L * sizeof(float2), cudaHostAllocDefault));
         h_fill = 0;
@@ -174,6 +183,7 @@ int cutesdr_bank::run_block(const float2* d_block, float* d_audio_out, int audio
         const int n = nbursts * kBurst;
         if (n > kMaxBurstSamples) { set_error("more than %d FIR bursts in one DSP block", kMaxBurstSamples / kBurst); return CUTESDR_E_STATE; }
         CSDR_CK(cudaStreamWaitEvent(g.st_post, g.dec.done_event(), 0));
+        if (d2h_pending) CSDR_CK(cudaStreamWaitEvent(g.st_post, ev_d2h, 0));
         CSDR_TRY(g.fir.run(g.dec.ring(), g.bursts_done, nbursts, g.post.y_in(), g.post.y_stride()));
         g.bursts_done += nbursts;
         g.last_fir_n = n;
@@ -223,6 +233,9 @@ int cutesdr_bank::sync_all()
 {
     CSDR_TRY(join());
     CSDR_CK(cudaStreamSynchronize(st));
+    if (st_h2d) CSDR_CK(cudaStreamSynchronize(st_h2d));
+    if (st_d2h) CSDR_CK(cudaStreamSynchronize(st_d2h));
+    d2h_pending = false;
     return CUTESDR_OK;
 }
 
@@ -498,6 +511,53 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
     CSDR_CK(cudaStreamSynchronize(b->st));
     if (n_out) memcpy(n_out, nout.data(), b->nch * sizeof(int));
     return nmax;
+}
+
+int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out)
+{
+    if (!b || !iq || (audio && audio_stride <= 0)) { set_error("bank_process_async: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    if (n_in != b->L || b->h_fill != 0) {
+        set_error("bank_process_async: n_in %d must equal the block length %d (and no partial block may be pending)", n_in, b->L);
+        return CUTESDR_E_ARG;
+    }
+    if (audio) CSDR_TRY(ensure_audio(b, audio_stride));
+    if (!b->st_h2d) {
+        CSDR_CK(cudaStreamCreateWithFlags(&b->st_h2d, cudaStreamNonBlocking));
+        CSDR_CK(cudaStreamCreateWithFlags(&b->st_d2h, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CSDR_CK(cudaEventCreateWithFlags(&b->ev_h2d[k], cudaEventDisableTiming));
+            CSDR_CK(cudaEventCreateWithFlags(&b->ev_free[k], cudaEventDisableTiming));
+        }
+        CSDR_CK(cudaEventCreateWithFlags(&b->ev_d2h, cudaEventDisableTiming));
+    }
+    const int slot = (int)(b->async_blocks & 1);
+    if (!b->d_xs[slot]) CSDR_CK(cudaMalloc(&b->d_xs[slot], (size_t)b->L * sizeof(float2)));
+    // H2D of this block on the copy stream, as soon as the slot's previous block has been consumed
+    if (b->async_blocks >= 2) CSDR_CK(cudaStreamWaitEvent(b->st_h2d, b->ev_free[slot], 0));
+    CSDR_CK(cudaMemcpyAsync(b->d_xs[slot], iq, (size_t)b->L * sizeof(float2), cudaMemcpyHostToDevice, b->st_h2d));
+    CSDR_CK(cudaEventRecord(b->ev_h2d[slot], b->st_h2d));
+    CSDR_CK(cudaStreamWaitEvent(b->st, b->ev_h2d[slot], 0));
+    const float2* dblk = nullptr;
+    CSDR_TRY(stage_block(b, b->d_xs[slot], cudaMemcpyDeviceToDevice, &dblk));
+    int m = 0;
+    std::vector<int> goff(b->groups.size(), 0);
+    CSDR_TRY(b->run_block(dblk, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
+    CSDR_CK(cudaEventRecord(b->ev_free[slot], b->st));
+    b->async_blocks++;
+    if (n_out) for (int c = 0; c < b->nch; c++) n_out[c] = b->blk_nout[c];
+    if (audio && m > 0) {
+        // D2H of the finished audio rows on its own stream, after every group's burst chain
+        for (auto& g : b->groups)
+            for (auto& p : g->pending) if (p.block == b->block_index - 1) CSDR_CK(cudaStreamWaitEvent(b->st_d2h, p.ev, 0));
+        CSDR_CK(cudaMemcpy2DAsync(audio, (size_t)audio_stride * sizeof(float), b->d_audio, (size_t)b->audio_cap * sizeof(float),
+                                  (size_t)m * sizeof(float), b->nch, cudaMemcpyDeviceToHost, b->st_d2h));
+        CSDR_CK(cudaEventRecord(b->ev_d2h, b->st_d2h));
+        b->d2h_pending = true;
+    }
+    return m;
 }
 
 int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, void* d_audio, int audio_stride, int* n_out_max)

@@ -65,6 +65,12 @@ struct cutesdr_bank {
     bool layout_dirty = true;
     int L = 0;                           // m_InBufLimit
     float2* d_x = nullptr;               // [L] staging of host / blanked blocks
+    // pipelined host interface (process_async): two H2D staging slots on a copy stream, D2H on another
+    float2* d_xs[2] = {nullptr, nullptr};
+    cudaStream_t st_h2d = 0, st_d2h = 0;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_d2h = nullptr;
+    long long async_blocks = 0;
+    bool d2h_pending = false;
     float2* d_halo[2] = {nullptr, nullptr};   // [kHaloMax] tail of the previous block (double buffer)
     int halo_cur = 0;
     const float2* last_block = nullptr;  // device block of the most recent DSP block (after the blanker)

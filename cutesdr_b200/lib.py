@@ -45,6 +45,7 @@ PROTOTYPES = {
     "cutesdr_bank_set_noiseproc": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double]),
     "cutesdr_bank_set_audio_rate": (C.c_int, [_vp, C.c_double]),
     "cutesdr_bank_process": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _ip]),
+    "cutesdr_bank_process_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_synchronize": (C.c_int, [_vp]),
     "cutesdr_bank_join": (C.c_int, [_vp]),

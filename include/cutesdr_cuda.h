@@ -95,6 +95,14 @@ int cutesdr_bank_set_audio_rate(cutesdr_bank* b, double audio_rate);
  * (0 or 1024 per completed DSP block without the resampler). Returns the maximum n_out. */
 int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out);
 
+/* Pipelined form of cutesdr_bank_process for exactly one DSP block per call (n_in == block_length,
+ * iq and audio in PINNED host memory): the call only queues work -- the H2D copy of this block runs on
+ * a copy stream under the previous block's kernels, the D2H of finished audio on another. n_out[] is
+ * filled on return (burst timing is deterministic); the audio bytes are valid after
+ * cutesdr_bank_synchronize. iq must stay unchanged until the second following call (or synchronize);
+ * audio rows of a call that produced output must not be reused before they were synchronised. */
+int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out);
+
 /* Same, with the block already resident in device memory (d_iq: complex64[n_in], n_in must
  * equal block_length) and results left in device memory: d_audio float32
  * [n_channels][audio_stride] (may be NULL to keep them internal). Asynchronous on the bank's
