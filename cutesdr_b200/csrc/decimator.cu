@@ -371,7 +371,7 @@ static K1Fn k1_kernel(int ncic, int nhb)
 
 // ------------------------------------------------------------------------------------------
 // K2a: NS consecutive 11-tap half-band stages in ONE pass over HBM (the stages right after
-// kernel 1 carry most of kernel 2's traffic). A CTA owns 32 channels x T final outputs: it stages
+// kernel 1 carry most of kernel 2's traffic). A CTA owns CH (16) channels x T final outputs: it stages
 // the 2^NS*T + halo input rows in shared memory (all 8 warps issue whole-row 256-byte loads, ~30 in
 // flight per warp), then runs the stages time-parallel out of shared memory (lane = channel, so a
 // warp reads one row per LDS.64, conflict-free), each stage writing the next stage's rows, the last
@@ -383,15 +383,18 @@ template <int NS, int T> struct HbcCfg {
     static constexpr int smem_rows() { return NS == 2 ? c(0) + c(1) : c(0) + c(1) + c(2); }
 };
 
-template <int NS, int T>
+template <int NS, int T, int CH>
 __global__ void __launch_bounds__(256) k_hb11_chain(const float2* __restrict__ in, unsigned in_mask, long long in_base, int stride,
                                                     int n_out, OutDesc od)
 {
+    // CH channels per CTA (16: a row is one 128-byte line, which halves shared memory per output and
+    // lets T grow, i.e. less halo); a warp covers 32/CH rows per instruction
     typedef HbcCfg<NS, T> Cfg;
+    constexpr int RPW = 32 / CH;                   // rows per warp instruction
     extern __shared__ float2 sm_rows[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.y * 32 + lane;
-    const bool live = c < stride;
+    const int sub = lane / CH, l = lane % CH;
+    const int c = blockIdx.y * CH + l;
     const int o0 = blockIdx.x * T;
     const float h0 = c_hb_taps[0], h2 = c_hb_taps[1], h4 = c_hb_taps[2];
     // first input row of every stage for this tile: lo[NS] = o0, lo[j] = 2 lo[j+1] - 10
@@ -400,13 +403,15 @@ __global__ void __launch_bounds__(256) k_hb11_chain(const float2* __restrict__ i
     for (int j = 0; j < NS; j++) lo0 = 2 * lo0 - 10;
     float2* buf = sm_rows;
     {
-        // stage the input rows with cp.async (LDGSTS): 16 bytes = 2 channels per lane, two rows per
-        // warp instruction, no registers held -- the whole tile (c(0) x 256 B) is in flight at once
-        const int half = lane >> 4, l16 = lane & 15;
-        const int cbase = blockIdx.y * 32 + 2 * l16;
-        for (int r = 2 * warp + half; r < Cfg::c(0); r += 16) {
+        // stage the input rows with cp.async (LDGSTS): 16 bytes = 2 channels per lane, no registers
+        // held -- the whole tile is in flight at once
+        constexpr int LPR = CH / 2;                // lanes per row
+        constexpr int RPI = 32 / LPR;              // rows per warp instruction
+        const int rsub = lane / LPR, l2 = lane % LPR;
+        const int cbase = blockIdx.y * CH + 2 * l2;
+        for (int r = RPI * warp + rsub; r < Cfg::c(0); r += 8 * RPI) {
             const float2* g = in + (size_t)((in_base + lo0 + r) & in_mask) * stride + cbase;
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + r * 32 + 2 * l16);
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + r * CH + 2 * l2);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -416,18 +421,16 @@ __global__ void __launch_bounds__(256) k_hb11_chain(const float2* __restrict__ i
 #pragma unroll
     for (int j = 0; j < NS; j++) {
         const int n_j = Cfg::c(j + 1);             // outputs of this stage
-        float2* nxt = buf + Cfg::c(j) * 32;
-        if (live) {
-            for (int i = warp; i < n_j; i += 8) {
-                const float2* x = buf + (2 * i) * 32 + lane;
-                const float2 a0 = x[0], a2 = x[2 * 32], a4 = x[4 * 32], a5 = x[5 * 32], a6 = x[6 * 32], a8 = x[8 * 32], a10 = x[10 * 32];
-                float2 y;
-                // same operation order as k_halfband, so a stage gives identical bits on either path
-                y.x = fmaf(h4, a4.x + a6.x, fmaf(h2, a2.x + a8.x, fmaf(h0, a0.x + a10.x, 0.5f * a5.x)));
-                y.y = fmaf(h4, a4.y + a6.y, fmaf(h2, a2.y + a8.y, fmaf(h0, a0.y + a10.y, 0.5f * a5.y)));
-                if (j + 1 < NS) nxt[i * 32 + lane] = y;
-                else if (o0 + i < n_out) store_out(od, o0 + i, c, y);
-            }
+        float2* nxt = buf + Cfg::c(j) * CH;
+        for (int i = RPW * warp + sub; i < n_j; i += 8 * RPW) {
+            const float2* x = buf + (2 * i) * CH + l;
+            const float2 a0 = x[0], a2 = x[2 * CH], a4 = x[4 * CH], a5 = x[5 * CH], a6 = x[6 * CH], a8 = x[8 * CH], a10 = x[10 * CH];
+            float2 y;
+            // same operation order as k_halfband, so a stage gives identical bits on either path
+            y.x = fmaf(h4, a4.x + a6.x, fmaf(h2, a2.x + a8.x, fmaf(h0, a0.x + a10.x, 0.5f * a5.x)));
+            y.y = fmaf(h4, a4.y + a6.y, fmaf(h2, a2.y + a8.y, fmaf(h0, a0.y + a10.y, 0.5f * a5.y)));
+            if (j + 1 < NS) nxt[i * CH + l] = y;
+            else if (o0 + i < n_out) store_out(od, o0 + i, c, y);
         }
         if (j + 1 < NS) __syncthreads();
         buf = nxt;
@@ -799,21 +802,22 @@ int Decimator::run_block(const float2* d_x, const float2* halo_cur, float2* halo
                 o2.base = total_out_;
             }
             const unsigned mask0 = (unsigned)(stage_rows_[0] - 1);
-            const int chan_blocks = (stride_ + 31) / 32;
+            constexpr int CH = 16;
+            const int chan_blocks = stride_ / CH;
             if (nchain == 2) {
-                constexpr int T = 48;
-                const size_t smem = (size_t)HbcCfg<2, T>::smem_rows() * 32 * sizeof(float2);
+                constexpr int T = 96;
+                const size_t smem = (size_t)HbcCfg<2, T>::smem_rows() * CH * sizeof(float2);
                 static bool attr2 = false;
-                if (!attr2) { CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr2 = true; }
+                if (!attr2) { CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<2, T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr2 = true; }
                 dim3 grid((n_out + T - 1) / T, chan_blocks);
-                k_hb11_chain<2, T><<<grid, 256, smem, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, o2);
+                k_hb11_chain<2, T, CH><<<grid, 256, smem, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, o2);
             } else {
-                constexpr int T = 24;
-                const size_t smem = (size_t)HbcCfg<3, T>::smem_rows() * 32 * sizeof(float2);
+                constexpr int T = 48;
+                const size_t smem = (size_t)HbcCfg<3, T>::smem_rows() * CH * sizeof(float2);
                 static bool attr3 = false;
-                if (!attr3) { CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<3, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr3 = true; }
+                if (!attr3) { CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<3, T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr3 = true; }
                 dim3 grid((n_out + T - 1) / T, chan_blocks);
-                k_hb11_chain<3, T><<<grid, 256, smem, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, o2);
+                k_hb11_chain<3, T, CH><<<grid, 256, smem, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, o2);
             }
             lc_->n++;
             CSDR_CK(cudaGetLastError());

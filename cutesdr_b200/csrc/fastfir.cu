@@ -8,7 +8,7 @@
 // Layout: input windows come from the per-channel ring [c][kDecRing] the decimator fills;
 // H lives as complex64 [n_filters][2048] (channels with equal (lo,hi,offset,rate) share a row);
 // output goes channel-major [c][row_stride] (one contiguous 1024-sample run per burst and channel).
-// The FFT is a shared-memory Stockham autosort (radix-2, ping-pong buffers, 32 KB).
+// The FFT is a shared-memory Stockham autosort (five radix-4 passes + one radix-2, ping-pong buffers).
 #include "fastfir.cuh"
 
 namespace csdr {
@@ -83,24 +83,73 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b)
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// One radix-2 Stockham pass over 2048 points held in shared memory (256 threads, 4 butterflies
-// each). tw[m] = e^{-2 pi i m / 2048}; CONJ selects the inverse kernel.
+// 2048 = 4^5 * 2: five radix-4 Stockham passes and one radix-2 pass (autosort: natural order in and
+// out, ping-pong buffers). 256 threads; a radix-4 pass gives every thread two butterflies.
+// tw[m] = e^{-2 pi i m / 2048}; CONJ selects the inverse kernel.
 template <bool CONJ>
-__device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, float2* __restrict__ dst,
-                                              const float2* __restrict__ tw, int ns, int tw_shift)
+__device__ __forceinline__ float2 twiddle(const float2* __restrict__ tw, int m)
 {
+    // m in [0, 2048): the table holds the first half, the second half is its negation
+    float2 w = tw[m & 1023];
+    if (m & 1024) { w.x = -w.x; w.y = -w.y; }
+    if (CONJ) w.y = -w.y;
+    return w;
+}
+
+template <bool CONJ>
+__device__ __forceinline__ void stockham_r4(const float2* __restrict__ src, float2* __restrict__ dst,
+                                            const float2* __restrict__ tw, int ns)
+{
+    // butterflies j = 0..511; inputs j + r*512; k = j mod ns; outputs (j-k)*4 + k + r*ns
+    const int tw_mul = 512 / ns;           // 2048 / (4 ns)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int j = threadIdx.x + q * 256;
+        const int k = j & (ns - 1);
+        float2 a0 = src[j], a1 = src[j + 512], a2 = src[j + 1024], a3 = src[j + 1536];
+        if (ns > 1) {
+            a1 = cmulf(a1, twiddle<CONJ>(tw, k * tw_mul));
+            a2 = cmulf(a2, twiddle<CONJ>(tw, 2 * k * tw_mul));
+            a3 = cmulf(a3, twiddle<CONJ>(tw, 3 * k * tw_mul));
+        }
+        const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
+        const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
+        // forward: multiply d13 by -i; inverse: by +i
+        const float2 r13 = CONJ ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);
+        const int j0 = ((j - k) << 2) + k;
+        dst[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+        dst[j0 + ns] = make_float2(d02.x + r13.x, d02.y + r13.y);
+        dst[j0 + 2 * ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+        dst[j0 + 3 * ns] = make_float2(d02.x - r13.x, d02.y - r13.y);
+    }
+}
+
+template <bool CONJ>
+__device__ __forceinline__ void stockham_r2_last(const float2* __restrict__ src, float2* __restrict__ dst,
+                                                 const float2* __restrict__ tw)
+{
+    // final pass: ns = 1024, k = j, w = e^{-+2 pi i j / 2048}
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int j = threadIdx.x + q * 256;
-        const int k = j & (ns - 1);
-        float2 w = tw[k << tw_shift];
-        if (CONJ) w.y = -w.y;
         const float2 a = src[j];
-        const float2 b = cmulf(src[j + 1024], w);
-        const int j0 = ((j - k) << 1) + k;
-        dst[j0] = make_float2(a.x + b.x, a.y + b.y);
-        dst[j0 + ns] = make_float2(a.x - b.x, a.y - b.y);
+        const float2 b = cmulf(src[j + 1024], twiddle<CONJ>(tw, j));
+        dst[j] = make_float2(a.x + b.x, a.y + b.y);
+        dst[j + 1024] = make_float2(a.x - b.x, a.y - b.y);
     }
+}
+
+template <bool CONJ>
+__device__ __forceinline__ float2* fft2048(float2* src, float2* dst, const float2* __restrict__ tw)
+{
+    for (int ns = 1; ns < 1024; ns <<= 2) {
+        stockham_r4<CONJ>(src, dst, tw, ns);
+        __syncthreads();
+        float2* t = src; src = dst; dst = t;
+    }
+    stockham_r2_last<CONJ>(src, dst, tw);
+    __syncthreads();
+    return dst;
 }
 
 __global__ void __launch_bounds__(256) k_fastfir(const float2* __restrict__ ring, long long first_burst,
@@ -121,26 +170,15 @@ __global__ void __launch_bounds__(256) k_fastfir(const float2* __restrict__ ring
         bufA[i] = j < 0 ? make_float2(0.f, 0.f) : r[(size_t)(j & (kDecRing - 1))];
     }
     __syncthreads();
-    float2* src = bufA;
-    float2* dst = bufB;
-    int tw_shift = 10;
-    for (int ns = 1; ns < kFirFft; ns <<= 1, tw_shift--) {
-        stockham_pass<false>(src, dst, tw, ns, tw_shift);
-        __syncthreads();
-        float2* t = src; src = dst; dst = t;
-    }
+    float2* X = fft2048<false>(bufA, bufB, tw);
+    float2* other = (X == bufA) ? bufB : bufA;
     const float2* Hc = H + (size_t)filt_id[c] * kFirFft;
-    for (int i = threadIdx.x; i < kFirFft; i += 256) src[i] = cmulf(Hc[i], src[i]);   // CpxMpy, dsp/fastfir.cpp:312-321
+    for (int i = threadIdx.x; i < kFirFft; i += 256) X[i] = cmulf(Hc[i], X[i]);   // CpxMpy, dsp/fastfir.cpp:312-321
     __syncthreads();
-    tw_shift = 10;
-    for (int ns = 1; ns < kFirFft; ns <<= 1, tw_shift--) {
-        stockham_pass<true>(src, dst, tw, ns, tw_shift);
-        __syncthreads();
-        float2* t = src; src = dst; dst = t;
-    }
+    float2* Y = fft2048<true>(X, other, tw);
     // keep samples 1024..2047 (dsp/fastfir.cpp:291-294); channel-major rows: coalesced stores
     float2* yo = y + (size_t)c * stride + (size_t)blockIdx.y * kBurst;
-    for (int i = threadIdx.x; i < kBurst; i += 256) yo[i] = src[kBurst + i];
+    for (int i = threadIdx.x; i < kBurst; i += 256) yo[i] = Y[kBurst + i];
 }
 
 // ------------------------------------------------------------------------------------------

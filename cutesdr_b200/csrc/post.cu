@@ -84,7 +84,7 @@ int design_kaiser_hp(double scale, double astop, double fpass, double fstop, dou
 enum { P_AGC_ON, P_AGC_HANG, P_KNEE, P_GAIN_SLOPE, P_FIXED_GAIN, P_MANUAL_GAIN, P_A_RISE, P_A_FALL, P_D_RISE,
        P_D_FALL, P_HANG_TIME, P_SQ_THRESH, P_NTAPS, P_COUNT };
 enum { S_SM_ATT, S_SM_DEC, S_SM_AVE, S_SM_PEAK, S_AGC_ATT, S_AGC_DEC, S_Z1, S_PHASE, S_FREQ, S_FM_DC,
-       S_SQ_AVE, S_LP_W1, S_LP_W2, S_COUNT };
+       S_SQ_AVE, S_LP_W1, S_LP_W2, S_LP_W1N, S_LP_W2N, S_COUNT };
 enum { I_AGC_HANGT, I_SQUELCHED, I_COUNT };
 enum { R_AGC = 1, R_DEMOD = 2, R_FIR = 4, R_SMETER = 8 };
 
@@ -379,8 +379,16 @@ __global__ void __maxnreg__(128) k_post_seq2(PostBufs b, int n, PostUniform u, f
         ST(S_Z1) = z1;
     } else {
         // dsp/fmdemod.cpp:166-187: tmp = x e^{+j phase}; err = -atan2(tmp) = -wrap(arg x + phase)
+        // The 3 kHz low-pass biquad (CIir::ProcessFilter, dsp/iir.cpp:171-180) only runs -- and only
+        // advances its state -- while the squelch is open, which is decided per burst from the whole
+        // burst (k_post_fir). It is a recurrence, so it is computed here SPECULATIVELY beside the PLL
+        // (independent dependency chain): outputs go to the (otherwise unused) envelope row and the
+        // end state to S_LP_W1N/W2N; k_post_fir commits or discards them.
         double fm_dc = ST(S_FM_DC);
+        double w1 = ST(S_LP_W1), w2 = ST(S_LP_W2);
         const double qdc = 1.0 - u.fm_dc_alpha;
+        double* lprow = b.u + (size_t)c * b.row;
+        double lp = 0.0;
         auto step = [&](double th) -> double {
             const double err = -wrap_pi(th + phase);
             freq += (u.fm_beta * err);
@@ -388,18 +396,26 @@ __global__ void __maxnreg__(128) k_post_seq2(PostBufs b, int n, PostUniform u, f
             else if (freq < u.fm_lo) freq = u.fm_lo;
             phase = wrap_pi(phase + (freq + u.fm_alpha * err));
             fm_dc = qdc * fm_dc + u.fm_dc_alpha * freq;
-            return (freq - fm_dc) * u.fm_gain;
+            const double pre = (freq - fm_dc) * u.fm_gain;
+            const double w0 = pre - u.lp_a1 * w1 - u.lp_a2 * w2;
+            lp = u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2;
+            w2 = w1;
+            w1 = w0;
+            return pre;
         };
         if (n16 > 0) load16(throw_, cur);
         for (int t0 = 0; t0 < n16; t0 += 16) {
             if (t0 + 16 < n16) load16(throw_ + t0 + 16, nxt);
+            double lpo[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) vrow[t0 + k] = step(cur[k]);
+            for (int k = 0; k < 16; k++) { vrow[t0 + k] = step(cur[k]); lpo[k] = lp; }
+            store16(lprow + t0, lpo);
 #pragma unroll
             for (int k = 0; k < 16; k++) cur[k] = nxt[k];
         }
-        for (int t = n16; t < n; t++) vrow[t] = step(throw_[t]);
+        for (int t = n16; t < n; t++) { vrow[t] = step(throw_[t]); lprow[t] = lp; }
         ST(S_FM_DC) = fm_dc;
+        ST(S_LP_W1N) = w1; ST(S_LP_W2N) = w2;
     }
     ST(S_PHASE) = phase; ST(S_FREQ) = freq;
 }
@@ -457,38 +473,13 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
         else { if (sq_ave >= (sq_thresh + 100.0)) squelched = 1; }
         IST(I_SQUELCHED) = squelched;
         s_squelched = squelched;
-        if (!squelched) {
-            // 3 kHz low-pass biquad only runs while the squelch is open, CIir::ProcessFilter dsp/iir.cpp:171-180
-            double w1 = ST(S_LP_W1), w2 = ST(S_LP_W2);
-            double* vv = v + kHist;
-            int t = 0;
-            for (; t + 8 <= n; t += 8) {        // 8 samples per trip in registers: the loop is one dependent chain
-                double r[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) r[k] = vv[t + k];
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const double w0 = r[k] - u.lp_a1 * w1 - u.lp_a2 * w2;
-                    r[k] = u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2;
-                    w2 = w1;
-                    w1 = w0;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) vv[t + k] = r[k];
-            }
-            for (; t < n; t++) {
-                const double w0 = vv[t] - u.lp_a1 * w1 - u.lp_a2 * w2;
-                vv[t] = u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2;
-                w2 = w1;
-                w1 = w0;
-            }
-            ST(S_LP_W1) = w1; ST(S_LP_W2) = w2;
-        }
+        if (!squelched) { ST(S_LP_W1) = ST(S_LP_W1N); ST(S_LP_W2) = ST(S_LP_W2N); }   // commit the speculative biquad state
     }
     __syncthreads();
     if (aout) {
+        const double* lprow = b.u + (size_t)c * b.row;
         if (s_squelched) for (int t = threadIdx.x; t < n; t += blockDim.x) aout[t] = 0.f;
-        else for (int t = threadIdx.x; t < n; t += blockDim.x) aout[t] = (float)v[kHist + t];
+        else for (int t = threadIdx.x; t < n; t += blockDim.x) aout[t] = (float)lprow[t];
     }
 }
 #undef PAR
