@@ -166,11 +166,12 @@ int cutesdr_bank::run_block(const float2* d_block, float* d_audio_out, int audio
     std::fill(blk_nout.begin(), blk_nout.end(), 0);
     for (size_t gi = 0; gi < groups.size(); gi++) {
         Group& g = *groups[gi];
-        // The decimator may run ahead of the burst chain by two blocks, not more: the FIR window of
-        // a burst must not be overwritten in the 4096-sample ring (3 blocks of <= 1200 samples fit
-        // in the 2048 samples of slack).
+        // The decimator may run ahead of the burst chain only as far as the 4096-sample ring allows:
+        // the FIR window of a pending burst (2048 samples) must not be overwritten, which leaves 2048
+        // samples of slack = `lag` further blocks of n_dec samples (one block is always in flight).
+        const int lag = std::max(1, std::min(4, (kDecRing - kFirFft) / std::max(1, g.dec.out_per_block()) - 1));
         for (size_t k = 0; k < g.pending.size();) {
-            if (g.pending[k].block <= block_index - 2) {
+            if (g.pending[k].block <= block_index - lag) {
                 CSDR_TRY(g.dec.wait_before_output(g.pending[k].ev));
                 g.pending.erase(g.pending.begin() + k);
             } else k++;
