@@ -1,5 +1,4 @@
-// Drop-in for dsp/fft.h:24-85 (display path; FwdFFT/RevFFT only serve CFastFIR inside the reference
-// and are not exported -- CFastFIR here owns its own device FFT).
+// Drop-in for dsp/fft.h:24-85.
 #ifndef CUTESDR_B200_COMPAT_FFT_H
 #define CUTESDR_B200_COMPAT_FFT_H
 #include "dsp/datatypes.h"
@@ -29,6 +28,8 @@ public:
         cutesdr_shim_check(cutesdr_fft_put(m_h, n, (const double*)InBuf, &total), "PutInDisplayFFT");
         return total;
     }
+    void FwdFFT(TYPECPX* pInOutBuf) { cutesdr_shim_check(cutesdr_fft_fwd(m_h, (double*)pInOutBuf), "FwdFFT"); }
+    void RevFFT(TYPECPX* pInOutBuf) { cutesdr_shim_check(cutesdr_fft_rev(m_h, (double*)pInOutBuf), "RevFFT"); }
 private:
     CFft(const CFft&);
     CFft& operator=(const CFft&);

@@ -123,6 +123,51 @@ __global__ void __launch_bounds__(128) k_dispfft_rows(const float2* __restrict__
     for (int k2 = threadIdx.x; k2 < N2; k2 += blockDim.x) average_bin(k1 + N1 * k2, r[k2], p, sum, pwr_ave, ave);
 }
 
+// ---- CFft::FwdFFT / RevFFT (dsp/fft.cpp:416-426): plain complex transforms of the object's size.
+// The reference's "forward" uses the e^{+j} kernel and its "reverse" the e^{-j} kernel, neither
+// normalises. e^{+j} transform = conj(DFT(conj x)).
+__global__ void __launch_bounds__(512) k_fft_plain_small(float2* __restrict__ x, const float2* __restrict__ tw, int N, int plus_j)
+{
+    extern __shared__ float2 sm[];
+    float2* a = sm;
+    float2* b = sm + N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { float2 v = x[i]; if (plus_j) v.y = -v.y; a[i] = v; }
+    __syncthreads();
+    float2* r = smem_fft(a, b, N, tw);
+    for (int k = threadIdx.x; k < N; k += blockDim.x) { float2 v = r[k]; if (plus_j) v.y = -v.y; x[k] = v; }
+}
+
+__global__ void __launch_bounds__(128) k_fft_plain_cols(const float2* __restrict__ x, const float2* __restrict__ tw, int N, int N1,
+                                                        int N2, float2* __restrict__ mid, int plus_j)
+{
+    extern __shared__ float2 sm[];
+    float2* a = sm;
+    float2* b = sm + N1;
+    const int n2 = blockIdx.x;
+    for (int n1 = threadIdx.x; n1 < N1; n1 += blockDim.x) { float2 v = x[n1 * N2 + n2]; if (plus_j) v.y = -v.y; a[n1] = v; }
+    __syncthreads();
+    float2* r = smem_fft(a, b, N1, tw);
+    for (int k1 = threadIdx.x; k1 < N1; k1 += blockDim.x) {
+        const int m = (int)(((long long)n2 * k1) % N);
+        float s, c;
+        sincospif(-2.0f * (float)m / (float)N, &s, &c);
+        mid[(size_t)k1 * N2 + n2] = cmulf2(r[k1], make_float2(c, s));
+    }
+}
+
+__global__ void __launch_bounds__(128) k_fft_plain_rows(const float2* __restrict__ mid, const float2* __restrict__ tw, int N1, int N2,
+                                                        float2* __restrict__ out, int plus_j)
+{
+    extern __shared__ float2 sm[];
+    float2* a = sm;
+    float2* b = sm + N2;
+    const int k1 = blockIdx.x;
+    for (int n2 = threadIdx.x; n2 < N2; n2 += blockDim.x) a[n2] = mid[(size_t)k1 * N2 + n2];
+    __syncthreads();
+    float2* r = smem_fft(a, b, N2, tw);
+    for (int k2 = threadIdx.x; k2 < N2; k2 += blockDim.x) { float2 v = r[k2]; if (plus_j) v.y = -v.y; out[k1 + N1 * k2] = v; }
+}
+
 // ---- GetScreenIntegerFFTData, dsp/fft.cpp:365-407: one thread per pixel
 __global__ void k_screen(const double* __restrict__ ave, int N, int invert, int bin_min, int bin_max, int width,
                          int max_height, double gain, double off, int32_t* __restrict__ out)
@@ -170,6 +215,7 @@ struct cutesdr_fft {
     float2* d_tw = nullptr;
     float2* d_x = nullptr;
     float2* d_mid = nullptr;
+    float2* d_plain = nullptr;
     double *d_sum = nullptr, *d_pwr = nullptr, *d_ave = nullptr;
     int* d_flag = nullptr;
     int32_t* d_screen = nullptr;
@@ -186,7 +232,7 @@ struct cutesdr_fft {
     {
         if (st) cudaStreamSynchronize(st);
         free_bufs();
-        cudaFree(d_tw); cudaFree(d_flag); cudaFree(d_screen);
+        cudaFree(d_tw); cudaFree(d_flag); cudaFree(d_screen); cudaFree(d_plain);
         if (st) cudaStreamDestroy(st);
     }
     int reset()
@@ -387,6 +433,38 @@ int cutesdr_fft_get_ave(cutesdr_fft* h, float* out, int cap)
     for (int i = 0; i < n; i++) out[i] = (float)tmp[i];
     return n;
 }
+
+static int fft_plain(cutesdr_fft* h, double* io, int plus_j)
+{
+    if (!h || !io) { set_error("fft fwd/rev: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CSDR_CK(cudaSetDevice(h->device));
+    const int N = h->size;
+    for (int i = 0; i < N; i++) h->h_x[i] = make_float2((float)io[2 * i], (float)io[2 * i + 1]);
+    CSDR_CK(cudaMemcpyAsync(h->d_x, h->h_x, (size_t)N * sizeof(float2), cudaMemcpyHostToDevice, h->st));
+    float2* result = h->d_x;
+    if (N <= 4096) {
+        size_t smem = 2 * (size_t)N * sizeof(float2);
+        if (smem > 48 * 1024) CSDR_CK(cudaFuncSetAttribute(k_fft_plain_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fft_plain_small<<<1, 512, smem, h->st>>>(h->d_x, h->d_tw, N, plus_j);
+        h->lc.n++;
+    } else {
+        const int N1 = 256, N2 = N / 256;
+        if (!h->d_plain) CSDR_CK(cudaMalloc(&h->d_plain, (size_t)65536 * sizeof(float2)));
+        k_fft_plain_cols<<<N2, 128, 2 * N1 * sizeof(float2), h->st>>>(h->d_x, h->d_tw, N, N1, N2, h->d_mid, plus_j);
+        k_fft_plain_rows<<<N1, 128, 2 * N2 * sizeof(float2), h->st>>>(h->d_mid, h->d_tw, N1, N2, h->d_plain, plus_j);
+        h->lc.n += 2;
+        result = h->d_plain;
+    }
+    CSDR_CK(cudaGetLastError());
+    CSDR_CK(cudaMemcpyAsync(h->h_x, result, (size_t)N * sizeof(float2), cudaMemcpyDeviceToHost, h->st));
+    CSDR_CK(cudaStreamSynchronize(h->st));
+    for (int i = 0; i < N; i++) { io[2 * i] = h->h_x[i].x; io[2 * i + 1] = h->h_x[i].y; }
+    return CUTESDR_OK;
+}
+
+int cutesdr_fft_fwd(cutesdr_fft* h, double* io) { return fft_plain(h, io, 1); }
+int cutesdr_fft_rev(cutesdr_fft* h, double* io) { return fft_plain(h, io, 0); }
 
 int cutesdr_fft_launch_count(cutesdr_fft* h, long long* n)
 {

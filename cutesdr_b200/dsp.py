@@ -302,6 +302,16 @@ class CFft(_Handle):
                                             int(stop), out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ov)))
         return bool(ov.value), out
 
+    def FwdFFT(self, x):
+        buf = _cpx_to_f64(x)
+        check(self.L.cutesdr_fft_fwd(self.h, _dptr(buf)))
+        return _f64_to_cpx(buf, len(x))
+
+    def RevFFT(self, x):
+        buf = _cpx_to_f64(x)
+        check(self.L.cutesdr_fft_rev(self.h, _dptr(buf)))
+        return _f64_to_cpx(buf, len(x))
+
     def avebuf(self):
         out = np.empty(getattr(self, "_size", 2048), dtype=np.float32)
         n = check(self.L.cutesdr_fft_get_ave(self.h, out.ctypes.data_as(C.POINTER(C.c_float)), len(out)))

@@ -188,6 +188,11 @@ int cutesdr_fft_launch_count(cutesdr_fft* h, long long* n);
 /* GetScreenIntegerFFTData(...) -> out[max_width], *overload   dsp/fft.cpp:308-410 */
 int cutesdr_fft_get_screen(cutesdr_fft* h, int max_height, int max_width, double max_db, double min_db,
                            int start_freq, int stop_freq, int32_t* out, int* overload);
+/* FwdFFT / RevFFT(TYPECPX* pInOutBuf): in-place complex transform of the object's size, unnormalised.
+ * As in the reference, "forward" is the e^{+j 2 pi nk/N} kernel and "reverse" its conjugate
+ *                                                              dsp/fft.cpp:416-426 */
+int cutesdr_fft_fwd(cutesdr_fft* h, double* io);
+int cutesdr_fft_rev(cutesdr_fft* h, double* io);
 /* averaged log-power buffer in bels, fft-shifted (index N/2 = DC) -- test tap */
 int cutesdr_fft_get_ave(cutesdr_fft* h, float* out, int cap);
 

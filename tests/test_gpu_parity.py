@@ -592,3 +592,17 @@ def test_process_async_matches_process(lib):
             assert n_outs[k][c] == len(a)
             assert np.array_equal(bufs[k][c, :len(a)], a)
     assert sum(int(n.max()) for n in n_outs) >= 4096
+
+
+@pytest.mark.parametrize("N", [2048, 4096, 65536])
+def test_fft_fwd_rev(lib, ref, N):
+    """CFft::FwdFFT / RevFFT against the reference's Ooura transforms (same sign convention, unnormalised)."""
+    a, b = ref.RefFft(), cs.CFft()
+    a.SetFFTParams(N, False, 0.0, 1.0)
+    b.SetFFTParams(N, False, 0.0, 1.0)
+    x = noise(N, 1000.0)
+    fa, fb = a.FwdFFT(x), b.FwdFFT(x)
+    assert snr_db(fa, fb) > 110.0
+    ra, rb = a.RevFFT(fa), b.RevFFT(fa.astype(np.complex64).astype(np.complex128))
+    assert snr_db(ra, rb) > 110.0
+    assert snr_db(x * N, rb) > 110.0          # fwd then rev = N * identity
