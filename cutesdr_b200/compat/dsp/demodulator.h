@@ -53,6 +53,11 @@ public:
         int n = cutesdr_shim_check(cutesdr_demodulator_process(m_h, InLength, (const double*)pInData, pOutData), "CDemodulator::ProcessData");
         return n < 0 ? 0 : n;
     }
+    int ProcessData(int InLength, TYPECPX* pInData, TYPECPX* pOutData)
+    {
+        int n = cutesdr_shim_check(cutesdr_demodulator_process_stereo(m_h, InLength, (const double*)pInData, (double*)pOutData), "CDemodulator::ProcessData(stereo)");
+        return n < 0 ? 0 : n;
+    }
 private:
     CDemodulator(const CDemodulator&);
     CDemodulator& operator=(const CDemodulator&);

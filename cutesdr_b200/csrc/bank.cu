@@ -89,6 +89,10 @@ int cutesdr_bank::rebuild()
         if (!ch[c].configured) { set_error("channel %d has no demodulator (call set_demod first)", c); return CUTESDR_E_STATE; }
         by_bw[ch[c].max_bw].push_back(c);
     }
+    if (stereo && audio_rate > 0.0) {
+        set_error("stereo output together with the bank resampler is not supported (resample the stereo stream with cutesdr_resampler_stereo16)");
+        return CUTESDR_E_ARG;
+    }
     int newL = -1;
     for (auto& kv : by_bw) {
         std::vector<int> lens;
@@ -133,6 +137,7 @@ int cutesdr_bank::rebuild()
         const int stride = g->dec.stride();
         CSDR_TRY(g->fir.init(n, stride, g->st_post, &lc));
         CSDR_TRY(g->post.init(n, stride, g->dec.out_rate(), kMaxBurstSamples, g->st_post, &lc));
+        g->post.set_stereo(stereo);
         CSDR_CK(cudaMalloc(&g->d_chan_map, stride * sizeof(int)));
         CSDR_CK(cudaMalloc(&g->d_local_map, stride * sizeof(int)));
         std::vector<int> map(stride, 0), ident(stride, 0);
@@ -200,7 +205,7 @@ int cutesdr_bank::run_block(const float2* d_block, float* d_audio_out, int audio
             }
             CSDR_TRY(g.rs->run(n, rate, d_audio_out, audio_stride, off, g.d_chan_map, &produced));
         } else {
-            if (d_audio_out && off + n > audio_stride) {
+            if (d_audio_out && (stereo ? 2 : 1) * (off + n) > audio_stride) {
                 set_error("audio_stride %d too small for %d samples at offset %d", audio_stride, n, off);
                 return CUTESDR_E_ARG;
             }
@@ -405,6 +410,14 @@ int cutesdr_bank_set_noiseproc(cutesdr_bank* b, int on, double threshold, double
     return CUTESDR_OK;
 }
 
+int cutesdr_bank_set_stereo(cutesdr_bank* b, int stereo)
+{
+    if (!b) { set_error("set_stereo: bad handle"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((stereo != 0) != b->stereo) { b->stereo = stereo != 0; b->layout_dirty = true; }
+    return CUTESDR_OK;
+}
+
 int cutesdr_bank_set_audio_rate(cutesdr_bank* b, double audio_rate)
 {
     if (!b) { set_error("set_audio_rate: bad handle"); return CUTESDR_E_ARG; }
@@ -490,8 +503,9 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
                 // PROFILE_4 tap = the audio rows themselves
                 for (int c : g.chans) if (b->ch[c].tap_mask & 16u) {
                     CSDR_TRY(b->sync_all());
-                    std::vector<float> tmp(produced);
-                    CSDR_CK(cudaMemcpyAsync(tmp.data(), b->d_audio + (size_t)c * b->audio_cap + goff[gi], produced * sizeof(float), cudaMemcpyDeviceToHost, b->st));
+                    const int w = b->stereo ? 2 : 1;
+                    std::vector<float> tmp((size_t)w * produced);
+                    CSDR_CK(cudaMemcpyAsync(tmp.data(), b->d_audio + (size_t)c * b->audio_cap + (size_t)w * goff[gi], (size_t)w * produced * sizeof(float), cudaMemcpyDeviceToHost, b->st));
                     CSDR_CK(cudaStreamSynchronize(b->st));
                     b->ch[c].tap[4].insert(b->ch[c].tap[4].end(), tmp.begin(), tmp.end());
                 }
@@ -507,7 +521,7 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
     CSDR_TRY(b->join());
     if (audio && nmax > 0) {
         CSDR_CK(cudaMemcpy2DAsync(audio, (size_t)audio_stride * sizeof(float), b->d_audio, (size_t)b->audio_cap * sizeof(float),
-                                  (size_t)nmax * sizeof(float), b->nch, cudaMemcpyDeviceToHost, b->st));
+                                  (size_t)nmax * (b->stereo ? 2 : 1) * sizeof(float), b->nch, cudaMemcpyDeviceToHost, b->st));
     }
     CSDR_CK(cudaStreamSynchronize(b->st));
     if (n_out) memcpy(n_out, nout.data(), b->nch * sizeof(int));
@@ -554,7 +568,7 @@ int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float
         for (auto& g : b->groups)
             for (auto& p : g->pending) if (p.block == b->block_index - 1) CSDR_CK(cudaStreamWaitEvent(b->st_d2h, p.ev, 0));
         CSDR_CK(cudaMemcpy2DAsync(audio, (size_t)audio_stride * sizeof(float), b->d_audio, (size_t)b->audio_cap * sizeof(float),
-                                  (size_t)m * sizeof(float), b->nch, cudaMemcpyDeviceToHost, b->st_d2h));
+                                  (size_t)m * (b->stereo ? 2 : 1) * sizeof(float), b->nch, cudaMemcpyDeviceToHost, b->st_d2h));
         CSDR_CK(cudaEventRecord(b->ev_d2h, b->st_d2h));
         b->d2h_pending = true;
     }

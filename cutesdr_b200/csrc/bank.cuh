@@ -81,6 +81,7 @@ struct cutesdr_bank {
     float* d_audio = nullptr;            // [nch][audio_cap]
     int audio_cap = 0;
     double audio_rate = 0.0;             // > 0: CFractResampler to this rate
+    bool stereo = false;                 // CDemodulator::ProcessData(.., TYPECPX*) : interleaved L,R output
     std::unique_ptr<csdr::Blanker> nb;
     bool nb_on = false;
     double nb_thresh = 50.0, nb_width = 2.0;

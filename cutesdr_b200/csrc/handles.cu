@@ -676,11 +676,29 @@ int cutesdr_demodulator_get_smeter(cutesdr_demodulator* h, double* peak, double*
     return cutesdr_bank_get_smeter(h->bank, 0, peak, ave);
 }
 
+int cutesdr_demodulator_process_stereo(cutesdr_demodulator* h, int n_in, const double* in, double* out)
+{
+    if (!h || !h->bank || n_in < 0 || (n_in && (!in || !out))) { set_error("demodulator_process_stereo: bad arguments / state"); return CUTESDR_E_STATE; }
+    CSDR_TRY(cutesdr_bank_set_stereo(h->bank, 1));
+    int L = 0;
+    CSDR_TRY(cutesdr_bank_block_length(h->bank, &L));
+    h->iq.resize((size_t)2 * n_in);
+    for (int i = 0; i < 2 * n_in; i++) h->iq[i] = (float)in[i];
+    const int cap = 2 * (n_in / L + 2) * kMaxBurstSamples;
+    h->audio.resize(cap);
+    int nout = 0;
+    int rc = cutesdr_bank_process(h->bank, n_in, h->iq.data(), h->audio.data(), cap, &nout);
+    if (rc < 0) return rc;
+    for (int i = 0; i < 2 * nout; i++) out[i] = h->audio[i];
+    return nout;
+}
+
 int cutesdr_demodulator_process(cutesdr_demodulator* h, int n_in, const double* in, double* out)
 {
     if (!h || !h->bank || n_in < 0 || (n_in && (!in || !out))) { set_error("demodulator_process: bad arguments / state"); return CUTESDR_E_STATE; }
     int L = 0;
     CSDR_TRY(cutesdr_bank_block_length(h->bank, &L));
+    CSDR_TRY(cutesdr_bank_set_stereo(h->bank, 0));
     h->iq.resize((size_t)2 * n_in);
     for (int i = 0; i < 2 * n_in; i++) h->iq[i] = (float)in[i];
     const int cap = (n_in / L + 2) * kMaxBurstSamples;

@@ -83,7 +83,7 @@ int design_kaiser_hp(double scale, double astop, double fpass, double fstop, dou
 // ------------------------------------------------------------------------------------------
 enum { P_AGC_ON, P_AGC_HANG, P_KNEE, P_GAIN_SLOPE, P_FIXED_GAIN, P_MANUAL_GAIN, P_A_RISE, P_A_FALL, P_D_RISE,
        P_D_FALL, P_HANG_TIME, P_SQ_THRESH, P_NTAPS, P_COUNT };
-enum { S_SM_ATT, S_SM_DEC, S_SM_AVE, S_SM_PEAK, S_AGC_ATT, S_AGC_DEC, S_Z1, S_PHASE, S_FREQ, S_FM_DC,
+enum { S_SM_ATT, S_SM_DEC, S_SM_AVE, S_SM_PEAK, S_AGC_ATT, S_AGC_DEC, S_Z1, S_Y1, S_PHASE, S_FREQ, S_FM_DC,
        S_SQ_AVE, S_LP_W1, S_LP_W2, S_LP_W1N, S_LP_W2N, S_COUNT };
 enum { I_AGC_HANGT, I_SQUELCHED, I_COUNT };
 enum { R_AGC = 1, R_DEMOD = 2, R_FIR = 4, R_SMETER = 8 };
@@ -94,7 +94,8 @@ struct PostBufs {
     float2* y; int y_row;          // [c][kYHist + max_n]
     double* magh;                  // [c][kAgcBuf]
     double* smag; double* peak; float2* z; double* u; double* th; int row;   // [c][max_n]
-    double* v; int v_row;          // [c][kHist + max_n]
+    double* v; double* v2; int v_row;   // [c][kHist + max_n]
+    const double* sam_taps;        // [2][kFirMax]
     const double* par; const double* taps; const int* mode; int* reset;
     const double* qpow;            // [max_n + 1] powers of (1 - squelch alpha)
     double* state; int* istate;
@@ -115,12 +116,12 @@ __global__ void __launch_bounds__(128) k_post_reset(PostBufs b)
         for (int i = threadIdx.x; i < kYHist; i += blockDim.x) b.y[(size_t)c * b.y_row + i] = make_float2(0.f, 0.f);
         for (int i = threadIdx.x; i < kAgcBuf; i += blockDim.x) b.magh[(size_t)c * kAgcBuf + i] = -16.0;
     }
-    if (rf & R_FIR) for (int i = threadIdx.x; i < kHist; i += blockDim.x) b.v[(size_t)c * b.v_row + i] = 0.0;
+    if (rf & R_FIR) for (int i = threadIdx.x; i < kHist; i += blockDim.x) { b.v[(size_t)c * b.v_row + i] = 0.0; b.v2[(size_t)c * b.v_row + i] = 0.0; }
     if (threadIdx.x == 0) {
         if (rf & R_SMETER) { ST(S_SM_ATT) = -120.0; ST(S_SM_DEC) = -120.0; ST(S_SM_AVE) = 0.0; ST(S_SM_PEAK) = 0.0; }
         if (rf & R_AGC) { IST(I_AGC_HANGT) = 0; ST(S_AGC_DEC) = -5.0; ST(S_AGC_ATT) = -5.0; }
         if (rf & R_DEMOD) {
-            ST(S_Z1) = 0.0; ST(S_PHASE) = 0.0; ST(S_FREQ) = 0.0; ST(S_FM_DC) = 0.0; ST(S_SQ_AVE) = 0.0;
+            ST(S_Z1) = 0.0; ST(S_Y1) = 0.0; ST(S_PHASE) = 0.0; ST(S_FREQ) = 0.0; ST(S_FM_DC) = 0.0; ST(S_SQ_AVE) = 0.0;
             ST(S_LP_W1) = 0.0; ST(S_LP_W2) = 0.0;
             IST(I_SQUELCHED) = 1;
         }
@@ -268,8 +269,8 @@ __global__ void __maxnreg__(128) k_post_seq1(PostBufs b, int n, PostUniform u)
 }
 
 // ---- gain law, delayed signal, per-mode pointwise front end; CTA per channel
-__global__ void __launch_bounds__(256) k_post_mid(PostBufs b, int n, int delay, float* __restrict__ audio, int audio_stride,
-                                                  int audio_off, const int* __restrict__ chan_map)
+__global__ void __launch_bounds__(256) k_post_mid(PostBufs b, int n, int delay, int stereo, float* __restrict__ audio,
+                                                  int audio_stride, int audio_off, const int* __restrict__ chan_map)
 {
     const int c = blockIdx.x;
     const int mode = b.mode[c];
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(256) k_post_mid(PostBufs b, int n, int delay, 
     const double knee = PAR(P_KNEE), gain_slope = PAR(P_GAIN_SLOPE), fixed_gain = PAR(P_FIXED_GAIN);
     const double manual_gain = PAR(P_MANUAL_GAIN);
     float2* yrow = b.y + (size_t)c * b.y_row;
-    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + audio_off : nullptr;
+    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + (stereo ? 2 : 1) * audio_off : nullptr;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
         double zr, zi;
         if (agc_on) {
@@ -297,7 +298,12 @@ __global__ void __launch_bounds__(256) k_post_mid(PostBufs b, int n, int delay, 
             b.u[(size_t)c * b.row + t] = sqrt(zr * zr + zi * zi);
             b.th[(size_t)c * b.row + t] = atan2(zi, zr);
         } else if (mode == POST_FM) b.th[(size_t)c * b.row + t] = atan2(zi, zr);
-        else if (mode == POST_SSB) { if (aout) aout[t] = (float)zr; }                       // dsp/ssbdemod.cpp:48-53
+        else if (mode == POST_SSB) {                                                        // dsp/ssbdemod.cpp:48-60
+            if (aout) {
+                if (stereo) { aout[2 * t] = (float)zr; aout[2 * t + 1] = (float)zi; }
+                else aout[t] = (float)zr;
+            }
+        }
     }
     __syncthreads();
     // the last kYHist samples of [history | burst] become the next burst's delay history
@@ -322,7 +328,7 @@ __global__ void __maxnreg__(128) k_post_seq2(PostBufs b, int n, PostUniform u, f
     if (c >= b.nch) return;
     const int mode = b.mode[c];
     if (mode != POST_AM && mode != POST_SAM && mode != POST_FM) return;
-    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + audio_off : nullptr;
+    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + (u.stereo ? 2 : 1) * audio_off : nullptr;
     double* vrow = b.v + (size_t)c * b.v_row + kHist;
     const int n16 = n & ~15;
     double cur[16], nxt[16];
@@ -350,7 +356,30 @@ __global__ void __maxnreg__(128) k_post_seq2(PostBufs b, int n, PostUniform u, f
     }
     double phase = ST(S_PHASE), freq = ST(S_FREQ);
     const double* throw_ = b.th + (size_t)c * b.row;
-    if (mode == POST_SAM) {
+    if (mode == POST_SAM && u.stereo) {
+        // stereo SAM, dsp/samdemod.cpp:115-147: opposite NCO sign to the mono path (tmp = x e^{+j phase},
+        // err = -atan2(tmp)); BOTH parts of tmp are DC-blocked and go on to the Hilbert-pair FIR.
+        // arg(tmp) = -err, so tmp = |x| (cos err, -sin err).
+        double z1 = ST(S_Z1), y1 = ST(S_Y1);
+        const double* urow = b.u + (size_t)c * b.row;
+        double* v2row = b.v2 + (size_t)c * b.v_row + kHist;
+        for (int t = 0; t < n; t++) {
+            const double err = -wrap_pi(throw_[t] + phase);
+            freq += (u.sam_beta * err);
+            if (freq > u.sam_hi) freq = u.sam_hi;
+            else if (freq < u.sam_lo) freq = u.sam_lo;
+            phase = wrap_pi(phase + (freq + u.sam_alpha * err));
+            double sn, cs;
+            sincos(err, &sn, &cs);
+            const double z0 = urow[t] * cs + (z1 * 0.99);
+            const double y0 = -urow[t] * sn + (y1 * 0.99);
+            vrow[t] = z0 - z1;
+            v2row[t] = y0 - y1;
+            z1 = z0;
+            y1 = y0;
+        }
+        ST(S_Z1) = z1; ST(S_Y1) = y1;
+    } else if (mode == POST_SAM) {
         // dsp/samdemod.cpp:81-105: tmp = x e^{-j phase}; err = atan2(tmp) = wrap(arg x - phase);
         // tmp.re = |x| cos(err)
         double z1 = ST(S_Z1);
@@ -429,12 +458,32 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
     __shared__ int s_squelched;
     const int c = blockIdx.x;
     const int mode = b.mode[c];
+    const int stereo = u.stereo;
+    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + (stereo ? 2 : 1) * audio_off : nullptr;
+    if (mode == POST_SAM && stereo) {
+        // Hilbert-pair band-pass on (re, im) with separate real coefficient sets, then the sideband
+        // split L = re + im (lower), R = re - im (upper): dsp/samdemod.cpp:148-156, dsp/fir.cpp:101-127
+        double* vre = sm_d;
+        double* vim = sm_d + kHist + b.row;
+        __shared__ double hi[kFirMax], hq[kFirMax];
+        double* r1 = b.v + (size_t)c * b.v_row;
+        double* r2 = b.v2 + (size_t)c * b.v_row;
+        for (int i = threadIdx.x; i < kHist + n; i += blockDim.x) { vre[i] = r1[i]; vim[i] = r2[i]; }
+        for (int i = threadIdx.x; i < kFirMax; i += blockDim.x) { hi[i] = b.sam_taps[i]; hq[i] = b.sam_taps[kFirMax + i]; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kHist; i += blockDim.x) { r1[i] = vre[n + i]; r2[i] = vim[n + i]; }
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            double are = 0.0, aim = 0.0;
+            for (int k = 0; k < u.sam_ntaps; k++) { are += hi[k] * vre[kHist + t - k]; aim += hq[k] * vim[kHist + t - k]; }
+            if (aout) { aout[2 * t] = (float)(are + aim); aout[2 * t + 1] = (float)(are - aim); }
+        }
+        return;
+    }
     if (mode != POST_AM && mode != POST_FM) return;
     double* v = sm_d;
     double* h = sm_d + kHist + b.row;
     const int ntaps = (int)PAR(P_NTAPS);
     double* vrow = b.v + (size_t)c * b.v_row;
-    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + audio_off : nullptr;
     for (int i = threadIdx.x; i < kHist + n; i += blockDim.x) v[i] = vrow[i];
     for (int i = threadIdx.x; i < kFirMax; i += blockDim.x) h[i] = b.taps[(size_t)c * kFirMax + i];
     __syncthreads();
@@ -444,7 +493,10 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
         for (int t = threadIdx.x; t < n; t += blockDim.x) {
             double acc = 0.0;
             for (int k = 0; k < ntaps; k++) acc += h[k] * v[kHist + t - k];
-            if (aout) aout[t] = (float)acc;
+            if (aout) {
+                if (stereo) { aout[2 * t] = (float)acc; aout[2 * t + 1] = (float)acc; }   // dsp/amdemod.cpp:87-104
+                else aout[t] = (float)acc;
+            }
         }
         return;
     }
@@ -478,8 +530,10 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
     __syncthreads();
     if (aout) {
         const double* lprow = b.u + (size_t)c * b.row;
-        if (s_squelched) for (int t = threadIdx.x; t < n; t += blockDim.x) aout[t] = 0.f;
-        else for (int t = threadIdx.x; t < n; t += blockDim.x) aout[t] = (float)lprow[t];
+        // stereo FM copies the mono stream into both channels (dsp/fmdemod.cpp:229-234)
+        const int m = stereo ? 2 * n : n;
+        if (s_squelched) for (int t = threadIdx.x; t < m; t += blockDim.x) aout[t] = 0.f;
+        else for (int t = threadIdx.x; t < m; t += blockDim.x) aout[t] = (float)lprow[stereo ? (t >> 1) : t];
     }
 }
 #undef PAR
@@ -493,7 +547,7 @@ PostBank::~PostBank()
 {
     cudaFree(d_par_); cudaFree(d_taps_); cudaFree(d_mode_); cudaFree(d_reset_); cudaFree(d_state_);
     cudaFree(d_istate_); cudaFree(d_y_); cudaFree(d_magh_); cudaFree(d_smag_); cudaFree(d_peak_); cudaFree(d_z_);
-    cudaFree(d_u_); cudaFree(d_th_); cudaFree(d_v_); cudaFree(d_qpow_);
+    cudaFree(d_u_); cudaFree(d_th_); cudaFree(d_v_); cudaFree(d_v2_); cudaFree(d_sam_taps_); cudaFree(d_qpow_);
 }
 
 int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream_t st, LaunchCounter* lc)
@@ -557,6 +611,21 @@ int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream
     CSDR_CK(cudaMalloc(&d_u_, rows * max_n_ * sizeof(double)));
     CSDR_CK(cudaMalloc(&d_th_, rows * max_n_ * sizeof(double)));
     CSDR_CK(cudaMalloc(&d_v_, rows * v_row_ * sizeof(double)));
+    CSDR_CK(cudaMalloc(&d_v2_, rows * v_row_ * sizeof(double)));
+    CSDR_CK(cudaMemsetAsync(d_v2_, 0, rows * v_row_ * sizeof(double), st_));
+    {   // CSamDemod ctor, dsp/samdemod.cpp:67-72: 40 dB Kaiser LP 4500/5500 Hz turned into a Hilbert pair at 5 kHz
+        double coef[kFirMax];
+        std::vector<double> iq(2 * kFirMax, 0.0);
+        const int nt = design_kaiser_lp(1.0, 40.0, 4500, 5500, rate, coef);
+        for (int k = 0; k < nt; k++) {      // CFir::GenerateHBFilter, dsp/fir.cpp:374-386
+            const double arg = (kTwoPi * 5000.0 / rate) * ((double)k - ((double)(nt - 1) / 2.0));
+            iq[k] = 2.0 * coef[k] * cos(arg);
+            iq[kFirMax + k] = 2.0 * coef[k] * sin(arg);
+        }
+        uni_.sam_ntaps = nt;
+        CSDR_CK(cudaMalloc(&d_sam_taps_, iq.size() * sizeof(double)));
+        CSDR_CK(cudaMemcpy(d_sam_taps_, iq.data(), iq.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     {
         std::vector<double> qp(max_n_ + 1);
         const double q = 1.0 - uni_.fm_sq_alpha;
@@ -570,7 +639,7 @@ int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream
     CSDR_CK(cudaMemsetAsync(d_y_, 0, rows * y_row_ * sizeof(float2), st_));
     CSDR_CK(cudaMemsetAsync(d_v_, 0, rows * v_row_ * sizeof(double), st_));
     const size_t smem_pre = 2 * (size_t)(kAgcBuf + max_n_) * sizeof(double);
-    const size_t smem_fir = (size_t)(kHist + max_n_ + kFirMax) * sizeof(double);
+    const size_t smem_fir = (size_t)(2 * (kHist + max_n_) + kFirMax) * sizeof(double);
     if (smem_pre > 200 * 1024) { set_error("post: burst capacity %d too large", max_n_); return CUTESDR_E_ARG; }
     CSDR_CK(cudaFuncSetAttribute(k_post_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pre));
     CSDR_CK(cudaFuncSetAttribute(k_post_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_fir, 1024)));
@@ -672,7 +741,7 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
     CSDR_TRY(upload());
     PostBufs b;
     b.y = d_y_; b.y_row = y_row_; b.magh = d_magh_; b.smag = d_smag_; b.peak = d_peak_; b.z = d_z_; b.u = d_u_; b.th = d_th_;
-    b.row = max_n_; b.v = d_v_; b.v_row = v_row_; b.par = d_par_; b.taps = d_taps_; b.mode = d_mode_; b.reset = d_reset_;
+    b.row = max_n_; b.v = d_v_; b.v2 = d_v2_; b.sam_taps = d_sam_taps_; b.v_row = v_row_; b.par = d_par_; b.taps = d_taps_; b.mode = d_mode_; b.reset = d_reset_;
     b.state = d_state_; b.istate = d_istate_; b.nch = nch_; b.stride = stride_; b.qpow = d_qpow_;
     if (need_reset_kernel_) {
         k_post_reset<<<nch_, 128, 0, st_>>>(b);
@@ -680,11 +749,11 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
         need_reset_kernel_ = false;
     }
     const size_t smem_pre = 2 * (size_t)(kAgcBuf + max_n_) * sizeof(double);
-    const size_t smem_fir = (size_t)(kHist + max_n_ + kFirMax) * sizeof(double);
+    const size_t smem_fir = (size_t)((uni_.stereo ? 2 : 1) * (kHist + max_n_) + kFirMax) * sizeof(double);
     const int seq_blocks = (nch_ + 31) / 32;
     k_post_pre<<<nch_, 256, smem_pre, st_>>>(b, n, uni_.agc_window);
     k_post_seq1<<<2 * seq_blocks, 32, 0, st_>>>(b, n, uni_);
-    k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, d_audio, audio_stride, audio_off, d_chan_map);
+    k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, uni_.stereo, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_seq2<<<seq_blocks, 32, 0, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_fir<<<nch_, 256, smem_fir, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     lc_->n += 5;

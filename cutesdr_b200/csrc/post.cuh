@@ -22,6 +22,8 @@ struct PostUniform {
     double sam_alpha, sam_beta, sam_lo, sam_hi; // CSamDemod PLL
     double fm_alpha, fm_beta, fm_lo, fm_hi, fm_gain, fm_dc_alpha, fm_sq_alpha;
     double lp_b0, lp_b1, lp_b2, lp_a1, lp_a2;   // 3 kHz Q=1 biquad of CFmDemod
+    int stereo;                                 // 1: interleaved (L,R) output, CDemodulator::ProcessData(.., TYPECPX*)
+    int sam_ntaps;                              // Hilbert pair of the stereo SAM demodulator
 };
 
 class PostBank {
@@ -52,6 +54,9 @@ public:
     int run(int n, float* d_audio, int audio_stride, int audio_off, const int* d_chan_map);
     const float2* tap3() const { return d_z_; }
     int tap3_stride() const { return max_n_; }
+    // stereo output (dsp/demodulator.cpp:221-273): audio rows then hold interleaved L,R float pairs
+    void set_stereo(bool on) { uni_.stereo = on ? 1 : 0; }
+    bool stereo() const { return uni_.stereo != 0; }
     // S-meter readout for local channel i (synchronises the stream)
     int read_smeter(int i, double* peak, double* ave);
     double rate() const { return rate_; }
@@ -85,6 +90,8 @@ private:
     double* d_u_ = nullptr;         // [nch][max_n]            envelope (AM/SAM)
     double* d_th_ = nullptr;        // [nch][max_n]            phase angle (SAM/FM)
     double* d_v_ = nullptr;         // [nch][kHist + max_n]    FIR input with history (AM post filter / FM squelch)
+    double* d_v2_ = nullptr;        // [nch][kHist + max_n]    second FIR input row (stereo SAM imaginary part)
+    double* d_sam_taps_ = nullptr;  // [2][kFirMax] I and Q coefficient sets of the stereo SAM Hilbert pair
     double* d_qpow_ = nullptr;      // [max_n+1] powers of (1 - squelch alpha)
     int y_row_ = 0, v_row_ = 0;
 };

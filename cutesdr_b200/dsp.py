@@ -103,6 +103,9 @@ class ReceiverBank:
     def SetAudioRate(self, rate):
         check(self.L.cutesdr_bank_set_audio_rate(self.h, float(rate)))
 
+    def SetStereo(self, on):
+        check(self.L.cutesdr_bank_set_stereo(self.h, int(bool(on))))
+
     def block_length(self):
         n = C.c_int()
         check(self.L.cutesdr_bank_block_length(self.h, C.byref(n)))
@@ -216,8 +219,12 @@ class CDemodulator(_Handle):
         check(self.L.cutesdr_demodulator_get_smeter(self.h, C.byref(p), C.byref(a)))
         return a.value
 
-    def ProcessData(self, iq):
+    def ProcessData(self, iq, stereo=False):
         buf = _cpx_to_f64(iq)
+        if stereo:
+            out = np.empty(2 * (len(iq) // 4 + 8192), dtype=np.float64)
+            n = check(self.L.cutesdr_demodulator_process_stereo(self.h, len(iq), _dptr(buf), _dptr(out)))
+            return _f64_to_cpx(out, n)
         out = np.empty(len(iq) // 4 + 8192, dtype=np.float64)
         n = check(self.L.cutesdr_demodulator_process(self.h, len(iq), _dptr(buf), _dptr(out)))
         return out[:n].copy()

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "cutesdr_bank_get_smeter": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "cutesdr_bank_set_noiseproc": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double]),
     "cutesdr_bank_set_audio_rate": (C.c_int, [_vp, C.c_double]),
+    "cutesdr_bank_set_stereo": (C.c_int, [_vp, C.c_int]),
     "cutesdr_bank_process": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _ip]),
@@ -107,6 +108,7 @@ PROTOTYPES = {
     "cutesdr_demodulator_get_output_rate": (C.c_int, [_vp, _dp]),
     "cutesdr_demodulator_get_smeter": (C.c_int, [_vp, _dp, _dp]),
     "cutesdr_demodulator_process": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "cutesdr_demodulator_process_stereo": (C.c_int, [_vp, C.c_int, _dp, _dp]),
 }
 
 _lib = None

@@ -88,6 +88,13 @@ int cutesdr_bank_set_noiseproc(cutesdr_bank* b, int on, double threshold, double
  * audio_rate <= 0 disables it (audio is delivered at the demodulator output rate). */
 int cutesdr_bank_set_audio_rate(cutesdr_bank* b, double audio_rate);
 
+/* Stereo output, CDemodulator::ProcessData(int, TYPECPX*, TYPECPX*) (dsp/demodulator.cpp:221-273): audio
+ * rows then hold interleaved (left,right) float32 pairs, n_out counts frames and audio_stride (in floats)
+ * must hold 2 floats per frame. AM and FM put the mono signal on both channels, SSB/CW pass the complex
+ * filter output through, SAM splits lower/upper sideband with its Hilbert pair (dsp/samdemod.cpp:115-158).
+ * Switching rebuilds the bank (all channel state restarts). Not combinable with set_audio_rate. */
+int cutesdr_bank_set_stereo(cutesdr_bank* b, int stereo);
+
 /* N x CDemodulator::ProcessData(n_in, iq, audio) -- mono    dsp/demodulator.cpp:163-215
  * iq: n_in complex64 samples in HOST memory (any n_in; blocks are cut every block_length
  * samples exactly like m_pDemodInBuf). audio: HOST float32 [n_channels][audio_stride];
@@ -241,6 +248,10 @@ int cutesdr_demodulator_get_smeter(cutesdr_demodulator* h, double* peak, double*
 /* ProcessData(InLength, TYPECPX* in, TYPEREAL* out) mono; returns samples written to out
  *                                                              dsp/demodulator.cpp:163-215 */
 int cutesdr_demodulator_process(cutesdr_demodulator* h, int n_in, const double* in, double* out);
+/* ProcessData(InLength, TYPECPX* in, TYPECPX* out) stereo; returns frames written (2 doubles each). Mixing
+ * mono and stereo calls on one object restarts its state (the reference keeps one set of demod objects).
+ *                                                              dsp/demodulator.cpp:221-273 */
+int cutesdr_demodulator_process_stereo(cutesdr_demodulator* h, int n_in, const double* in, double* out);
 
 #ifdef __cplusplus
 }

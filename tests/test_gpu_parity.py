@@ -606,3 +606,79 @@ def test_fft_fwd_rev(lib, ref, N):
     ra, rb = a.RevFFT(fa), b.RevFFT(fa.astype(np.complex64).astype(np.complex128))
     assert snr_db(ra, rb) > 110.0
     assert snr_db(x * N, rb) > 110.0          # fwd then rev = N * identity
+
+
+def test_live_retune_and_filter_change(lib, orc):
+    """SetDemodFreq / SetDemod (filter, AGC) on a RUNNING bank take effect at the next DSP block, like the
+    reference's setters between ProcessData calls (CDemodulator::SetDemodFreq -> CDownConvert::SetFrequency
+    keeps the phasor; CFastFIR::SetupParameters swaps the response for the next FFT)."""
+    fs = 2e6
+    modes = [M.DEMOD_AM, M.DEMOD_USB, M.DEMOD_AM]
+    carriers = np.array([-300e3, 100e3, 420e3])
+    infos = [M.demod_info(M.DEMOD_AM), M.demod_info(M.DEMOD_USB, HiCut=2800, LowCut=100), M.demod_info(M.DEMOD_AM)]
+    bank = cs.ReceiverBank(3, fs)
+    refs = [orc.Demodulator() for _ in range(3)]
+    for c in range(3):
+        bank.SetDemod(c, modes[c], infos[c])
+        bank.SetDemodFreq(c, -carriers[c])
+        refs[c].SetInputSampleRate(fs)
+        refs[c].SetDemod(modes[c], infos[c])
+        refs[c].SetDemodFreq(-carriers[c])
+    L = bank.block_length()
+    nblk = 40
+    iq = syn_iq(fs, nblk * L, modes, carriers, seed=99, total_amp=9000.0)
+    got = [[] for _ in range(3)]
+    exp = [[] for _ in range(3)]
+    for k in range(nblk):
+        if k == 12:      # retune channel 0 by 700 Hz, narrow channel 2's filter, change channel 1's AGC
+            bank.SetDemodFreq(0, -carriers[0] + 700.0)
+            refs[0].SetDemodFreq(-carriers[0] + 700.0)
+            i2 = M.demod_info(M.DEMOD_AM, HiCut=2500, LowCut=-2500)
+            bank.SetDemod(2, M.DEMOD_AM, i2)
+            refs[2].SetDemod(M.DEMOD_AM, i2)
+            i1 = M.demod_info(M.DEMOD_USB, HiCut=2400, LowCut=300, AgcSlope=4, AgcDecay=500, AgcThresh=-60)
+            bank.SetDemod(1, M.DEMOD_USB, i1)
+            refs[1].SetDemod(M.DEMOD_USB, i1)
+        blk = iq[k * L:(k + 1) * L]
+        audio, n_out = bank.ProcessData(blk)
+        for c in range(3):
+            got[c].append(audio[c, :n_out[c]].copy())
+            exp[c].append(refs[c].run(blk))
+    for c in range(3):
+        a, b = np.concatenate(exp[c]), np.concatenate(got[c])
+        assert len(a) == len(b) >= 10 * 1024
+        assert snr_db(a, b) > SNR_MIN, "channel %d: %.1f dB" % (c, snr_db(a, b))
+
+
+@pytest.mark.parametrize("mode,lo,hi", [(M.DEMOD_AM, -5000, 5000), (M.DEMOD_SAM, -5000, 5000), (M.DEMOD_FM, -5000, 5000),
+                                        (M.DEMOD_USB, 100, 2800)])
+def test_stereo_output_paths(lib, ref, mode, lo, hi):
+    """CDemodulator::ProcessData(.., TYPECPX*) (dsp/demodulator.cpp:221-273) against the compiled reference:
+    AM/FM duplicate the mono stream, SSB passes the complex filter output, SAM splits the sidebands."""
+    fs, fc = 2e6, 250000.0
+    n = 800000
+    iq = syn_iq(fs, n, [mode], [fc], seed=20266, total_amp=8000.0)
+    info = M.demod_info(mode, HiCut=hi, LowCut=lo)
+    a = ref.RefDemodulator()
+    a.SetInputSampleRate(fs)
+    a.SetDemod(mode, info)
+    a.SetDemodFreq(-fc)
+    ya = a.run(iq, stereo=True)
+    bank = cs.ReceiverBank(2, fs)
+    bank.SetStereo(True)
+    for c in range(2):
+        bank.SetDemod(c, mode, info)
+        bank.SetDemodFreq(c, -fc)
+    audio, n_out = bank.ProcessData(iq)
+    yb = audio[1, 0:2 * n_out[1]:2].astype(np.float64) + 1j * audio[1, 1:2 * n_out[1]:2].astype(np.float64)
+    assert len(ya) == len(yb) >= 10 * 1024
+    skip = {M.DEMOD_SAM: 6 * 1024, M.DEMOD_FM: 14 * 1024}.get(mode, 0)
+    assert snr_db(ya[skip:], yb[skip:]) > SNR_MIN, "%.1f dB" % snr_db(ya[skip:], yb[skip:])
+    if mode in (M.DEMOD_AM, M.DEMOD_FM):
+        assert np.array_equal(yb.real, yb.imag)
+    d = cs.CDemodulator()
+    d.SetInputSampleRate(fs)
+    d.SetDemod(mode, info)
+    d.SetDemodFreq(-fc)
+    yc = d.ProcessData(iq.astype(np.complex128), stereo=True)
+    assert len(yc) == len(yb) and np.array_equal(yc.astype(np.complex64), yb.astype(np.complex64))
