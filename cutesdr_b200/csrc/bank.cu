@@ -165,7 +165,7 @@ int cutesdr_bank::rebuild()
 
 // One DSP block. d_block points at the block's first sample (kHaloMax history in front).
 // audio_off[group] = samples already written for that group's channels in d_audio_out.
-int cutesdr_bank::run_block(const float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max)
+int cutesdr_bank::run_block(const void* d_block, int fmt, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max)
 {
     int nmax = 0;
     std::fill(blk_nout.begin(), blk_nout.end(), 0);
@@ -181,7 +181,7 @@ int cutesdr_bank::run_block(const float2* d_block, float* d_audio_out, int audio
                 g.pending.erase(g.pending.begin() + k);
             } else k++;
         }
-        CSDR_TRY(g.dec.run_block(d_block, d_halo[halo_cur], d_halo[halo_cur ^ 1]));
+        CSDR_TRY(g.dec.run_block(d_block, d_halo[halo_cur], d_halo[halo_cur ^ 1], -1, fmt));
         const long long total = g.dec.total_out();
         const int nbursts = (int)(total / kBurst - g.bursts_done);
         g.last_fir_n = 0;
@@ -219,6 +219,7 @@ int cutesdr_bank::run_block(const float2* d_block, float* d_audio_out, int audio
     }
     halo_cur ^= 1;      // kernel 1 saved this block's tail into the other halo buffer
     last_block = d_block;
+    last_fmt = fmt;
     stream_pos += L;
     block_index++;
     if (n_out_max) *n_out_max = nmax;
@@ -441,32 +442,64 @@ static int ensure_audio(cutesdr_bank* b, int stride)
 // the caller's own device buffer when nothing has to touch it, else the bank's staging buffer
 // (host input, the noise blanker's output, or the first block of a stream whose first samples get the
 // oscillator's start-up amplitude).
-static int stage_block(cutesdr_bank* b, const float2* src, cudaMemcpyKind kind, const float2** blk)
+static int stage_block(cutesdr_bank* b, const void* src, int fmt, cudaMemcpyKind kind, const void** blk, int* blk_fmt)
 {
     const bool nb_on = b->nb && b->nb->on();
     const bool startup = b->stream_pos < kNcoStartup;
-    if (kind == cudaMemcpyDeviceToDevice && !nb_on && !startup) { *blk = src; return CUTESDR_OK; }
-    float2* dst = b->d_x;
-    if (nb_on) {
-        float2* raw = nullptr;
-        const float2* in = src;
-        if (kind != cudaMemcpyDeviceToDevice) {
-            CSDR_CK(cudaMallocAsync(&raw, (size_t)b->L * sizeof(float2), b->st));
-            CSDR_CK(cudaMemcpyAsync(raw, src, (size_t)b->L * sizeof(float2), kind, b->st));
-            in = raw;
-        }
-        int rc = b->nb->run(in, dst, b->L);
-        if (raw) CSDR_CK(cudaFreeAsync(raw, b->st));
-        if (rc < 0) return rc;
-    } else {
-        CSDR_CK(cudaMemcpyAsync(dst, src, (size_t)b->L * sizeof(float2), kind, b->st));
+    const size_t bytes = (size_t)b->L * sample_bytes(fmt);
+    *blk_fmt = 0;
+    if (!nb_on && !startup) {
+        // fast paths: kernel 1 reads the block where it lies, in whatever format it has
+        *blk_fmt = fmt;
+        if (kind == cudaMemcpyDeviceToDevice) { *blk = src; return CUTESDR_OK; }
+        CSDR_CK(cudaMemcpyAsync(b->d_x, src, bytes, kind, b->st));
+        *blk = b->d_x;
+        return CUTESDR_OK;
     }
-    if (startup) CSDR_TRY(apply_nco_startup_gain(dst, b->stream_pos, b->L, b->st, &b->lc));
-    *blk = dst;
+    // slow paths need complex64 in a scratch buffer first
+    float2* f32 = nullptr;
+    const float2* in = nullptr;
+    if (kind == cudaMemcpyDeviceToDevice && fmt == 0) in = reinterpret_cast<const float2*>(src);
+    else {
+        CSDR_CK(cudaMallocAsync(&f32, (size_t)b->L * sizeof(float2), b->st));
+        if (fmt == 0) CSDR_CK(cudaMemcpyAsync(f32, src, bytes, kind, b->st));
+        else {
+            const void* raw = src;
+            void* tmp = nullptr;
+            if (kind != cudaMemcpyDeviceToDevice) {
+                CSDR_CK(cudaMallocAsync(&tmp, bytes, b->st));
+                CSDR_CK(cudaMemcpyAsync(tmp, src, bytes, kind, b->st));
+                raw = tmp;
+            }
+            CSDR_TRY(unpack_samples(raw, fmt, f32, b->L, b->st, &b->lc));
+            if (tmp) CSDR_CK(cudaFreeAsync(tmp, b->st));
+        }
+        in = f32;
+    }
+    int rc = CUTESDR_OK;
+    if (nb_on) rc = b->nb->run(in, b->d_x, b->L);
+    else CSDR_CK(cudaMemcpyAsync(b->d_x, in, (size_t)b->L * sizeof(float2), cudaMemcpyDeviceToDevice, b->st));
+    if (f32) CSDR_CK(cudaFreeAsync(f32, b->st));
+    if (rc < 0) return rc;
+    if (startup) CSDR_TRY(apply_nco_startup_gain(b->d_x, b->stream_pos, b->L, b->st, &b->lc));
+    *blk = b->d_x;
     return CUTESDR_OK;
 }
 
+static int bank_process_host(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out);
+
+int cutesdr_bank_process_raw(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out)
+{
+    if (fmt < 0 || fmt > 2) { set_error("bank_process_raw: unknown sample format %d", fmt); return CUTESDR_E_ARG; }
+    return bank_process_host(b, n_in, data, fmt, audio, audio_stride, n_out);
+}
+
 int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out)
+{
+    return bank_process_host(b, n_in, iq, 0, audio, audio_stride, n_out);
+}
+
+static int bank_process_host(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out)
 {
     if (!b || n_in < 0 || (n_in > 0 && !iq) || (audio && audio_stride <= 0)) { set_error("bank_process: bad arguments"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
@@ -475,26 +508,30 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
     if (audio) CSDR_TRY(ensure_audio(b, audio_stride));
     std::vector<int> goff(b->groups.size(), 0);
     std::vector<int> nout(b->nch, 0);
-    const float2* src = reinterpret_cast<const float2*>(iq);
+    const int sb = sample_bytes(fmt);
+    if (b->h_fill > 0 && fmt != b->h_fmt) { set_error("bank_process: sample format changed inside a partially filled block"); return CUTESDR_E_STATE; }
+    b->h_fmt = fmt;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(iq);
     int pos = 0, nmax = 0;
     while (pos < n_in) {
-        const float2* blk = nullptr;
+        const void* blk = nullptr;
         if (b->h_fill == 0 && n_in - pos >= b->L) {      // whole block available: no staging copy
-            blk = src + pos;
+            blk = src + (size_t)pos * sb;
             pos += b->L;
         } else {
             int take = std::min(n_in - pos, b->L - b->h_fill);
-            memcpy(b->h_stage + b->h_fill, src + pos, (size_t)take * sizeof(float2));
+            memcpy(reinterpret_cast<unsigned char*>(b->h_stage) + (size_t)b->h_fill * sb, src + (size_t)pos * sb, (size_t)take * sb);
             b->h_fill += take;
             pos += take;
             if (b->h_fill < b->L) break;
             blk = b->h_stage;
             b->h_fill = 0;
         }
-        const float2* dblk = nullptr;
-        CSDR_TRY(stage_block(b, blk, cudaMemcpyHostToDevice, &dblk));
+        const void* dblk = nullptr;
+        int dfmt = 0;
+        CSDR_TRY(stage_block(b, blk, fmt, cudaMemcpyHostToDevice, &dblk, &dfmt));
         int m = 0;
-        CSDR_TRY(b->run_block(dblk, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
+        CSDR_TRY(b->run_block(dblk, dfmt, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
         for (size_t gi = 0; gi < b->groups.size(); gi++) {
             Group& g = *b->groups[gi];
             if (g.chans.empty()) continue;
@@ -528,7 +565,20 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
     return nmax;
 }
 
+static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out);
+
 int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out)
+{
+    return bank_process_async(b, n_in, iq, 0, audio, audio_stride, n_out);
+}
+
+int cutesdr_bank_process_async_raw(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out)
+{
+    if (fmt < 0 || fmt > 2) { set_error("bank_process_async_raw: unknown sample format %d", fmt); return CUTESDR_E_ARG; }
+    return bank_process_async(b, n_in, data, fmt, audio, audio_stride, n_out);
+}
+
+static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out)
 {
     if (!b || !iq || (audio && audio_stride <= 0)) { set_error("bank_process_async: bad arguments"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
@@ -552,14 +602,15 @@ int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float
     if (!b->d_xs[slot]) CSDR_CK(cudaMalloc(&b->d_xs[slot], (size_t)b->L * sizeof(float2)));
     // H2D of this block on the copy stream, as soon as the slot's previous block has been consumed
     if (b->async_blocks >= 2) CSDR_CK(cudaStreamWaitEvent(b->st_h2d, b->ev_free[slot], 0));
-    CSDR_CK(cudaMemcpyAsync(b->d_xs[slot], iq, (size_t)b->L * sizeof(float2), cudaMemcpyHostToDevice, b->st_h2d));
+    CSDR_CK(cudaMemcpyAsync(b->d_xs[slot], iq, (size_t)b->L * sample_bytes(fmt), cudaMemcpyHostToDevice, b->st_h2d));
     CSDR_CK(cudaEventRecord(b->ev_h2d[slot], b->st_h2d));
     CSDR_CK(cudaStreamWaitEvent(b->st, b->ev_h2d[slot], 0));
-    const float2* dblk = nullptr;
-    CSDR_TRY(stage_block(b, b->d_xs[slot], cudaMemcpyDeviceToDevice, &dblk));
+    const void* dblk = nullptr;
+    int dfmt = 0;
+    CSDR_TRY(stage_block(b, b->d_xs[slot], fmt, cudaMemcpyDeviceToDevice, &dblk, &dfmt));
     int m = 0;
     std::vector<int> goff(b->groups.size(), 0);
-    CSDR_TRY(b->run_block(dblk, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
+    CSDR_TRY(b->run_block(dblk, dfmt, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
     CSDR_CK(cudaEventRecord(b->ev_free[slot], b->st));
     b->async_blocks++;
     if (n_out) for (int c = 0; c < b->nch; c++) n_out[c] = b->blk_nout[c];
@@ -582,10 +633,11 @@ int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, voi
     CSDR_CK(cudaSetDevice(b->device));
     if (b->layout_dirty) CSDR_TRY(b->rebuild());
     if (n_in != b->L) { set_error("bank_process_device: n_in %d must equal the block length %d", n_in, b->L); return CUTESDR_E_ARG; }
-    const float2* dblk = nullptr;
-    CSDR_TRY(stage_block(b, reinterpret_cast<const float2*>(d_iq), cudaMemcpyDeviceToDevice, &dblk));
+    const void* dblk = nullptr;
+    int dfmt = 0;
+    CSDR_TRY(stage_block(b, d_iq, 0, cudaMemcpyDeviceToDevice, &dblk, &dfmt));
     int m = 0;
-    CSDR_TRY(b->run_block(dblk, reinterpret_cast<float*>(d_audio), audio_stride, nullptr, &m));
+    CSDR_TRY(b->run_block(dblk, dfmt, reinterpret_cast<float*>(d_audio), audio_stride, nullptr, &m));
     CSDR_TRY(b->collect_taps());
     if (n_out_max) *n_out_max = m;
     return m;
@@ -611,6 +663,7 @@ int cutesdr_bank_last_block(cutesdr_bank* b, const void** d_block, int* n)
 {
     if (!b || !d_block) { set_error("last_block: bad arguments"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
+    if (b->last_fmt != 0) { set_error("last_block: the last block is still in its raw integer format"); return CUTESDR_E_STATE; }
     *d_block = b->last_block;
     if (n) *n = b->L;
     return b->last_block ? CUTESDR_OK : CUTESDR_E_STATE;

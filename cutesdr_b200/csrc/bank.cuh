@@ -73,9 +73,11 @@ struct cutesdr_bank {
     bool d2h_pending = false;
     float2* d_halo[2] = {nullptr, nullptr};   // [kHaloMax] tail of the previous block (double buffer)
     int halo_cur = 0;
-    const float2* last_block = nullptr;  // device block of the most recent DSP block (after the blanker)
+    const void* last_block = nullptr;    // device block of the most recent DSP block (after the blanker)
+    int last_fmt = 0;
     float2* h_stage = nullptr;           // pinned staging of one block
     int h_fill = 0;
+    int h_fmt = 0;                       // sample format of the partially filled staging block
     long long stream_pos = 0;
     long long block_index = 0;
     float* d_audio = nullptr;            // [nch][audio_cap]
@@ -88,7 +90,7 @@ struct cutesdr_bank {
     std::vector<int> blk_nout;           // per channel, samples produced by the last block
 
     int rebuild();
-    int run_block(const float2* d_block, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);
+    int run_block(const void* d_block, int fmt, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);
     int collect_taps();
     int join();                          // order the main stream after every outstanding burst chain
     int sync_all();

@@ -104,14 +104,31 @@ static int k1_halo(int ncic, int nhb)
     return (need + q - 1) / q * q;
 }
 
+// Wideband input formats kernel 1 reads directly (the radio's wire formats, interface/netiobase.cpp:497-527):
+//   0 = complex64;  1 = interleaved little-endian int16 I,Q (value = the integer);
+//   2 = packed little-endian int24 I,Q (value = integer / 256: +-32768 range with 8 fraction bits).
+// The conversion to float32 is exact for all three.
+__device__ __forceinline__ float2 fetch_sample(const void* __restrict__ x, int fmt, int j)
+{
+    if (fmt == 0) return reinterpret_cast<const float2*>(x)[j];
+    if (fmt == 1) {
+        const short2 v = reinterpret_cast<const short2*>(x)[j];
+        return make_float2((float)v.x, (float)v.y);
+    }
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(x) + (size_t)6 * j;
+    const int i24 = (int)((unsigned)p[0] << 8 | (unsigned)p[1] << 16 | (unsigned)p[2] << 24) >> 8;
+    const int q24 = (int)((unsigned)p[3] << 8 | (unsigned)p[4] << 16 | (unsigned)p[5] << 24) >> 8;
+    return make_float2((float)i24 * (1.0f / 256.0f), (float)q24 * (1.0f / 256.0f));
+}
+
 // The last kHaloMax samples of [previous halo | this block] become the next block's halo
 // (written to the other half of a double buffer, so concurrent readers of halo_cur are safe).
-__device__ __forceinline__ void save_halo(const float2* __restrict__ x, const float2* __restrict__ halo_cur,
+__device__ __forceinline__ void save_halo(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur,
                                           float2* __restrict__ halo_next, int L)
 {
     for (int i = threadIdx.x; i < kHaloMax; i += blockDim.x) {
         const int j = L - kHaloMax + i;
-        halo_next[i] = j >= 0 ? x[j] : halo_cur[kHaloMax + j];
+        halo_next[i] = j >= 0 ? fetch_sample(x, fmt, j) : halo_cur[kHaloMax + j];
     }
 }
 
@@ -218,7 +235,7 @@ template <int NCIC, int NHB, int B> struct Body<NCIC, NHB, B, B> {
 // K1: fused NCO mix + NCIC x CIC3 + NHB x HB11
 // ------------------------------------------------------------------------------------------
 template <int NCIC, int NHB>
-__global__ void __launch_bounds__(256, 3) k_mix_cic(const float2* __restrict__ x, const float2* __restrict__ halo_cur,
+__global__ void __launch_bounds__(256, 3) k_mix_cic(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur,
                                                  float2* __restrict__ halo_next, int L, int tile_len,
                                                  const NcoDev* __restrict__ nco,
                                                  const unsigned long long* __restrict__ phase_cur,
@@ -233,13 +250,34 @@ __global__ void __launch_bounds__(256, 3) k_mix_cic(const float2* __restrict__ x
     const int n_load = n_tile + H;
     {
         // samples before the block start (first tile's halo) come from the saved tail of the
-        // previous block: halo_cur[kHaloMax + j] for j < 0
-        const float4* src = reinterpret_cast<const float4*>(x + (t0 - H));
+        // previous block: halo_cur[kHaloMax + j] for j < 0. Two samples per iteration; the radio's
+        // integer formats are unpacked here, on the way into shared memory (no separate pass).
         const float4* hsrc = reinterpret_cast<const float4*>(halo_cur + (kHaloMax + t0 - H));
         const int n_neg = t0 < H ? ((H - t0) >> 1) : 0;
-        for (int i = threadIdx.x; i < (n_load >> 1); i += blockDim.x) smem4[i] = i < n_neg ? __ldg(hsrc + i) : __ldg(src + i);
+        if (fmt == 0) {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(x) + (t0 - H));
+            for (int i = threadIdx.x; i < (n_load >> 1); i += blockDim.x) smem4[i] = i < n_neg ? __ldg(hsrc + i) : __ldg(src + i);
+        } else if (fmt == 1) {
+            const int2* src = reinterpret_cast<const int2*>(reinterpret_cast<const short2*>(x) + (t0 - H));
+            for (int i = threadIdx.x; i < (n_load >> 1); i += blockDim.x) {
+                if (i < n_neg) smem4[i] = __ldg(hsrc + i);
+                else {
+                    const int2 v = __ldg(src + i);
+                    smem4[i] = make_float4((float)(short)(v.x & 0xffff), (float)(short)(v.x >> 16), (float)(short)(v.y & 0xffff),
+                                           (float)(short)(v.y >> 16));
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < (n_load >> 1); i += blockDim.x) {
+                if (i < n_neg) smem4[i] = __ldg(hsrc + i);
+                else {
+                    const float2 a = fetch_sample(x, 2, t0 - H + 2 * i), b2 = fetch_sample(x, 2, t0 - H + 2 * i + 1);
+                    smem4[i] = make_float4(a.x, a.y, b2.x, b2.y);
+                }
+            }
+        }
     }
-    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == 0) save_halo(x, halo_cur, halo_next, L);
+    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == 0) save_halo(x, fmt, halo_cur, halo_next, L);
     __syncthreads();
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= nch) return;
@@ -298,12 +336,12 @@ __global__ void __launch_bounds__(256, 3) k_mix_cic(const float2* __restrict__ x
 
 // Slow generic path for block lengths that are not a multiple of the unrolled body (single-object
 // API with odd sizes). Same math, run-time stage counts, one tile.
-__global__ void k_mix_cic_generic(const float2* __restrict__ x, const float2* __restrict__ halo_cur,
+__global__ void k_mix_cic_generic(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur,
                                   float2* __restrict__ halo_next, int L, int ncic, int nhb, const NcoDev* __restrict__ nco,
                                   const unsigned long long* __restrict__ phase_cur,
                                   unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
 {
-    if (blockIdx.x == 0) save_halo(x, halo_cur, halo_next, L);
+    if (blockIdx.x == 0) save_halo(x, fmt, halo_cur, halo_next, L);
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nch) return;
     const int G = 1 << ncic;
@@ -327,7 +365,7 @@ __global__ void k_mix_cic_generic(const float2* __restrict__ x, const float2* __
     long long q = -(long long)(H >> ncic);
     for (int i = -H; i < L; i++) {
         if ((i & 31) == 0 || i == -H) o = seed_osc(ph0 + (unsigned long long)(long long)(i + 1) * p.inc);
-        float2 v = cmul(i >= 0 ? x[i] : halo_cur[kHaloMax + i], o);
+        float2 v = cmul(i >= 0 ? fetch_sample(x, fmt, i) : halo_cur[kHaloMax + i], o);
         o = cmul(o, w1);
         int s = 0;
         while (s < ncic) {
@@ -356,7 +394,7 @@ __global__ void k_mix_cic_generic(const float2* __restrict__ x, const float2* __
     }
 }
 
-typedef void (*K1Fn)(const float2*, const float2*, float2*, int, int, const NcoDev*, const unsigned long long*,
+typedef void (*K1Fn)(const void*, int, const float2*, float2*, int, int, const NcoDev*, const unsigned long long*,
                      unsigned long long*, int, OutDesc, float);
 
 static K1Fn k1_kernel(int ncic, int nhb)
@@ -479,6 +517,20 @@ __global__ void __launch_bounds__(128) k_halfband(const float2* __restrict__ in,
 // ------------------------------------------------------------------------------------------
 // NCO start-up amplitude
 // ------------------------------------------------------------------------------------------
+__global__ void k_unpack(const void* __restrict__ raw, int fmt, float2* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fetch_sample(raw, fmt, i);
+}
+
+int unpack_samples(const void* d_raw, int fmt, float2* d_out, int n, cudaStream_t st, LaunchCounter* lc)
+{
+    k_unpack<<<(n + 255) / 256, 256, 0, st>>>(d_raw, fmt, d_out, n);
+    if (lc) lc->n++;
+    CSDR_CK(cudaGetLastError());
+    return CUTESDR_OK;
+}
+
 __global__ void k_scale_prefix(float2* x, const float* gain, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -715,7 +767,7 @@ int Decimator::upload_dirty()
     return CUTESDR_OK;
 }
 
-int Decimator::run_block(const float2* d_x, const float2* halo_cur, float2* halo_next, int L)
+int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_next, int L, int fmt)
 {
     CSDR_TRY(upload_dirty());
     if (L < 0) L = block_len_;
@@ -763,10 +815,10 @@ int Decimator::run_block(const float2* d_x, const float2* halo_cur, float2* halo
         dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);
         const int H = k1_halo(ncic_, nhbf_);
         size_t smem = (size_t)(tile_len_ + H) * sizeof(float2);
-        k1_kernel(ncic_, nhbf_)<<<grid, threads, smem, st_>>>(d_x, halo_cur, halo_next, L, tile_len_, d_nco_, pc, pn, stride_, od,
+        k1_kernel(ncic_, nhbf_)<<<grid, threads, smem, st_>>>(d_x, fmt, halo_cur, halo_next, L, tile_len_, d_nco_, pc, pn, stride_, od,
                                                                scale);
     } else {
-        k_mix_cic_generic<<<(stride_ + 63) / 64, 64, 0, st_>>>(d_x, halo_cur, halo_next, L, ncic_, nhbf_, d_nco_, pc, pn, stride_, od, scale);
+        k_mix_cic_generic<<<(stride_ + 63) / 64, 64, 0, st_>>>(d_x, fmt, halo_cur, halo_next, L, ncic_, nhbf_, d_nco_, pc, pn, stride_, od, scale);
     }
     lc_->n++;
     CSDR_CK(cudaGetLastError());

@@ -15,6 +15,9 @@ double plan_stages(double in_rate, double max_bw, std::vector<int>& lens);
 // kNcoStartup samples of a stream, in place, on the device copy of the wideband block.
 constexpr int kNcoStartup = 512;
 int apply_nco_startup_gain(float2* d_x, long long stream_pos, int n, cudaStream_t st, LaunchCounter* lc);
+// raw radio samples (fmt 1/2, see Decimator::run_block) -> complex64
+int unpack_samples(const void* d_raw, int fmt, float2* d_out, int n, cudaStream_t st, LaunchCounter* lc);
+inline int sample_bytes(int fmt) { return fmt == 0 ? 8 : (fmt == 1 ? 4 : 6); }
 
 struct NcoDev {
     unsigned long long inc;   // phase increment per input sample, turns * 2^64
@@ -41,7 +44,8 @@ public:
     // it in the stream (zeros at stream start); halo_next (a different buffer) receives the last
     // kHaloMax samples of [halo_cur | block] for the next call -- kernel 1 writes it itself, so the
     // caller's block is read in place and no copy node sits between consecutive launches.
-    int run_block(const float2* d_x, const float2* halo_cur, float2* halo_next, int L = -1);
+    // fmt: 0 = complex64, 1 = int16 I,Q pairs, 2 = packed int24 I,Q (unpacked inside kernel 1's tile load)
+    int run_block(const void* d_x, const float2* halo_cur, float2* halo_next, int L = -1, int fmt = 0);
     int block_len() const { return block_len_; }
     // Overlap mode (used by the bank): the HBM-bound half-band stages (kernel 2) run on an internal
     // second stream so they execute under the FP32-bound kernel 1 of the NEXT block. The first stage

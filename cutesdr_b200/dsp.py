@@ -156,6 +156,18 @@ class ReceiverBank:
                                           n_out.ctypes.data_as(C.POINTER(C.c_int))))
         return audio, n_out
 
+    def ProcessRaw(self, data, fmt, audio_stride=None):
+        """Wire-format ingest: data = int16 array [n,2] (fmt 1) or uint8 array [n*6] of packed int24 (fmt 2)."""
+        data = np.ascontiguousarray(data)
+        n = data.size // 2 if fmt == 1 else (data.size // 6 if fmt == 2 else data.size)
+        L = self.block_length()
+        audio_stride = audio_stride or (n // L + 2) * 2048 * 2
+        audio = np.zeros((self.n_channels, audio_stride), dtype=np.float32)
+        n_out = np.zeros(self.n_channels, dtype=np.int32)
+        check(self.L.cutesdr_bank_process_raw(self.h, int(n), data.ctypes.data, int(fmt), audio.ctypes.data, int(audio_stride),
+                                              n_out.ctypes.data_as(C.POINTER(C.c_int))))
+        return audio, n_out
+
     def process_ptr(self, n_in, iq_ptr, audio_ptr, audio_stride, n_out_arr=None):
         """Raw-pointer form (pinned host memory) used by bench.py's end-to-end leg."""
         p = n_out_arr.ctypes.data_as(C.POINTER(C.c_int)) if n_out_arr is not None else None

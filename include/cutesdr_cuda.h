@@ -102,6 +102,18 @@ int cutesdr_bank_set_stereo(cutesdr_bank* b, int stereo);
  * (0 or 1024 per completed DSP block without the resampler). Returns the maximum n_out. */
 int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out);
 
+/* Wire-format ingest (interface/netiobase.cpp:497-527): the same as cutesdr_bank_process / _async with
+ * the samples still in the radio's integer format -- fmt 1 = interleaved little-endian int16 I,Q (4 bytes
+ * per sample, value = the integer), fmt 2 = packed little-endian int24 I,Q (6 bytes per sample, value =
+ * integer/256), fmt 0 = complex64. The unpack happens inside kernel 1's tile load, so H2D traffic is half
+ * (int16) or three quarters (int24) of the float path and no conversion pass exists. Packet headers
+ * (4 bytes per UDP packet) are the caller's to strip. */
+#define CUTESDR_FMT_CF32 0
+#define CUTESDR_FMT_CS16 1
+#define CUTESDR_FMT_CS24 2
+int cutesdr_bank_process_raw(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out);
+int cutesdr_bank_process_async_raw(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out);
+
 /* Pipelined form of cutesdr_bank_process for exactly one DSP block per call (n_in == block_length,
  * iq and audio in PINNED host memory): the call only queues work -- the H2D copy of this block runs on
  * a copy stream under the previous block's kernels, the D2H of finished audio on another. n_out[] is

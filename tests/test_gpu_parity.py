@@ -682,3 +682,44 @@ def test_stereo_output_paths(lib, ref, mode, lo, hi):
     d.SetDemodFreq(-fc)
     yc = d.ProcessData(iq.astype(np.complex128), stereo=True)
     assert len(yc) == len(yb) and np.array_equal(yc.astype(np.complex64), yb.astype(np.complex64))
+
+
+def test_wire_format_ingest_is_bit_identical(lib):
+    """int16 and packed-int24 samples unpacked inside kernel 1 (interface/netiobase.cpp:497-527) give the
+    same bits as the caller converting to complex64 first -- the conversions are exact in float32."""
+    fs = 2e6
+    nch = 6
+    modes = [[M.DEMOD_AM, M.DEMOD_USB, M.DEMOD_FM][c % 3] for c in range(nch)]
+    carriers = carrier_grid(nch, 200e3)
+    infos = [M.demod_info(m, HiCut=2800, LowCut=100) if m == M.DEMOD_USB else M.demod_info(m) for m in modes]
+
+    def make():
+        b = cs.ReceiverBank(nch, fs)
+        for c in range(nch):
+            b.SetDemod(c, modes[c], infos[c])
+            b.SetDemodFreq(c, -carriers[c])
+        return b
+
+    L = make().block_length()
+    n = 9 * L + 777                      # ragged tail stays buffered
+    base = syn_iq(fs, n, modes, carriers, seed=55)
+    base = base * np.float32(30000.0 / max(np.abs(base.real).max(), np.abs(base.imag).max()))   # inside int16 / int24 range
+    i16 = np.empty((n, 2), dtype=np.int16)
+    i16[:, 0] = np.round(base.real).astype(np.int16)
+    i16[:, 1] = np.round(base.imag).astype(np.int16)
+    f_from16 = (i16[:, 0].astype(np.float32) + 1j * i16[:, 1].astype(np.float32)).astype(np.complex64)
+    a_ref, n_ref = make().ProcessData(f_from16)
+    a16, n16 = make().ProcessRaw(i16, 1)
+    assert np.array_equal(n_ref, n16) and n_ref.max() >= 3 * 1024
+    assert np.array_equal(a_ref, a16)
+    # packed int24: value = integer / 256
+    v24 = np.round(np.stack([base.real, base.imag], axis=1) * 256.0).astype(np.int32)
+    packed = np.empty((n, 2, 3), dtype=np.uint8)
+    packed[:, :, 0] = v24 & 0xff
+    packed[:, :, 1] = (v24 >> 8) & 0xff
+    packed[:, :, 2] = (v24 >> 16) & 0xff
+    f_from24 = ((v24[:, 0] / 256.0).astype(np.float32) + 1j * (v24[:, 1] / 256.0).astype(np.float32)).astype(np.complex64)
+    a_ref, n_ref = make().ProcessData(f_from24)
+    a24, n24 = make().ProcessRaw(packed.reshape(-1), 2)
+    assert np.array_equal(n_ref, n24)
+    assert np.array_equal(a_ref, a24)
