@@ -45,6 +45,7 @@ double plan_stages(double in_rate, double max_bw, std::vector<int>& lens)
 // device helpers
 // ------------------------------------------------------------------------------------------
 __constant__ float c_hb_taps[88];
+__constant__ float c_cic4[48];      // impulse response of four cascaded CIC3 decimate-by-2 stages (46 taps, unnormalised)
 static std::once_flag g_taps_once[16];
 
 static int upload_taps()
@@ -56,6 +57,19 @@ static int upload_taps()
         float h[88];
         for (int i = 0; i < 88; i++) h[i] = (float)csdr_hb_taps[i];
         err = cudaMemcpyToSymbol(c_hb_taps, h, sizeof(h));
+        if (err != cudaSuccess) return;
+        // four cascaded CIC3 decimate-by-2 stages as one FIR: (1,3,3,1) upsampled by 1, 2, 4, 8 and convolved
+        std::vector<double> acc(1, 1.0);
+        for (int up = 1; up <= 8; up <<= 1) {
+            std::vector<double> nxt(acc.size() + 3 * up, 0.0);
+            const double k[4] = {1.0, 3.0, 3.0, 1.0};
+            for (size_t a = 0; a < acc.size(); a++)
+                for (int b = 0; b < 4; b++) nxt[a + (size_t)b * up] += acc[a] * k[b];
+            acc.swap(nxt);
+        }
+        float c4[48] = {0};
+        for (size_t a = 0; a < acc.size() && a < 48; a++) c4[a] = (float)acc[a];       // 46 taps, integers < 2^24
+        err = cudaMemcpyToSymbol(c_cic4, c4, sizeof(c4));
     });
     if (err != cudaSuccess) { set_error("tap upload: %s", cudaGetErrorString(err)); return CUTESDR_E_CUDA; }
     return CUTESDR_OK;
@@ -148,6 +162,7 @@ template <int NCIC, int NHB> struct K1Cfg {
 struct EmitCtx {
     OutDesc od;
     long long row_lo;     // first output row this tile owns (rows before it belong to the halo)
+    long long row_hi;     // one past the last row this tile owns (kernel 1T's last MMA tile overshoots)
     int c;
     float scale;
     float h0, h2, h4;     // HB11 taps 0/2/4 (= 10/8/6); centre tap is 0.5
@@ -161,7 +176,7 @@ template <int NHB, int J>
 __device__ __forceinline__ void hb_feed(float2 v, long long q, Hb11St* hs, const EmitCtx& em)
 {
     if constexpr (J == NHB) {
-        if (q >= em.row_lo) store_out(em.od, q, em.c, make_float2(v.x * em.scale, v.y * em.scale));
+        if (q >= em.row_lo && q < em.row_hi) store_out(em.od, q, em.c, make_float2(v.x * em.scale, v.y * em.scale));
     } else {
         Hb11St& s = hs[J];
         if ((q & 1) == 0) {
@@ -309,6 +324,7 @@ __global__ void __launch_bounds__(256, 3) k_mix_cic(const void* __restrict__ x, 
     EmitCtx em;
     em.od = od;
     em.row_lo = (long long)(t0 / (G << NHB));
+    em.row_hi = 0x7fffffffffffffffLL;
     em.c = c;
     em.scale = scale;
     em.h0 = c_hb_taps[0]; em.h2 = c_hb_taps[1]; em.h4 = c_hb_taps[2];
@@ -405,6 +421,338 @@ static K1Fn k1_kernel(int ncic, int nhb)
         {k_mix_cic<4, 0>, k_mix_cic<4, 1>, k_mix_cic<4, 2>}, {k_mix_cic<5, 0>, k_mix_cic<5, 1>, k_mix_cic<5, 2>},
         {k_mix_cic<6, 0>, k_mix_cic<6, 1>, k_mix_cic<6, 2>}};
     return table[ncic][nhb];
+}
+
+
+// ------------------------------------------------------------------------------------------
+// K1T: kernel 1 on the tensor cores (tcgen05, kind::tf32, accumulators in TMEM).
+//
+// The NCO mix followed by the first FOUR CIC3 stages is one complex FIR-decimate-by-16 per channel,
+//     y4[m] = sum_{j<46} H[j] x[16m+15-j] e^{j phi(16m+15-j)}
+//           = e^{j phi(16m+15)} * sum_k A_c[k] x[16(m-2)+k],   A_c[k] = H[47-k] e^{-j 2 pi (47-k) f_c/fs},
+// i.e. a GEMM  Y[channel, time] = A[channel, 48] * X[48, time]  against a Hankel matrix of the wideband
+// block that every channel shares. A CTA owns 128 channels (the MMA's M) and a time segment; per tile of
+// 128 outputs (2048 input samples) it issues  D_re = Ar Xr - Ai Xi,  D_im = Ar Xi + Ai Xr  as M128 N128 K8
+// MMAs with every operand split into tf32 hi + lo parts (3 products per term: lo*hi, hi*lo, hi*hi; the
+// dropped lo*lo is 2^-22 relative), fp32 accumulation in TMEM.
+//   * A (per-channel coefficients, 4 planes Ar/Ai x hi/lo, 96 KB) stays resident in shared memory,
+//     K-major, no swizzle: byte (row, k) = 16 (row%8) + 1536 (row/8) + 128 (k/4) + 4 (k%4).
+//   * X is staged by 4 producer warps as 4 planes (re/im x hi/lo) of 8 interleaved STRIPS: strip r holds
+//     288 consecutive samples, 16-byte chunk w of strip r at byte 16 r + 128 w. MMA row n = 8 g + r then
+//     reads chunks 4 g + (k/4): descriptor LBO 128, SBO 512 -- overlapping rows, so the Hankel matrix
+//     costs 9/8 of the raw samples instead of 3x. Column n of the accumulator is output m0 + 16 r + g.
+//   * 4 epilogue warps (TMEM lane = channel) read the columns in time order, multiply by the
+//     oscillator at the decimated rate (re-seeded exactly from the 64-bit phase every 16 outputs), and
+//     run the remaining CIC3 / fused 11-tap half-band stages and the store exactly as kernel 1 does.
+//   * B is double-buffered in shared memory, the accumulators in TMEM (2 x 256 columns), so staging,
+//     MMA and epilogue of consecutive tiles overlap; mbarriers + tcgen05.commit order them.
+// Segments re-prime the feed-forward stages with a halo of PRE outputs, like kernel 1's tiles.
+// ------------------------------------------------------------------------------------------
+constexpr int kTcAPlane = 16 * 1536;                      // bytes per A plane (128 rows x 48 tf32)
+constexpr int kTcBPlane = 72 * 128;                       // bytes per B plane (8 strips x 72 chunks x 16 B)
+constexpr int kTcBarOff = 4 * kTcAPlane + 8 * kTcBPlane;
+constexpr int kTcSmem = kTcBarOff + 128;
+constexpr int kTcThreads = 288;                           // 4 epilogue + 4 producer + 1 MMA warp
+
+
+template <int NCR, int NHB> struct TcCfg {
+    static constexpr int Gr = 1 << NCR;                                             // fs/16 samples per CIC-chain output
+    static constexpr int need = (NCR == 0 ? 0 : (2 << NCR)) + 10 * Gr * ((1 << NHB) - 1);
+    static constexpr int q = (Gr << NHB) > 16 ? (Gr << NHB) : 16;
+    static constexpr int PRE = (need + q - 1) / q * q;                              // priming outputs (fs/16) per segment
+};
+static int tc_pre(int ncr, int nhb)
+{
+    const int gr = 1 << ncr;
+    const int need = (ncr == 0 ? 0 : (2 << ncr)) + 10 * gr * ((1 << nhb) - 1);
+    const int q = std::max(gr << nhb, 16);
+    return (need + q - 1) / q * q;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float tf32_rn(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr)
+{
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+    return __uint_as_float(v);
+}
+
+// A-operand images for every 128-channel group: [group][Ar_hi, Ar_lo, Ai_hi, Ai_lo][kTcAPlane bytes]
+__global__ void k_tc_coeffs(const NcoDev* __restrict__ nco, int nch, int groups, float* __restrict__ img)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= groups * 128 * 48) return;
+    const int k = idx % 48, row = (idx / 48) % 128, cg = idx / (48 * 128);
+    const int c = cg * 128 + row, j = 47 - k;
+    double ar = 0.0, ai = 0.0;
+    if (c < nch && j < 46) {
+        const unsigned long long ph = 0ull - nco[c].inc * (unsigned long long)j;       // -j * inc, turns * 2^64 (wraps)
+        double sn, cs;
+        sincospi((double)(long long)ph * (1.0 / 9223372036854775808.0), &sn, &cs);
+        ar = (double)c_cic4[j] * cs;
+        ai = (double)c_cic4[j] * sn;
+    }
+    const float rh = tf32_rn((float)ar), rl = tf32_rn((float)(ar - (double)rh));
+    const float ih = tf32_rn((float)ai), il = tf32_rn((float)(ai - (double)ih));
+    const int off = (16 * (row & 7) + 1536 * (row >> 3) + 128 * (k >> 2) + 4 * (k & 3)) >> 2;
+    float* g = img + (size_t)cg * 4 * (kTcAPlane / 4);
+    g[off] = rh;
+    g[(kTcAPlane / 4) + off] = rl;
+    g[2 * (kTcAPlane / 4) + off] = ih;
+    g[3 * (kTcAPlane / 4) + off] = il;
+}
+
+template <int NCR, int NHB, int G0, int G1> struct TcStrip {
+    static __device__ __forceinline__ void run(const float* re, const float* im, float2& S, float2 w, CicSt* st, float2* ev, Hb11St* hs,
+                                               long long q0, const EmitCtx& em)
+    {
+        float2 v = cmul(make_float2(re[G0], im[G0]), S);
+        if (G0 + 1 < G1) S = cmul(S, w);
+        cic_feed<NCR, NHB, 0, G0>(v, st, ev, hs, q0, em);
+        TcStrip<NCR, NHB, G0 + 1, G1>::run(re, im, S, w, st, ev, hs, q0, em);
+    }
+};
+template <int NCR, int NHB, int G1> struct TcStrip<NCR, NHB, G1, G1> {
+    static __device__ __forceinline__ void run(const float*, const float*, float2&, float2, CicSt*, float2*, Hb11St*, long long,
+                                               const EmitCtx&) {}
+};
+
+template <int NCR, int NHB>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    k_mix_tc(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, float2* __restrict__ halo_next, int L, int seg_len,
+             const float* __restrict__ coef_img, const NcoDev* __restrict__ nco, const unsigned long long* __restrict__ phase_cur,
+             unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
+{
+    typedef TcCfg<NCR, NHB> Cfg;
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    unsigned char* sA = tc_smem;
+    unsigned char* sB = tc_smem + 4 * kTcAPlane;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + kTcBarOff);      // b_full[2] b_empty[2] acc_full[2] acc_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int t0 = blockIdx.x * seg_len;
+    const int n_seg = min(seg_len, L - t0);
+    const int m_start = t0 / 16 - Cfg::PRE;             // first fs/16 output this CTA computes (negative inside the halo)
+    const int m_end = (t0 + n_seg) / 16;
+    const int ntiles = (m_end - m_start + 127) / 128;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(bars + (i < 2 ? i : i + 4))));   // b_full, acc_empty
+            for (int i = 2; i < 6; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));                       // b_empty, acc_full
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(coef_img + (size_t)blockIdx.y * 4 * (kTcAPlane / 4));
+        float4* dst = reinterpret_cast<float4*>(sA);
+        for (int i = tid; i < 4 * kTcAPlane / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+    }
+    if (blockIdx.x == gridDim.x - 1 && blockIdx.y == 0) save_halo(x, fmt, halo_cur, halo_next, L);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = *tmem_slot;
+    uint64_t* b_full = bars;
+    uint64_t* b_empty = bars + 2;
+    uint64_t* acc_full = bars + 4;
+    uint64_t* acc_empty = bars + 6;
+
+    if (warp >= 4 && warp < 8) {
+        // ===== producers: wideband samples -> tf32 hi/lo planes of the Hankel operand =====
+        const int ptid = tid - 128;
+        for (int it = 0; it < ntiles; it++) {
+            const int s = it & 1;
+            bar_wait(b_empty + s, ((it >> 1) & 1) ^ 1);
+            unsigned char* pl = sB + s * 4 * kTcBPlane;
+            const int mt = m_start + 128 * it;
+            for (int idx = ptid; idx < 576; idx += 128) {
+                const int r = idx & 7, w = idx >> 3;
+                const int i0 = 16 * (mt + 16 * r - 2) + 4 * w;           // first of 4 consecutive samples; i0 % 4 == 0
+                float4 a, b;                                              // (re0, im0, re1, im1), (re2, im2, re3, im3)
+                if (i0 < 0) {
+                    const float4* h = reinterpret_cast<const float4*>(halo_cur + (kHaloMax + i0));
+                    a = __ldg(h);
+                    b = __ldg(h + 1);
+                } else if (i0 >= L) {
+                    a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    b = a;
+                } else if (fmt == 0) {
+                    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(x) + i0);
+                    a = __ldg(p);
+                    b = __ldg(p + 1);
+                } else if (fmt == 1) {
+                    const int4 v = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const short2*>(x) + i0));
+                    a = make_float4((float)(short)(v.x & 0xffff), (float)(short)(v.x >> 16), (float)(short)(v.y & 0xffff), (float)(short)(v.y >> 16));
+                    b = make_float4((float)(short)(v.z & 0xffff), (float)(short)(v.z >> 16), (float)(short)(v.w & 0xffff), (float)(short)(v.w >> 16));
+                } else {
+                    const float2 s0 = fetch_sample(x, 2, i0), s1 = fetch_sample(x, 2, i0 + 1), s2 = fetch_sample(x, 2, i0 + 2),
+                                 s3 = fetch_sample(x, 2, i0 + 3);
+                    a = make_float4(s0.x, s0.y, s1.x, s1.y);
+                    b = make_float4(s2.x, s2.y, s3.x, s3.y);
+                }
+                const float4 rh = make_float4(tf32_rn(a.x), tf32_rn(a.z), tf32_rn(b.x), tf32_rn(b.z));
+                const float4 ih = make_float4(tf32_rn(a.y), tf32_rn(a.w), tf32_rn(b.y), tf32_rn(b.w));
+                const float4 rl = make_float4(tf32_rn(a.x - rh.x), tf32_rn(a.z - rh.y), tf32_rn(b.x - rh.z), tf32_rn(b.z - rh.w));
+                const float4 il = make_float4(tf32_rn(a.y - ih.x), tf32_rn(a.w - ih.y), tf32_rn(b.y - ih.z), tf32_rn(b.w - ih.w));
+                *reinterpret_cast<float4*>(pl + 16 * idx) = rh;
+                *reinterpret_cast<float4*>(pl + kTcBPlane + 16 * idx) = rl;
+                *reinterpret_cast<float4*>(pl + 2 * kTcBPlane + 16 * idx) = ih;
+                *reinterpret_cast<float4*>(pl + 3 * kTcBPlane + 16 * idx) = il;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(b_full + s);
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_na = idesc | (1u << 13);       // negate A
+        const uint32_t a0 = smem_u32(sA);
+        for (int it = 0; it < ntiles; it++) {
+            const int s = it & 1;
+            const uint32_t par = (it >> 1) & 1;
+            bar_wait(b_full + s, par);
+            bar_wait(acc_empty + s, par ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t b0 = smem_u32(sB + s * 4 * kTcBPlane);
+                // planes: A 0=Ar_hi 1=Ar_lo 2=Ai_hi 3=Ai_lo;  B 0=Xr_hi 1=Xr_lo 2=Xi_hi 3=Xi_lo. Small terms first.
+                const int a_re[6] = {1, 0, 3, 2, 0, 2}, b_re[6] = {0, 1, 2, 3, 0, 2}, n_re[6] = {0, 0, 1, 1, 0, 1};
+                const int a_im[6] = {1, 0, 3, 2, 0, 2}, b_im[6] = {2, 3, 0, 1, 2, 0};
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t d = tm + (uint32_t)(s * 256 + half * 128);
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int t = 0; t < 6; t++) {
+                        const int ap = half ? a_im[t] : a_re[t], bp = half ? b_im[t] : b_re[t];
+                        const uint32_t id = (!half && n_re[t]) ? idesc_na : idesc;
+#pragma unroll
+                        for (int ks = 0; ks < 6; ks++) {
+                            tc_mma(d, tc_desc(a0 + ap * kTcAPlane + 256 * ks, 128, 1536), tc_desc(b0 + bp * kTcBPlane + 256 * ks, 128, 512), id, acc);
+                            acc = 1;
+                        }
+                    }
+                }
+                tc_commit(b_empty + s);
+                tc_commit(acc_full + s);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: TMEM lane = channel =====
+        const int c = blockIdx.y * 128 + tid;
+        const bool valid = c < nch;
+        NcoDev p = nco[valid ? c : 0];
+        const unsigned long long ph0 = phase_cur[valid ? c : 0];
+        if (blockIdx.x == 0 && valid) phase_next[c] = ph0 + (unsigned long long)L * p.inc;
+        const float2 w16 = make_float2(p.wtc, p.wts);
+        CicSt st[NCR > 0 ? NCR : 1];
+        float2 ev[NCR > 0 ? NCR : 1];
+        Hb11St hs[NHB > 0 ? NHB : 1];
+#pragma unroll
+        for (int i = 0; i < (NCR > 0 ? NCR : 1); i++) {
+            st[i].xodd = make_float2(0.f, 0.f);
+            st[i].xeven = make_float2(0.f, 0.f);
+            ev[i] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < (NHB > 0 ? NHB : 1); i++) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) hs[i].e[k] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 3; k++) hs[i].o[k] = make_float2(0.f, 0.f);
+        }
+        EmitCtx em;
+        em.od = od;
+        em.row_lo = valid ? (long long)(t0 / (16 << (NCR + NHB))) : 0x7fffffffffffffffLL;
+        em.row_hi = (long long)((t0 + n_seg) / (16 << (NCR + NHB)));
+        em.c = c;
+        em.scale = scale;
+        em.h0 = c_hb_taps[0]; em.h2 = c_hb_taps[1]; em.h4 = c_hb_taps[2];
+        const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16);
+        for (int it = 0; it < ntiles; it++) {
+            const int s = it & 1;
+            bar_wait(acc_full + s, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tcol = lane_base + (uint32_t)(s * 256);
+            const int mt = m_start + 128 * it;
+#pragma unroll 1
+            for (int r = 0; r < 8; r++) {
+                float re[16], im[16];
+#pragma unroll
+                for (int g = 0; g < 16; g++) {
+                    re[g] = tmem_ld1(tcol + (uint32_t)(8 * g + r));
+                    im[g] = tmem_ld1(tcol + (uint32_t)(128 + 8 * g + r));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int m0 = mt + 16 * r;                                   // multiple of 16
+                // output m is rotated by the oscillator value of its newest input sample 16m+15: phase P + (16m+16) inc
+                float2 S = seed_osc(ph0 + (unsigned long long)(long long)(16 * m0 + 16) * p.inc);
+                TcStrip<NCR, NHB, 0, 16>::run(re, im, S, w16, st, ev, hs, (long long)(m0 >> NCR), em);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(acc_empty + s);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
+}
+
+typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const float*, const NcoDev*, const unsigned long long*,
+                      unsigned long long*, int, OutDesc, float);
+static K1TFn k1t_kernel(int ncr, int nhb)
+{
+    static const K1TFn table[3][3] = {{k_mix_tc<0, 0>, k_mix_tc<0, 1>, k_mix_tc<0, 2>},
+                                      {k_mix_tc<1, 0>, k_mix_tc<1, 1>, k_mix_tc<1, 2>},
+                                      {k_mix_tc<2, 0>, k_mix_tc<2, 1>, k_mix_tc<2, 2>}};
+    return table[ncr][nhb];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -620,6 +968,7 @@ Decimator::~Decimator()
     for (auto& e : ev_k2_) if (e) cudaEventDestroy(e);
     for (auto& p : ev_pool_) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaFree(d_nco_);
+    cudaFree(d_tc_coef_);
     cudaFree(d_phase_[0]);
     cudaFree(d_phase_[1]);
     for (float2* p : d_stage_) cudaFree(p);
@@ -659,7 +1008,7 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     if (n_out_ > kDecRing - kFirFft) { set_error("decimated block of %d samples exceeds the FIR ring", n_out_); return CUTESDR_E_ARG; }
     CSDR_TRY(upload_taps());
 
-    h_nco_.assign(stride_, NcoDev{0ull, 1.f, 0.f, 1.f, 0.f});
+    h_nco_.assign(stride_, NcoDev{0ull, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f});
     CSDR_CK(cudaMalloc(&d_nco_, stride_ * sizeof(NcoDev)));
     for (int k = 0; k < 2; k++) {
         CSDR_CK(cudaMalloc(&d_phase_[k], stride_ * sizeof(unsigned long long)));
@@ -735,6 +1084,39 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
         fprintf(stderr, "[cutesdr] kernel-1 <%d,%d>: tile %d + halo %d, grid %d x %d, %d CTAs/SM\n", ncic_, nhbf_, tile_len_, H,
                 (block_len + tile_len_ - 1) / tile_len_, chan_blocks, occ);
     }
+    // kernel 1T: the ladder starts with >= 4 CIC3 stages and the block is a whole number of 256-sample units
+    tc_ = ncic_ >= 4 && ncic_ <= 6 && block_len % 256 == 0 && block_len >= 4096 && !getenv("CUTESDR_NO_TC");
+    if (tc_) {
+        const int ncr = ncic_ - 4;
+        if (16 * tc_pre(ncr, nhbf_) + 32 > kHaloMax) tc_ = false;
+    }
+    if (tc_) {
+        tc_groups_ = (stride_ + 127) / 128;
+        CSDR_CK(cudaMalloc(&d_tc_coef_, (size_t)tc_groups_ * 4 * kTcAPlane));
+        K1TFn tf = k1t_kernel(ncic_ - 4, nhbf_);
+        CSDR_CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+        // one persistent CTA per SM: time segments x channel groups ~ the SM count; every segment pays
+        // PRE priming outputs and rounds up to whole 128-output MMA tiles
+        const int pre = tc_pre(ncic_ - 4, nhbf_);
+        double best = 1e300;
+        int best_seg = block_len;
+        for (int segs = 1; segs <= std::max(1, 2 * sms / tc_groups_); segs++) {
+            int sl = (block_len + segs - 1) / segs;
+            sl = (sl + 255) / 256 * 256;
+            const int real = (block_len + sl - 1) / sl;
+            const long long grid = (long long)real * tc_groups_;
+            const long long waves = (grid + sms - 1) / sms;
+            const int tiles = (sl / 16 + pre + 127) / 128;
+            const double cost = (double)waves * (tiles + 0.6);          // + fixed per-CTA setup (A image, TMEM alloc)
+            if (cost < best * 0.999) { best = cost; best_seg = sl; }
+        }
+        tc_seg_len_ = best_seg;
+        if (const char* e = getenv("CUTESDR_TC_SEG")) tc_seg_len_ = std::max(256, atoi(e) / 256 * 256);           // tuning aid
+        tc_dirty_ = true;
+        if (getenv("CUTESDR_DEBUG_TIMING"))
+            fprintf(stderr, "[cutesdr] kernel-1T <%d,%d>: segment %d (+%d priming), grid %d x %d\n", ncic_ - 4, nhbf_, tc_seg_len_,
+                    16 * pre, (block_len + tc_seg_len_ - 1) / tc_seg_len_, tc_groups_);
+    }
     dirty_ = true;
     return CUTESDR_OK;
 }
@@ -754,7 +1136,10 @@ void Decimator::set_frequency(int i, double nco_freq)
     n.inc = inc;
     n.w1c = (float)cos(a1); n.w1s = (float)sin(a1);
     n.wgc = (float)cos(aB); n.wgs = (float)sin(aB);
+    const double a16 = kTwoPi * (double)((long double)(inc * 16ull) / 18446744073709551616.0L);
+    n.wtc = (float)cos(a16); n.wts = (float)sin(a16);
     dirty_ = true;
+    tc_dirty_ = true;
 }
 
 int Decimator::upload_dirty()
@@ -810,7 +1195,19 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
         CSDR_CK(cudaEventRecord(ev_a, st_));
     }
     const int Q = std::max((1 << ncic_) << nhbf_, k1_body(ncic_));
-    if (L % Q == 0) {
+    if (tc_ && L % 256 == 0) {
+        if (tc_dirty_) {
+            const int n = tc_groups_ * 128 * 48;
+            k_tc_coeffs<<<(n + 255) / 256, 256, 0, st_>>>(d_nco_, stride_, tc_groups_, d_tc_coef_);
+            lc_->n++;
+            CSDR_CK(cudaGetLastError());
+            tc_dirty_ = false;
+        }
+        const int sl = std::min(tc_seg_len_, L);
+        dim3 grid((L + sl - 1) / sl, tc_groups_);
+        k1t_kernel(ncic_ - 4, nhbf_)<<<grid, kTcThreads, kTcSmem, st_>>>(d_x, fmt, halo_cur, halo_next, L, sl, d_tc_coef_, d_nco_, pc, pn,
+                                                                          stride_, od, scale);
+    } else if (L % Q == 0) {
         const int threads = std::min(256, round_up(stride_, 32));
         dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);
         const int H = k1_halo(ncic_, nhbf_);

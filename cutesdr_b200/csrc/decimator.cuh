@@ -23,6 +23,7 @@ struct NcoDev {
     unsigned long long inc;   // phase increment per input sample, turns * 2^64
     float w1c, w1s;           // e^{j inc}
     float wgc, wgs;           // e^{j G inc}, G = 2^ncic
+    float wtc, wts;           // e^{j 16 inc} (kernel 1T's oscillator step at fs/16)
 };
 
 class Decimator {
@@ -79,6 +80,10 @@ private:
     LaunchCounter* lc_ = nullptr;
     std::vector<NcoDev> h_nco_;
     bool dirty_ = true;
+    // kernel 1T (tensor-core form of kernel 1, used when the ladder starts with >= 4 CIC3 stages)
+    bool tc_ = false, tc_dirty_ = true;
+    int tc_seg_len_ = 0, tc_groups_ = 0;
+    float* d_tc_coef_ = nullptr;
     NcoDev* d_nco_ = nullptr;
     unsigned long long* d_phase_[2] = {nullptr, nullptr};
     int phase_cur_ = 0;
