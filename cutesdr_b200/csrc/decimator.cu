@@ -166,17 +166,41 @@ struct EmitCtx {
     int c;
     float scale;
     float h0, h2, h4;     // HB11 taps 0/2/4 (= 10/8/6); centre tap is 0.5
+    __device__ __forceinline__ void emit(long long q, float2 v) const
+    {
+        if (q >= row_lo && q < row_hi) store_out(od, q, c, make_float2(v.x * scale, v.y * scale));
+    }
+};
+
+// Kernel 1T's emitter: its outputs leave strictly in row order, so the ring position and the
+// owned-range test are running 32-bit counters instead of 64-bit index arithmetic per store.
+struct TcEmit {
+    float2* p0;           // ring base + this channel's offset
+    unsigned mask;        // ring rows - 1
+    unsigned pos;         // ring row of the next output
+    int estride;          // float2 elements between ring rows
+    int rel;              // next output's row - first owned row (negative while priming)
+    int n_rows;           // rows this segment owns
+    float scale;
+    float h0, h2, h4;
+    __device__ __forceinline__ void emit(long long, float2 v)
+    {
+        float2* dst = p0 + (size_t)pos * (size_t)estride;
+        if ((unsigned)rel < (unsigned)n_rows) *dst = make_float2(v.x * scale, v.y * scale);
+        rel++;
+        pos = (pos + 1) & mask;
+    }
 };
 
 // 11-tap half-band decimate-by-2 in direct form on a register delay line
 // (y[m] = sum_j h[j] x[2m-10+j], dsp/downconvert.cpp:348-423): an output is complete when the
 // even-indexed input x[2m] arrives; odd-indexed inputs only feed the centre tap three outputs later.
 // q = block-relative index of v at this stage (may be negative inside the halo).
-template <int NHB, int J>
-__device__ __forceinline__ void hb_feed(float2 v, long long q, Hb11St* hs, const EmitCtx& em)
+template <int NHB, int J, class E>
+__device__ __forceinline__ void hb_feed(float2 v, long long q, Hb11St* hs, E& em)
 {
     if constexpr (J == NHB) {
-        if (q >= em.row_lo && q < em.row_hi) store_out(em.od, q, em.c, make_float2(v.x * em.scale, v.y * em.scale));
+        em.emit(q, v);
     } else {
         Hb11St& s = hs[J];
         if ((q & 1) == 0) {
@@ -184,7 +208,7 @@ __device__ __forceinline__ void hb_feed(float2 v, long long q, Hb11St* hs, const
             y.x = fmaf(em.h0, s.e[4].x + v.x, fmaf(em.h2, s.e[3].x + s.e[0].x, fmaf(em.h4, s.e[2].x + s.e[1].x, 0.5f * s.o[2].x)));
             y.y = fmaf(em.h0, s.e[4].y + v.y, fmaf(em.h2, s.e[3].y + s.e[0].y, fmaf(em.h4, s.e[2].y + s.e[1].y, 0.5f * s.o[2].y)));
             s.e[4] = s.e[3]; s.e[3] = s.e[2]; s.e[2] = s.e[1]; s.e[1] = s.e[0]; s.e[0] = v;
-            hb_feed<NHB, J + 1>(y, q >> 1, hs, em);
+            hb_feed<NHB, J + 1, E>(y, q >> 1, hs, em);
         } else {
             s.o[2] = s.o[1]; s.o[1] = s.o[0]; s.o[0] = v;
         }
@@ -194,8 +218,8 @@ __device__ __forceinline__ void hb_feed(float2 v, long long q, Hb11St* hs, const
 // First fused half-band when a body carries an EVEN number of CIC outputs (B/G >= 2): tiles start on
 // multiples of 2G, so the body's CIC output IDX is even-indexed iff IDX is even -- a compile-time
 // fact, no branch, and the compiler can keep the delay line in fixed registers.
-template <int NHB, int IDX>
-__device__ __forceinline__ void hb_feed_static(float2 v, int q0, Hb11St* hs, const EmitCtx& em)
+template <int NHB, int IDX, class E>
+__device__ __forceinline__ void hb_feed_static(float2 v, int q0, Hb11St* hs, E& em)
 {
     Hb11St& s = hs[0];
     if constexpr ((IDX & 1) == 0) {
@@ -203,7 +227,7 @@ __device__ __forceinline__ void hb_feed_static(float2 v, int q0, Hb11St* hs, con
         y.x = fmaf(em.h0, s.e[4].x + v.x, fmaf(em.h2, s.e[3].x + s.e[0].x, fmaf(em.h4, s.e[2].x + s.e[1].x, 0.5f * s.o[2].x)));
         y.y = fmaf(em.h0, s.e[4].y + v.y, fmaf(em.h2, s.e[3].y + s.e[0].y, fmaf(em.h4, s.e[2].y + s.e[1].y, 0.5f * s.o[2].y)));
         s.e[4] = s.e[3]; s.e[3] = s.e[2]; s.e[2] = s.e[1]; s.e[1] = s.e[0]; s.e[0] = v;
-        hb_feed<NHB, 1>(y, (long long)((q0 + IDX) >> 1), hs, em);
+        hb_feed<NHB, 1, E>(y, (long long)((q0 + IDX) >> 1), hs, em);
     } else {
         s.o[2] = s.o[1]; s.o[1] = s.o[0]; s.o[0] = v;
     }
@@ -211,13 +235,13 @@ __device__ __forceinline__ void hb_feed_static(float2 v, int q0, Hb11St* hs, con
 
 // CIC3 decimate-by-2, scale .125 folded into the kernel's output scale
 // (y = odd + Xeven + 3*(Xodd + even), dsp/downconvert.cpp:450-455).
-template <int NCIC, int NHB, int S, int IDX>
-__device__ __forceinline__ void cic_feed(float2 v, CicSt* st, float2* ev, Hb11St* hs, long long q0, const EmitCtx& em)
+template <int NCIC, int NHB, int S, int IDX, class E>
+__device__ __forceinline__ void cic_feed(float2 v, CicSt* st, float2* ev, Hb11St* hs, long long q0, E& em)
 {
     if constexpr (S == NCIC) {
         constexpr int G = 1 << NCIC, B = G < 32 ? 32 : G;
-        if constexpr (NHB >= 1 && (B / G) >= 2) hb_feed_static<NHB, IDX>(v, (int)q0, hs, em);
-        else hb_feed<NHB, 0>(v, q0 + IDX, hs, em);
+        if constexpr (NHB >= 1 && (B / G) >= 2) hb_feed_static<NHB, IDX, E>(v, (int)q0, hs, em);
+        else hb_feed<NHB, 0, E>(v, q0 + IDX, hs, em);
     } else if constexpr ((IDX & 1) == 0) {
         ev[S] = v;
     } else {
@@ -226,7 +250,7 @@ __device__ __forceinline__ void cic_feed(float2 v, CicSt* st, float2* ev, Hb11St
         r.y = (v.y + st[S].xeven.y) + 3.0f * (st[S].xodd.y + e.y);
         st[S].xodd = v;
         st[S].xeven = e;
-        cic_feed<NCIC, NHB, S + 1, (IDX >> 1)>(r, st, ev, hs, q0, em);
+        cic_feed<NCIC, NHB, S + 1, (IDX >> 1), E>(r, st, ev, hs, q0, em);
     }
 }
 
@@ -237,7 +261,7 @@ template <int NCIC, int NHB, int K, int B> struct Body {
         float2 xv = t[K];                 // all lanes read the same address: broadcast LDS
         float2 y = cmul(xv, o);           // mixer, dsp/downconvert.cpp:238-239
         if (K + 1 < B) o = cmul(o, w);    // oscillator step, :211-212
-        cic_feed<NCIC, NHB, 0, K>(y, st, ev, hs, q0, em);
+        cic_feed<NCIC, NHB, 0, K, const EmitCtx>(y, st, ev, hs, q0, em);
         Body<NCIC, NHB, K + 1, B>::run(t, o, w, st, ev, hs, q0, em);
     }
 };
@@ -425,35 +449,43 @@ static K1Fn k1_kernel(int ncic, int nhb)
 
 
 // ------------------------------------------------------------------------------------------
-// K1T: kernel 1 on the tensor cores (tcgen05, kind::tf32, accumulators in TMEM).
+// K1T: kernel 1 on the tensor cores (tcgen05, kind::tf32, operands and accumulators in TMEM).
 //
 // The NCO mix followed by the first FOUR CIC3 stages is one complex FIR-decimate-by-16 per channel,
 //     y4[m] = sum_{j<46} H[j] x[16m+15-j] e^{j phi(16m+15-j)}
 //           = e^{j phi(16m+15)} * sum_k A_c[k] x[16(m-2)+k],   A_c[k] = H[47-k] e^{-j 2 pi (47-k) f_c/fs},
 // i.e. a GEMM  Y[channel, time] = A[channel, 48] * X[48, time]  against a Hankel matrix of the wideband
-// block that every channel shares. A CTA owns 128 channels (the MMA's M) and a time segment; per tile of
-// 128 outputs (2048 input samples) it issues  D_re = Ar Xr - Ai Xi,  D_im = Ar Xi + Ai Xr  as M128 N128 K8
-// MMAs with every operand split into tf32 hi + lo parts (3 products per term: lo*hi, hi*lo, hi*hi; the
-// dropped lo*lo is 2^-22 relative), fp32 accumulation in TMEM.
-//   * A (per-channel coefficients, 4 planes Ar/Ai x hi/lo, 96 KB) stays resident in shared memory,
-//     K-major, no swizzle: byte (row, k) = 16 (row%8) + 1536 (row/8) + 128 (k/4) + 4 (k%4).
-//   * X is staged by 4 producer warps as 4 planes (re/im x hi/lo) of 8 interleaved STRIPS: strip r holds
-//     288 consecutive samples, 16-byte chunk w of strip r at byte 16 r + 128 w. MMA row n = 8 g + r then
-//     reads chunks 4 g + (k/4): descriptor LBO 128, SBO 512 -- overlapping rows, so the Hankel matrix
-//     costs 9/8 of the raw samples instead of 3x. Column n of the accumulator is output m0 + 16 r + g.
-//   * 4 epilogue warps (TMEM lane = channel) read the columns in time order, multiply by the
-//     oscillator at the decimated rate (re-seeded exactly from the 64-bit phase every 16 outputs), and
-//     run the remaining CIC3 / fused 11-tap half-band stages and the store exactly as kernel 1 does.
-//   * B is double-buffered in shared memory, the accumulators in TMEM (2 x 256 columns), so staging,
-//     MMA and epilogue of consecutive tiles overlap; mbarriers + tcgen05.commit order them.
+// block that every channel shares. A CTA owns 128 channels (the MMA's M); per tile of 32 outputs (512
+// input samples) it issues  D_re = Ar Xr - Ai Xi,  D_im = Ar Xi + Ai Xr  as M128 N32 K8 MMAs with every
+// operand split into tf32 hi + lo parts (3 products per term: lo*hi, hi*lo, hi*hi; the dropped lo*lo is
+// 2^-22 relative), fp32 accumulation in TMEM.
+//   * A (per-channel coefficients, planes Ar/Ai x hi/lo, 48 columns each) lives in TMEM for the whole
+//     CTA: the MMAs read only B from shared memory (an SS-form MMA of this shape saturates the 128 B/clk
+//     shared-memory port with its A re-reads).
+//   * X is staged by 4 producer warps (one tile per warp, 4 tiles in flight) as 4 planes (re/im x hi/lo)
+//     in NATURAL time order with zero duplication: 16-byte chunk q (4 samples) of X-row m (16 samples) sits
+//     at byte 16 m + P q. K-major, no swizzle, LBO = P, SBO = 128: MMA row n reads row m0-2+n+shift, and the
+//     three 16-sample shifts of the Hankel matrix are just the descriptor start address + 16 * shift.
+//   * 4 independent time segments per CTA, interleaved tile by tile; segment e owns TMEM accumulator slot
+//     e and epilogue warp set e (4 warps, TMEM lane = channel). An epilogue thread pulls 16 consecutive
+//     outputs per tcgen05.ld, multiplies by the oscillator at the decimated rate (re-seeded exactly from
+//     the 64-bit phase every 32 outputs), and runs the remaining CIC3 / fused 11-tap half-band stages and
+//     the store exactly as kernel 1 does. 16 epilogue warps keep 4 warps per scheduler busy, which this
+//     dependent-chain code needs; the accumulator slot is released as soon as its values are in registers.
+//   * mbarriers + tcgen05.commit order producers -> MMA -> epilogue; B runs through an 8-stage ring.
 // Segments re-prime the feed-forward stages with a halo of PRE outputs, like kernel 1's tiles.
 // ------------------------------------------------------------------------------------------
-constexpr int kTcAPlane = 16 * 1536;                      // bytes per A plane (128 rows x 48 tf32)
-constexpr int kTcBPlane = 72 * 128;                       // bytes per B plane (8 strips x 72 chunks x 16 B)
-constexpr int kTcBarOff = 4 * kTcAPlane + 8 * kTcBPlane;
-constexpr int kTcSmem = kTcBarOff + 128;
-constexpr int kTcThreads = 288;                           // 4 epilogue + 4 producer + 1 MMA warp
-
+constexpr int kTcN = 32;                                  // outputs (fs/16) per MMA tile
+constexpr int kTcRows = kTcN + 2;                         // X rows per tile (two rows of history)
+constexpr int kTcP = kTcRows * 16;                        // bytes per chunk-column q of a plane
+constexpr int kTcPlane = 4 * kTcP;                        // bytes per B plane
+constexpr int kTcStage = 4 * kTcPlane;                    // Xr_hi, Xr_lo, Xi_hi, Xi_lo
+constexpr int kTcStages = 8;
+constexpr int kTcBarOff = kTcStages * kTcStage;
+constexpr int kTcSmem = kTcBarOff + 512;
+constexpr int kTcSegs = 2;                                // time segments (= accumulator slots = epilogue sets) per CTA
+constexpr int kTcThreads = 32 * (4 * kTcSegs + 4 + 2 * kTcSegs);    // 8 epilogue + 4 producer + 4 MMA warps
+constexpr int kTcAccCol = 192;                            // TMEM: A planes in columns 0..191; segment e, slot b (tile parity) at 192 + 4 kTcN e + 2 kTcN b (re | im)
 
 template <int NCR, int NHB> struct TcCfg {
     static constexpr int Gr = 1 << NCR;                                             // fs/16 samples per CIC-chain output
@@ -476,18 +508,13 @@ __device__ __forceinline__ float tf32_rn(float x)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
-{
-    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) |
-           (1ull << 46);
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar)
@@ -510,20 +537,42 @@ __device__ __forceinline__ void bar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float tmem_ld1(uint32_t taddr)
+// one lane of a converged warp; ptxas recognises elect.sync and keeps the guarded code on the uniform datapath
+__device__ __forceinline__ bool elect_one()
 {
-    uint32_t v;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
-    return __uint_as_float(v);
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// 16 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
 }
 
-// A-operand images for every 128-channel group: [group][Ar_hi, Ar_lo, Ai_hi, Ai_lo][kTcAPlane bytes]
-__global__ void k_tc_coeffs(const NcoDev* __restrict__ nco, int nch, int groups, float* __restrict__ img)
+// A-operand table: [channel (padded to whole 128-channel groups)][Ar_hi, Ar_lo, Ai_hi, Ai_lo][48]
+__global__ void k_tc_coeffs(const NcoDev* __restrict__ nco, int nch, int groups, float* __restrict__ tab)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= groups * 128 * 48) return;
-    const int k = idx % 48, row = (idx / 48) % 128, cg = idx / (48 * 128);
-    const int c = cg * 128 + row, j = 47 - k;
+    const int k = idx % 48, c = idx / 48, j = 47 - k;
     double ar = 0.0, ai = 0.0;
     if (c < nch && j < 46) {
         const unsigned long long ph = 0ull - nco[c].inc * (unsigned long long)j;       // -j * inc, turns * 2^64 (wraps)
@@ -534,163 +583,255 @@ __global__ void k_tc_coeffs(const NcoDev* __restrict__ nco, int nch, int groups,
     }
     const float rh = tf32_rn((float)ar), rl = tf32_rn((float)(ar - (double)rh));
     const float ih = tf32_rn((float)ai), il = tf32_rn((float)(ai - (double)ih));
-    const int off = (16 * (row & 7) + 1536 * (row >> 3) + 128 * (k >> 2) + 4 * (k & 3)) >> 2;
-    float* g = img + (size_t)cg * 4 * (kTcAPlane / 4);
-    g[off] = rh;
-    g[(kTcAPlane / 4) + off] = rl;
-    g[2 * (kTcAPlane / 4) + off] = ih;
-    g[3 * (kTcAPlane / 4) + off] = il;
+    float* row = tab + (size_t)c * 192;
+    row[k] = rh;
+    row[48 + k] = rl;
+    row[96 + k] = ih;
+    row[144 + k] = il;
+}
+
+// 4 consecutive samples starting at i0 (i0 % 4 == 0) for the cases off the fast path: inside the saved halo (i0 < 0),
+// past the block end (zeros; only feeds outputs nobody keeps) or an integer wire format
+struct TcChunk { float4 a, b; };
+__device__ __noinline__ TcChunk tc_load_chunk_slow(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, int i0, int L)
+{
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (i0 < 0) {
+        const float4* h = reinterpret_cast<const float4*>(halo_cur + (kHaloMax + i0));
+        a = __ldg(h);
+        b = __ldg(h + 1);
+    } else if (i0 >= L) {
+    } else if (fmt == 0) {
+        const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(x) + i0);
+        a = __ldg(q);
+        b = __ldg(q + 1);
+    } else if (fmt == 1) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const short2*>(x) + i0));
+        a = make_float4((float)(short)(v.x & 0xffff), (float)(short)(v.x >> 16), (float)(short)(v.y & 0xffff), (float)(short)(v.y >> 16));
+        b = make_float4((float)(short)(v.z & 0xffff), (float)(short)(v.z >> 16), (float)(short)(v.w & 0xffff), (float)(short)(v.w >> 16));
+    } else {
+        const float2 s0 = fetch_sample(x, 2, i0), s1 = fetch_sample(x, 2, i0 + 1), s2 = fetch_sample(x, 2, i0 + 2), s3 = fetch_sample(x, 2, i0 + 3);
+        a = make_float4(s0.x, s0.y, s1.x, s1.y);
+        b = make_float4(s2.x, s2.y, s3.x, s3.y);
+    }
+    TcChunk r;
+    r.a = a;
+    r.b = b;
+    return r;
 }
 
 template <int NCR, int NHB, int G0, int G1> struct TcStrip {
     static __device__ __forceinline__ void run(const float* re, const float* im, float2& S, float2 w, CicSt* st, float2* ev, Hb11St* hs,
-                                               long long q0, const EmitCtx& em)
+                                               TcEmit& em)
     {
         float2 v = cmul(make_float2(re[G0], im[G0]), S);
-        if (G0 + 1 < G1) S = cmul(S, w);
-        cic_feed<NCR, NHB, 0, G0>(v, st, ev, hs, q0, em);
-        TcStrip<NCR, NHB, G0 + 1, G1>::run(re, im, S, w, st, ev, hs, q0, em);
+        S = cmul(S, w);
+        cic_feed<NCR, NHB, 0, G0, TcEmit>(v, st, ev, hs, 0LL, em);
+        TcStrip<NCR, NHB, G0 + 1, G1>::run(re, im, S, w, st, ev, hs, em);
     }
 };
 template <int NCR, int NHB, int G1> struct TcStrip<NCR, NHB, G1, G1> {
-    static __device__ __forceinline__ void run(const float*, const float*, float2&, float2, CicSt*, float2*, Hb11St*, long long,
-                                               const EmitCtx&) {}
+    static __device__ __forceinline__ void run(const float*, const float*, float2&, float2, CicSt*, float2*, Hb11St*, TcEmit&) {}
 };
 
 template <int NCR, int NHB>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_mix_tc(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, float2* __restrict__ halo_next, int L, int seg_len,
-             const float* __restrict__ coef_img, const NcoDev* __restrict__ nco, const unsigned long long* __restrict__ phase_cur,
+             const float* __restrict__ coef_tab, const NcoDev* __restrict__ nco, const unsigned long long* __restrict__ phase_cur,
              unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
 {
     typedef TcCfg<NCR, NHB> Cfg;
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    unsigned char* sA = tc_smem;
-    unsigned char* sB = tc_smem + 4 * kTcAPlane;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + kTcBarOff);      // b_full[2] b_empty[2] acc_full[2] acc_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    unsigned char* sB = tc_smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + kTcBarOff);
+    uint64_t* b_full = bars;                                  // [kTcStages] a producer warp filled the stage
+    uint64_t* b_empty = bars + kTcStages;                     // [kTcStages] the MMAs that read the stage completed
+    uint64_t* acc_full = bars + 2 * kTcStages;                // [kTcSegs][2] the tile's MMAs completed (slot = tile parity)
+    uint64_t* acc_empty = acc_full + 2 * kTcSegs;             // [kTcSegs][2] the epilogue set pulled the tile out of TMEM
+    uint64_t* a_ready = acc_empty + 2 * kTcSegs;              // A planes are in TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int kMmaWarp = 4 * kTcSegs + 4;                 // first of the 2 kTcSegs MMA-issuing warps
 
-    const int t0 = blockIdx.x * seg_len;
-    const int n_seg = min(seg_len, L - t0);
-    const int m_start = t0 / 16 - Cfg::PRE;             // first fs/16 output this CTA computes (negative inside the halo)
-    const int m_end = (t0 + n_seg) / 16;
-    const int ntiles = (m_end - m_start + 127) / 128;
+    // segment e of this CTA: start sample, length, first fs/16 output computed (negative inside the halo), tile count.
+    // Pure arithmetic on purpose (no per-segment arrays: dynamic indexing would put them in local memory).
+    auto seg_geom = [&](int e, int& t0, int& n_seg, int& m0, int& tiles) {
+        const long long t = (long long)(kTcSegs * blockIdx.x + e) * seg_len;
+        t0 = (int)min(t, (long long)L);
+        n_seg = max(0, min(seg_len, L - t0));
+        m0 = t0 / 16 - Cfg::PRE;
+        tiles = n_seg > 0 ? (n_seg / 16 + Cfg::PRE + kTcN - 1) / kTcN : 0;
+    };
+    auto seg_tiles = [&](int e) {
+        int a, b, c2, t;
+        seg_geom(e, a, b, c2, t);
+        return t;
+    };
+    const int max_tiles = seg_tiles(0);          // segment 0 of a CTA is never shorter than its later ones
 
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         if (lane == 0) {
-            for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(bars + (i < 2 ? i : i + 4))));   // b_full, acc_empty
-            for (int i = 2; i < 6; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));                       // b_empty, acc_full
+            for (int i = 0; i < kTcStages; i++) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 64;" ::"r"(smem_u32(b_full + i)));      // two producer warps
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_u32(b_empty + i)));      // the re and the im issuer
+            }
+            for (int i = 0; i < 2 * kTcSegs; i++) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_u32(acc_full + i)));
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(acc_empty + i)));
+            }
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(a_ready)), "r"(128 * kTcSegs));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    {
-        const float4* src = reinterpret_cast<const float4*>(coef_img + (size_t)blockIdx.y * 4 * (kTcAPlane / 4));
-        float4* dst = reinterpret_cast<float4*>(sA);
-        for (int i = tid; i < 4 * kTcAPlane / 16; i += kTcThreads) dst[i] = __ldg(src + i);
-    }
     if (blockIdx.x == gridDim.x - 1 && blockIdx.y == 0) save_halo(x, fmt, halo_cur, halo_next, L);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = *tmem_slot;
-    uint64_t* b_full = bars;
-    uint64_t* b_empty = bars + 2;
-    uint64_t* acc_full = bars + 4;
-    uint64_t* acc_empty = bars + 6;
 
-    if (warp >= 4 && warp < 8) {
-        // ===== producers: wideband samples -> tf32 hi/lo planes of the Hankel operand =====
-        const int ptid = tid - 128;
-        for (int it = 0; it < ntiles; it++) {
-            const int s = it & 1;
-            bar_wait(b_empty + s, ((it >> 1) & 1) ^ 1);
-            unsigned char* pl = sB + s * 4 * kTcBPlane;
-            const int mt = m_start + 128 * it;
-            for (int idx = ptid; idx < 576; idx += 128) {
-                const int r = idx & 7, w = idx >> 3;
-                const int i0 = 16 * (mt + 16 * r - 2) + 4 * w;           // first of 4 consecutive samples; i0 % 4 == 0
-                float4 a, b;                                              // (re0, im0, re1, im1), (re2, im2, re3, im3)
-                if (i0 < 0) {
-                    const float4* h = reinterpret_cast<const float4*>(halo_cur + (kHaloMax + i0));
-                    a = __ldg(h);
-                    b = __ldg(h + 1);
-                } else if (i0 >= L) {
-                    a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    b = a;
-                } else if (fmt == 0) {
-                    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(x) + i0);
-                    a = __ldg(p);
-                    b = __ldg(p + 1);
-                } else if (fmt == 1) {
-                    const int4 v = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const short2*>(x) + i0));
-                    a = make_float4((float)(short)(v.x & 0xffff), (float)(short)(v.x >> 16), (float)(short)(v.y & 0xffff), (float)(short)(v.y >> 16));
-                    b = make_float4((float)(short)(v.z & 0xffff), (float)(short)(v.z >> 16), (float)(short)(v.w & 0xffff), (float)(short)(v.w >> 16));
-                } else {
-                    const float2 s0 = fetch_sample(x, 2, i0), s1 = fetch_sample(x, 2, i0 + 1), s2 = fetch_sample(x, 2, i0 + 2),
-                                 s3 = fetch_sample(x, 2, i0 + 3);
-                    a = make_float4(s0.x, s0.y, s1.x, s1.y);
-                    b = make_float4(s2.x, s2.y, s3.x, s3.y);
-                }
-                const float4 rh = make_float4(tf32_rn(a.x), tf32_rn(a.z), tf32_rn(b.x), tf32_rn(b.z));
-                const float4 ih = make_float4(tf32_rn(a.y), tf32_rn(a.w), tf32_rn(b.y), tf32_rn(b.w));
-                const float4 rl = make_float4(tf32_rn(a.x - rh.x), tf32_rn(a.z - rh.y), tf32_rn(b.x - rh.z), tf32_rn(b.z - rh.w));
-                const float4 il = make_float4(tf32_rn(a.y - ih.x), tf32_rn(a.w - ih.y), tf32_rn(b.y - ih.z), tf32_rn(b.w - ih.w));
-                *reinterpret_cast<float4*>(pl + 16 * idx) = rh;
-                *reinterpret_cast<float4*>(pl + kTcBPlane + 16 * idx) = rl;
-                *reinterpret_cast<float4*>(pl + 2 * kTcBPlane + 16 * idx) = ih;
-                *reinterpret_cast<float4*>(pl + 3 * kTcBPlane + 16 * idx) = il;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bar_arrive(b_full + s);
-        }
-    } else if (warp == 8) {
-        // ===== MMA issuer =====
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc_na = idesc | (1u << 13);       // negate A
-        const uint32_t a0 = smem_u32(sA);
-        for (int it = 0; it < ntiles; it++) {
-            const int s = it & 1;
-            const uint32_t par = (it >> 1) & 1;
-            bar_wait(b_full + s, par);
-            bar_wait(acc_empty + s, par ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t b0 = smem_u32(sB + s * 4 * kTcBPlane);
-                // planes: A 0=Ar_hi 1=Ar_lo 2=Ai_hi 3=Ai_lo;  B 0=Xr_hi 1=Xr_lo 2=Xi_hi 3=Xi_lo. Small terms first.
-                const int a_re[6] = {1, 0, 3, 2, 0, 2}, b_re[6] = {0, 1, 2, 3, 0, 2}, n_re[6] = {0, 0, 1, 1, 0, 1};
-                const int a_im[6] = {1, 0, 3, 2, 0, 2}, b_im[6] = {2, 3, 0, 1, 2, 0};
+    if (warp >= 4 * kTcSegs && warp < kMmaWarp) {
+        // ===== producers: wideband samples -> tf32 hi/lo planes of the Hankel operand. Warp pair (pw >> 1) takes every
+        // other tile, each warp of the pair stages half of the tile's 16-byte chunks; two tiles are in flight. =====
+        const int pw = warp - 4 * kTcSegs;
+        constexpr int kChunks = 4 * kTcRows;                              // 16-byte chunks (4 samples) per plane and tile
+        constexpr int kHalf = (kChunks + 1) / 2;
+        constexpr int kRounds = (kHalf + 31) / 32;
+        int cnt = 0;
+        for (int k = 0; k < max_tiles; k++) {
+#pragma unroll 1
+            for (int e = 0; e < kTcSegs; e++) {
+                int t0, n_seg, m0, tiles;
+                seg_geom(e, t0, n_seg, m0, tiles);
+                if (k >= tiles) continue;
+                const int my = cnt++;
+                if ((my & 1) != (pw >> 1)) continue;
+                const int st = my % kTcStages;
+                unsigned char* pl = sB + st * kTcStage;
+                const int mt = m0 + kTcN * k;
+                float4 va[kRounds], vb[kRounds];                          // chunk: (re0, im0, re1, im1), (re2, im2, re3, im3)
+                const int i_lo = 16 * (mt - 2);
+                const bool fast = fmt == 0 && i_lo >= 0 && i_lo + 16 * kTcRows <= L;
+                const int c_lo = (pw & 1) * kHalf, c_hi = min(kChunks, c_lo + kHalf);
 #pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const uint32_t d = tm + (uint32_t)(s * 256 + half * 128);
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int t = 0; t < 6; t++) {
-                        const int ap = half ? a_im[t] : a_re[t], bp = half ? b_im[t] : b_re[t];
-                        const uint32_t id = (!half && n_re[t]) ? idesc_na : idesc;
-#pragma unroll
-                        for (int ks = 0; ks < 6; ks++) {
-                            tc_mma(d, tc_desc(a0 + ap * kTcAPlane + 256 * ks, 128, 1536), tc_desc(b0 + bp * kTcBPlane + 256 * ks, 128, 512), id, acc);
-                            acc = 1;
+                for (int j = 0; j < kRounds; j++) {
+                    const int idx = c_lo + lane + 32 * j;                 // chunk (row idx / 4, q = idx % 4)
+                    const int i0 = i_lo + 4 * idx;                        // first of 4 consecutive samples; i0 % 4 == 0
+                    va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vb[j] = va[j];
+                    if (idx < c_hi) {
+                        if (fast) {
+                            const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(x) + i0);
+                            va[j] = __ldg(q);
+                            vb[j] = __ldg(q + 1);
+                        } else {
+                            const TcChunk ch = tc_load_chunk_slow(x, fmt, halo_cur, i0, L);
+                            va[j] = ch.a;
+                            vb[j] = ch.b;
                         }
                     }
                 }
-                tc_commit(b_empty + s);
-                tc_commit(acc_full + s);
+                bar_wait(b_empty + st, ((my / kTcStages) & 1) ^ 1);       // loads are in flight while the MMAs drain this stage
+#pragma unroll
+                for (int j = 0; j < kRounds; j++) {
+                    const int idx = c_lo + lane + 32 * j;
+                    if (idx < c_hi) {
+                        const float4 a = va[j], b = vb[j];
+                        const float4 rh = make_float4(tf32_rn(a.x), tf32_rn(a.z), tf32_rn(b.x), tf32_rn(b.z));
+                        const float4 ih = make_float4(tf32_rn(a.y), tf32_rn(a.w), tf32_rn(b.y), tf32_rn(b.w));
+                        const float4 rl = make_float4(tf32_rn(a.x - rh.x), tf32_rn(a.z - rh.y), tf32_rn(b.x - rh.z), tf32_rn(b.z - rh.w));
+                        const float4 il = make_float4(tf32_rn(a.y - ih.x), tf32_rn(a.w - ih.y), tf32_rn(b.y - ih.z), tf32_rn(b.w - ih.w));
+                        const int off = 16 * (idx >> 2) + kTcP * (idx & 3);
+                        *reinterpret_cast<float4*>(pl + off) = rh;
+                        *reinterpret_cast<float4*>(pl + kTcPlane + off) = rl;
+                        *reinterpret_cast<float4*>(pl + 2 * kTcPlane + off) = ih;
+                        *reinterpret_cast<float4*>(pl + 3 * kTcPlane + off) = il;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bar_arrive(b_full + st);
             }
-            __syncwarp();
+        }
+    } else if (warp >= kMmaWarp) {
+        // ===== MMA issuers: one warp per (segment, re | im accumulator). A single warp sustains one tcgen05.mma per
+        // ~100 clocks whatever its shape, so the four accumulators get four issuing warps. =====
+        const int me = (warp - kMmaWarp) >> 1, half = (warp - kMmaWarp) & 1;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_na = idesc | (1u << 13);       // negate A
+        const uint32_t b_hi32 = (128u >> 4) | (1u << 14);   // SBO = 128 B (8 rows of 16 B), descriptor version 1
+        const uint32_t lo_lbo = ((uint32_t)kTcP >> 4) << 16;
+        const uint32_t d0 = tm + (uint32_t)(kTcAccCol + 4 * kTcN * me + kTcN * half);
+        bar_wait(a_ready, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int cnt = 0;
+        for (int k = 0; k < max_tiles; k++) {
+#pragma unroll 1
+            for (int e = 0; e < kTcSegs; e++) {
+                if (k >= seg_tiles(e)) continue;
+                const int my = cnt++;
+                if (e != me) continue;
+                const int st = my % kTcStages;
+                bar_wait(b_full + st, (my / kTcStages) & 1);
+                const int slot = k & 1;
+                bar_wait(acc_empty + 2 * e + slot, ((k >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t b0 = smem_u32(sB + st * kTcStage);
+                    const uint32_t d = d0 + (uint32_t)(2 * kTcN * slot);
+                    // planes: A 0=Ar_hi 1=Ar_lo 2=Ai_hi 3=Ai_lo (48 TMEM columns each);  B 0=Xr_hi 1=Xr_lo 2=Xi_hi 3=Xi_lo.
+                    // D_re = Ar Xr - Ai Xi,  D_im = Ar Xi + Ai Xr; small terms (lo*hi, hi*lo) first.
+                    constexpr int a_pl[6] = {1, 0, 3, 2, 0, 2};
+                    constexpr int b_re[6] = {0, 1, 2, 3, 0, 2}, n_re[6] = {0, 0, 1, 1, 0, 1};
+                    constexpr int b_im[6] = {2, 3, 0, 1, 2, 0};
+#pragma unroll
+                    for (int t = 0; t < 6; t++) {
+                        const int ap = a_pl[t];
+                        const int bp = half ? b_im[t] : b_re[t];
+                        const uint32_t id = (!half && n_re[t]) ? idesc_na : idesc;
+#pragma unroll
+                        for (int ks = 0; ks < 6; ks++) {
+                            const uint32_t baddr = b0 + bp * kTcPlane + 16 * (ks >> 1) + kTcP * ((2 * ks) & 3);
+                            const uint64_t bd = ((uint64_t)b_hi32 << 32) | (uint64_t)(((baddr >> 4) & 0x3fff) | lo_lbo);
+                            tc_mma_ts(d, tm + (uint32_t)(48 * ap + 8 * ks), bd, id, (t | ks) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(b_empty + st);
+                    tc_commit(acc_full + 2 * e + slot);
+                }
+                __syncwarp();
+            }
         }
     } else {
-        // ===== epilogue: TMEM lane = channel =====
-        const int c = blockIdx.y * 128 + tid;
+        // ===== epilogue set e (warps 4e .. 4e+3): TMEM lane = channel =====
+        const int e = warp >> 2;
+        const int ltid = tid & 127;
+        const int c = blockIdx.y * 128 + ltid;
         const bool valid = c < nch;
+        const uint32_t lane_base = tm + ((uint32_t)((warp & 3) * 32) << 16);
+        {
+            // set e puts A planes 2e, 2e+1 of its 128 rows into TMEM columns 96 e .. 96 e + 95
+            const float4* row = reinterpret_cast<const float4*>(coef_tab + (size_t)c * 192 + 96 * e);
+#pragma unroll
+            for (int blk = 0; blk < 6; blk++) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 f = __ldg(row + 4 * blk + i);
+                    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+                }
+                tmem_st16(lane_base + (uint32_t)(96 * e + 16 * blk), v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(a_ready);
+        }
+        int t0, n_seg, m_start, ntiles;
+        seg_geom(e, t0, n_seg, m_start, ntiles);
         NcoDev p = nco[valid ? c : 0];
         const unsigned long long ph0 = phase_cur[valid ? c : 0];
-        if (blockIdx.x == 0 && valid) phase_next[c] = ph0 + (unsigned long long)L * p.inc;
+        if (blockIdx.x == 0 && e == 0 && valid) phase_next[c] = ph0 + (unsigned long long)L * p.inc;
         const float2 w16 = make_float2(p.wtc, p.wts);
         CicSt st[NCR > 0 ? NCR : 1];
         float2 ev[NCR > 0 ? NCR : 1];
@@ -708,41 +849,53 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
             for (int k = 0; k < 3; k++) hs[i].o[k] = make_float2(0.f, 0.f);
         }
-        EmitCtx em;
-        em.od = od;
-        em.row_lo = valid ? (long long)(t0 / (16 << (NCR + NHB))) : 0x7fffffffffffffffLL;
-        em.row_hi = (long long)((t0 + n_seg) / (16 << (NCR + NHB)));
-        em.c = c;
+        constexpr int SH = NCR + NHB;                                   // fs/16 outputs per emitted row = 2^SH
+        const long long row_lo = (long long)(t0 / (16 << SH));
+        const long long q_first = (long long)(m_start >> SH);            // exact: 2^SH divides PRE and t0/16
+        TcEmit em;
+        em.mask = od.transposed ? (unsigned)(kDecRing - 1) : od.mask;
+        em.estride = od.transposed ? 1 : od.stride;
+        em.p0 = od.transposed ? od.p + (size_t)c * kDecRing : od.p + c;
+        em.pos = (unsigned)((od.base + q_first) & (long long)em.mask);
+        em.rel = (int)(q_first - row_lo);
+        em.n_rows = valid ? (int)((long long)((t0 + n_seg) / (16 << SH)) - row_lo) : 0;
         em.scale = scale;
         em.h0 = c_hb_taps[0]; em.h2 = c_hb_taps[1]; em.h4 = c_hb_taps[2];
-        const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16);
-        for (int it = 0; it < ntiles; it++) {
-            const int s = it & 1;
-            bar_wait(acc_full + s, (it >> 1) & 1);
+        // Oscillator at fs/16: output m is rotated by the phase of its newest input sample 16m+15, P + (16m+16) inc.
+        // It is re-seeded exactly (sincospi of the 64-bit phase) at ABSOLUTE multiples of 32 outputs and rotated in
+        // float32 in between; a segment that starts between two seed points replays the rotations since the last one,
+        // so every output bit is independent of how the block was cut into segments and tiles.
+        float2 S;
+        {
+            const int lead = ((m_start % 32) + 32) % 32;                 // 0 or 16
+            S = seed_osc(ph0 + (unsigned long long)(long long)(16 * (m_start - lead) + 16) * p.inc);
+            for (int i = 0; i < lead; i++) S = cmul(S, w16);
+        }
+        for (int k = 0; k < ntiles; k++) {
+            const int slot = k & 1;
+            const uint32_t acc = lane_base + (uint32_t)(kTcAccCol + 4 * kTcN * e + 2 * kTcN * slot);
+            bar_wait(acc_full + 2 * e + slot, (k >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tcol = lane_base + (uint32_t)(s * 256);
-            const int mt = m_start + 128 * it;
+            const int mt = m_start + kTcN * k;
 #pragma unroll 1
-            for (int r = 0; r < 8; r++) {
+            for (int h = 0; h < kTcN / 16; h++) {
                 float re[16], im[16];
-#pragma unroll
-                for (int g = 0; g < 16; g++) {
-                    re[g] = tmem_ld1(tcol + (uint32_t)(8 * g + r));
-                    im[g] = tmem_ld1(tcol + (uint32_t)(128 + 8 * g + r));
-                }
+                tmem_ld16(acc + (uint32_t)(16 * h), re);
+                tmem_ld16(acc + (uint32_t)(kTcN + 16 * h), im);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int m0 = mt + 16 * r;                                   // multiple of 16
-                // output m is rotated by the oscillator value of its newest input sample 16m+15: phase P + (16m+16) inc
-                float2 S = seed_osc(ph0 + (unsigned long long)(long long)(16 * m0 + 16) * p.inc);
-                TcStrip<NCR, NHB, 0, 16>::run(re, im, S, w16, st, ev, hs, (long long)(m0 >> NCR), em);
+                if (h == kTcN / 16 - 1) {
+                    // the tile is in registers: hand the accumulator slot back before doing the arithmetic
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    bar_arrive(acc_empty + 2 * e + slot);
+                }
+                if (((mt + 16 * h) & 31) == 0) S = seed_osc(ph0 + (unsigned long long)(long long)(16 * (mt + 16 * h) + 16) * p.inc);
+                TcStrip<NCR, NHB, 0, 16>::run(re, im, S, w16, st, ev, hs, em);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            bar_arrive(acc_empty + s);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
 }
 
 typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const float*, const NcoDev*, const unsigned long long*,
@@ -1092,30 +1245,22 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     }
     if (tc_) {
         tc_groups_ = (stride_ + 127) / 128;
-        CSDR_CK(cudaMalloc(&d_tc_coef_, (size_t)tc_groups_ * 4 * kTcAPlane));
+        CSDR_CK(cudaMalloc(&d_tc_coef_, (size_t)tc_groups_ * 128 * 192 * sizeof(float)));
         K1TFn tf = k1t_kernel(ncic_ - 4, nhbf_);
         CSDR_CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-        // one persistent CTA per SM: time segments x channel groups ~ the SM count; every segment pays
-        // PRE priming outputs and rounds up to whole 128-output MMA tiles
+        // one persistent CTA per SM, kTcSegs interleaved time segments per CTA; every segment pays PRE priming
+        // outputs and rounds up to whole MMA tiles
         const int pre = tc_pre(ncic_ - 4, nhbf_);
-        double best = 1e300;
-        int best_seg = block_len;
-        for (int segs = 1; segs <= std::max(1, 2 * sms / tc_groups_); segs++) {
-            int sl = (block_len + segs - 1) / segs;
-            sl = (sl + 255) / 256 * 256;
-            const int real = (block_len + sl - 1) / sl;
-            const long long grid = (long long)real * tc_groups_;
-            const long long waves = (grid + sms - 1) / sms;
-            const int tiles = (sl / 16 + pre + 127) / 128;
-            const double cost = (double)waves * (tiles + 0.6);          // + fixed per-CTA setup (A image, TMEM alloc)
-            if (cost < best * 0.999) { best = cost; best_seg = sl; }
+        {
+            const int ctas_x = std::max(1, sms / tc_groups_);
+            int sl = (block_len + kTcSegs * ctas_x - 1) / (kTcSegs * ctas_x);
+            tc_seg_len_ = std::max(256, (sl + 255) / 256 * 256);
         }
-        tc_seg_len_ = best_seg;
         if (const char* e = getenv("CUTESDR_TC_SEG")) tc_seg_len_ = std::max(256, atoi(e) / 256 * 256);           // tuning aid
         tc_dirty_ = true;
         if (getenv("CUTESDR_DEBUG_TIMING"))
             fprintf(stderr, "[cutesdr] kernel-1T <%d,%d>: segment %d (+%d priming), grid %d x %d\n", ncic_ - 4, nhbf_, tc_seg_len_,
-                    16 * pre, (block_len + tc_seg_len_ - 1) / tc_seg_len_, tc_groups_);
+                    16 * pre, ((block_len + tc_seg_len_ - 1) / tc_seg_len_ + kTcSegs - 1) / kTcSegs, tc_groups_);
     }
     dirty_ = true;
     return CUTESDR_OK;
@@ -1204,7 +1349,7 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
             tc_dirty_ = false;
         }
         const int sl = std::min(tc_seg_len_, L);
-        dim3 grid((L + sl - 1) / sl, tc_groups_);
+        dim3 grid(((L + sl - 1) / sl + kTcSegs - 1) / kTcSegs, tc_groups_);
         k1t_kernel(ncic_ - 4, nhbf_)<<<grid, kTcThreads, kTcSmem, st_>>>(d_x, fmt, halo_cur, halo_next, L, sl, d_tc_coef_, d_nco_, pc, pn,
                                                                           stride_, od, scale);
     } else if (L % Q == 0) {

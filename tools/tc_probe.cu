@@ -126,6 +126,105 @@ __global__ void __launch_bounds__(128, 1) k_probe(const float* __restrict__ A, c
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(128));
 }
 
+
+// ---- probe 2: A in TMEM (tcgen05.st), B in natural time order (chunk (m,q) at 16 m + P q), N = 32, x16 loads ----
+constexpr int N2 = 32, ROWS2 = N2 + 2, P2 = ROWS2 * 16;
+__global__ void __launch_bounds__(128, 1) k_probe2(const float* __restrict__ A, const float* __restrict__ X, float* __restrict__ D, int neg)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* b_hi = smem;                 // 4 q-subplanes of P2 bytes
+    unsigned char* b_lo = smem + 4 * P2;
+    __shared__ uint32_t tmem_base;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 16 * ROWS2; i += 128) {
+        const float v = X[i];
+        const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
+        const int u = i >> 2, e = i & 3, m = u >> 2, q = u & 3;
+        const int off = 16 * m + P2 * q + 4 * e;
+        *reinterpret_cast<float*>(b_hi + off) = hi;
+        *reinterpret_cast<float*>(b_lo + off) = lo;
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = tmem_base;
+    // A row (= this thread's TMEM lane) -> columns 0..47 (hi) and 48..95 (lo); accumulator at columns 128..159
+    {
+        const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16);
+        for (int part = 0; part < 2; part++)
+            for (int blk = 0; blk < 3; blk++) {
+                uint32_t r[16];
+                for (int j = 0; j < 16; j++) {
+                    const float v = A[tid * K + blk * 16 + j];
+                    const float hi = tf32_rn(v);
+                    r[j] = __float_as_uint(part ? tf32_rn(v - hi) : hi);
+                }
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+                                 lane_base + (uint32_t)(part * 48 + blk * 16)),
+                             "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                             "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                             : "memory");
+            }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        if (neg) idesc |= (1u << 13);
+        uint32_t acc = 0;
+        for (int term = 0; term < 3; term++) {
+            const uint32_t a_col = term == 0 ? 48 : 0;                       // lo*hi, hi*lo, hi*hi
+            const unsigned char* bp = term == 1 ? b_lo : b_hi;
+            for (int s = 0; s < K / 8; s++) {
+                const uint64_t bd = make_desc(smem_u32(bp) + 16 * (s >> 1) + P2 * ((2 * s) & 3), P2, 128);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm + 128),
+                    "r"(tm + a_col + 8 * s), "l"(bd), "r"(idesc), "r"(acc)
+                    : "memory");
+                acc = 1;
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(smem_u32(&bar)), "r"(0)
+                : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16) + 128;
+    for (int half = 0; half < 2; half++) {
+        uint32_t r[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                       "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(lane_base + 16 * half));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 16; j++) D[(size_t)tid * N2 + 16 * half + j] = __uint_as_float(r[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256));
+}
+
 int main()
 {
     std::vector<float> A(M * K), Xs(8 * 288), D(M * N);
@@ -163,6 +262,33 @@ int main()
         printf("mode %d: SNR %.1f dB, worst abs err %.3g (rms ref %.3g)\n", mode, snr, worst, sqrt(ref2 / (M * N)));
         const double need = mode == 0 ? 55.0 : 110.0;
         if (!(snr > need)) bad++;
+    }
+    {
+        std::vector<float> X(16 * ROWS2), D2(M * N2);
+        for (auto& v : X) v = ((float)rand() / RAND_MAX * 2.f - 1.f) * 1000.f;
+        float *dX2, *dD2;
+        CK(cudaMalloc(&dX2, X.size() * 4));
+        CK(cudaMalloc(&dD2, D2.size() * 4));
+        CK(cudaMemcpy(dX2, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+        for (int neg = 0; neg < 2; neg++) {
+            k_probe2<<<1, 128, 8 * P2>>>(dA, dX2, dD2, neg);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(D2.data(), dD2, D2.size() * 4, cudaMemcpyDeviceToHost));
+            double err2 = 0, ref2 = 0;
+            for (int m = 0; m < M; m++)
+                for (int n = 0; n < N2; n++) {
+                    double acc = 0;
+                    for (int k = 0; k < K; k++) acc += (double)A[m * K + k] * (double)X[16 * n + k];
+                    if (neg) acc = -acc;
+                    const double e = (double)D2[m * N2 + n] - acc;
+                    err2 += e * e;
+                    ref2 += acc * acc;
+                }
+            const double snr = 10 * log10(ref2 / (err2 + 1e-300));
+            printf("probe2 (A in TMEM, natural-order B, N=32, x16 ld) neg=%d: SNR %.1f dB\n", neg, snr);
+            if (!(snr > 110.0)) bad++;
+        }
     }
     printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
     return bad;
