@@ -186,7 +186,11 @@ struct TcEmit {
     __device__ __forceinline__ void emit(long long, float2 v)
     {
         float2* dst = p0 + (size_t)pos * (size_t)estride;
-        if ((unsigned)rel < (unsigned)n_rows) *dst = make_float2(v.x * scale, v.y * scale);
+        const unsigned ok = (unsigned)rel < (unsigned)n_rows;
+        // predicated store, no branch: priming outputs and the overshoot of the last tile are dropped
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v2.f32 [%1], {%2, %3};\n\t}\n" ::"r"(ok), "l"(dst),
+                     "f"(v.x * scale), "f"(v.y * scale)
+                     : "memory");
         rel++;
         pos = (pos + 1) & mask;
     }
@@ -523,15 +527,17 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar)
 }
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity)
 {
-    uint32_t done = 0;
-    const uint32_t a = smem_u32(bar);
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-    }
+    // try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase flips instead of
+    // re-issuing the poll (polls share the MIO queue the tcgen05 instructions go through)
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n"
+        "D_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680)
+        : "memory");
 }
 __device__ __forceinline__ void bar_arrive(uint64_t* bar)
 {
@@ -545,6 +551,14 @@ __device__ __forceinline__ bool elect_one()
         "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
         : "=r"(pred));
     return pred != 0;
+}
+// Compiler-level ordering for values produced by tcgen05.ld: arithmetic on them must stay behind the
+// tcgen05.wait::ld that completes the load. Volatile asm statements keep their order, and routing the registers
+// through an (empty) one after the wait makes every later use depend on it.
+__device__ __forceinline__ void tmem_pin16(float* v)
+{
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                      "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])::"memory");
 }
 // 16 consecutive TMEM columns of this thread's lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
@@ -638,7 +652,7 @@ template <int NCR, int NHB>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_mix_tc(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, float2* __restrict__ halo_next, int L, int seg_len,
              const float* __restrict__ coef_tab, const NcoDev* __restrict__ nco, const unsigned long long* __restrict__ phase_cur,
-             unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
+             unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale, int dbg)
 {
     typedef TcCfg<NCR, NHB> Cfg;
     extern __shared__ __align__(128) unsigned char tc_smem[];
@@ -699,7 +713,60 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         constexpr int kChunks = 4 * kTcRows;                              // 16-byte chunks (4 samples) per plane and tile
         constexpr int kHalf = (kChunks + 1) / 2;
         constexpr int kRounds = (kHalf + 31) / 32;
-        int cnt = 0;
+        const int c_lo = (pw & 1) * kHalf, c_hi = min(kChunks, c_lo + kHalf);
+        // The global loads of a tile are issued one tile ahead of its conversion (DRAM latency is ~1 us, more than a
+        // tile time): two register sets alternate.
+        struct Pending { int st, my; };
+        auto issue_loads = [&](int mt, float4* va, float4* vb) {
+            const int i_lo = 16 * (mt - 2);
+            const bool fast = fmt == 0 && i_lo >= 0 && i_lo + 16 * kTcRows <= L;
+#pragma unroll
+            for (int j = 0; j < kRounds; j++) {
+                const int idx = c_lo + lane + 32 * j;                     // chunk (row idx / 4, q = idx % 4)
+                const int i0 = i_lo + 4 * idx;                            // first of 4 consecutive samples; i0 % 4 == 0
+                va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[j] = va[j];
+                if (idx < c_hi) {
+                    if (fast) {
+                        const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(x) + i0);
+                        va[j] = __ldg(q);
+                        vb[j] = __ldg(q + 1);
+                    } else {
+                        const TcChunk ch = tc_load_chunk_slow(x, fmt, halo_cur, i0, L);
+                        va[j] = ch.a;
+                        vb[j] = ch.b;
+                    }
+                }
+            }
+        };
+        auto flush = [&](const Pending& pd, const float4* va, const float4* vb) {
+            // convert a tile's samples (in registers) and hand the stage to the MMA warps
+            unsigned char* pl = sB + pd.st * kTcStage;
+            bar_wait(b_empty + pd.st, ((pd.my / kTcStages) & 1) ^ 1);
+#pragma unroll
+            for (int j = 0; j < kRounds; j++) {
+                const int idx = c_lo + lane + 32 * j;
+                if (idx < c_hi) {
+                    const float4 a = va[j], b = vb[j];
+                    const float4 rh = make_float4(tf32_rn(a.x), tf32_rn(a.z), tf32_rn(b.x), tf32_rn(b.z));
+                    const float4 ih = make_float4(tf32_rn(a.y), tf32_rn(a.w), tf32_rn(b.y), tf32_rn(b.w));
+                    const float4 rl = make_float4(tf32_rn(a.x - rh.x), tf32_rn(a.z - rh.y), tf32_rn(b.x - rh.z), tf32_rn(b.z - rh.w));
+                    const float4 il = make_float4(tf32_rn(a.y - ih.x), tf32_rn(a.w - ih.y), tf32_rn(b.y - ih.z), tf32_rn(b.w - ih.w));
+                    const int off = 16 * (idx >> 2) + kTcP * (idx & 3);
+                    *reinterpret_cast<float4*>(pl + off) = rh;
+                    *reinterpret_cast<float4*>(pl + kTcPlane + off) = rl;
+                    *reinterpret_cast<float4*>(pl + 2 * kTcPlane + off) = ih;
+                    *reinterpret_cast<float4*>(pl + 3 * kTcPlane + off) = il;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(b_full + pd.st);
+        };
+        // this warp pair's tiles are those of segment (pw >> 1): tile k of the segment is global tile number 2 k + e
+        // while both segments are alive, so the (stage, use count) sequence is recomputed the same way every role does
+        float4 va0[kRounds], vb0[kRounds], va1[kRounds], vb1[kRounds];
+        Pending p0 = {-1, 0}, p1 = {-1, 0};
+        int cnt = 0, mine = 0;
         for (int k = 0; k < max_tiles; k++) {
 #pragma unroll 1
             for (int e = 0; e < kTcSegs; e++) {
@@ -708,55 +775,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (k >= tiles) continue;
                 const int my = cnt++;
                 if ((my & 1) != (pw >> 1)) continue;
-                const int st = my % kTcStages;
-                unsigned char* pl = sB + st * kTcStage;
-                const int mt = m0 + kTcN * k;
-                float4 va[kRounds], vb[kRounds];                          // chunk: (re0, im0, re1, im1), (re2, im2, re3, im3)
-                const int i_lo = 16 * (mt - 2);
-                const bool fast = fmt == 0 && i_lo >= 0 && i_lo + 16 * kTcRows <= L;
-                const int c_lo = (pw & 1) * kHalf, c_hi = min(kChunks, c_lo + kHalf);
-#pragma unroll
-                for (int j = 0; j < kRounds; j++) {
-                    const int idx = c_lo + lane + 32 * j;                 // chunk (row idx / 4, q = idx % 4)
-                    const int i0 = i_lo + 4 * idx;                        // first of 4 consecutive samples; i0 % 4 == 0
-                    va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    vb[j] = va[j];
-                    if (idx < c_hi) {
-                        if (fast) {
-                            const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(x) + i0);
-                            va[j] = __ldg(q);
-                            vb[j] = __ldg(q + 1);
-                        } else {
-                            const TcChunk ch = tc_load_chunk_slow(x, fmt, halo_cur, i0, L);
-                            va[j] = ch.a;
-                            vb[j] = ch.b;
-                        }
-                    }
+                const Pending now = {my % kTcStages, my};
+                if (dbg & 4) { bar_wait(b_empty + now.st, ((my / kTcStages) & 1) ^ 1); bar_arrive(b_full + now.st); continue; }
+                if ((mine++ & 1) == 0) {
+                    issue_loads(m0 + kTcN * k, va0, vb0);
+                    p0 = now;
+                    if (p1.st >= 0) { flush(p1, va1, vb1); p1.st = -1; }
+                } else {
+                    issue_loads(m0 + kTcN * k, va1, vb1);
+                    p1 = now;
+                    if (p0.st >= 0) { flush(p0, va0, vb0); p0.st = -1; }
                 }
-                bar_wait(b_empty + st, ((my / kTcStages) & 1) ^ 1);       // loads are in flight while the MMAs drain this stage
-#pragma unroll
-                for (int j = 0; j < kRounds; j++) {
-                    const int idx = c_lo + lane + 32 * j;
-                    if (idx < c_hi) {
-                        const float4 a = va[j], b = vb[j];
-                        const float4 rh = make_float4(tf32_rn(a.x), tf32_rn(a.z), tf32_rn(b.x), tf32_rn(b.z));
-                        const float4 ih = make_float4(tf32_rn(a.y), tf32_rn(a.w), tf32_rn(b.y), tf32_rn(b.w));
-                        const float4 rl = make_float4(tf32_rn(a.x - rh.x), tf32_rn(a.z - rh.y), tf32_rn(b.x - rh.z), tf32_rn(b.z - rh.w));
-                        const float4 il = make_float4(tf32_rn(a.y - ih.x), tf32_rn(a.w - ih.y), tf32_rn(b.y - ih.z), tf32_rn(b.w - ih.w));
-                        const int off = 16 * (idx >> 2) + kTcP * (idx & 3);
-                        *reinterpret_cast<float4*>(pl + off) = rh;
-                        *reinterpret_cast<float4*>(pl + kTcPlane + off) = rl;
-                        *reinterpret_cast<float4*>(pl + 2 * kTcPlane + off) = ih;
-                        *reinterpret_cast<float4*>(pl + 3 * kTcPlane + off) = il;
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                bar_arrive(b_full + st);
             }
         }
+        // drain in issue order
+        if ((mine & 1) == 0) { if (p0.st >= 0) flush(p0, va0, vb0); if (p1.st >= 0) flush(p1, va1, vb1); }
+        else { if (p1.st >= 0) flush(p1, va1, vb1); if (p0.st >= 0) flush(p0, va0, vb0); }
     } else if (warp >= kMmaWarp) {
-        // ===== MMA issuers: one warp per (segment, re | im accumulator). A single warp sustains one tcgen05.mma per
-        // ~100 clocks whatever its shape, so the four accumulators get four issuing warps. =====
+        // ===== MMA issuers: one warp per (segment, re | im accumulator); every accumulator has exactly one writer =====
         const int me = (warp - kMmaWarp) >> 1, half = (warp - kMmaWarp) & 1;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t idesc_na = idesc | (1u << 13);       // negate A
@@ -771,10 +807,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int e = 0; e < kTcSegs; e++) {
                 if (k >= seg_tiles(e)) continue;
                 const int my = cnt++;
+                const int slot = k & 1;
                 if (e != me) continue;
                 const int st = my % kTcStages;
                 bar_wait(b_full + st, (my / kTcStages) & 1);
-                const int slot = k & 1;
                 bar_wait(acc_empty + 2 * e + slot, ((k >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
@@ -785,6 +821,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     constexpr int a_pl[6] = {1, 0, 3, 2, 0, 2};
                     constexpr int b_re[6] = {0, 1, 2, 3, 0, 2}, n_re[6] = {0, 0, 1, 1, 0, 1};
                     constexpr int b_im[6] = {2, 3, 0, 1, 2, 0};
+                    if (!(dbg & 2))
 #pragma unroll
                     for (int t = 0; t < 6; t++) {
                         const int ap = a_pl[t];
@@ -871,26 +908,51 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             S = seed_osc(ph0 + (unsigned long long)(long long)(16 * (m_start - lead) + 16) * p.inc);
             for (int i = 0; i < lead; i++) S = cmul(S, w16);
         }
+        // Software pipeline over 16-output groups (two per tile): the tcgen05.ld of group g+1 -- and the wait for its
+        // tile's MMAs -- is in flight while group g runs through the oscillator / CIC / half-band arithmetic. The
+        // accumulator slot goes back to the MMA warps as soon as the tile's second group is in registers.
+        static_assert(kTcN == 32, "the epilogue pipeline below assumes two 16-output groups per tile");
+        float reA[16], imA[16], reB[16], imB[16];
+        auto acc_of = [&](int k) { return lane_base + (uint32_t)(kTcAccCol + 4 * kTcN * e + 2 * kTcN * (k & 1)); };
+        auto group_math = [&](const float* re, const float* im, int m_first) {
+            if ((m_first & 31) == 0) S = seed_osc(ph0 + (unsigned long long)(long long)(16 * m_first + 16) * p.inc);
+            if (dbg & 1) {
+                float a2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; i++) a2 += re[i] * im[i];
+                if (a2 == 1.2345f) em.rel++;
+                return;
+            }
+            TcStrip<NCR, NHB, 0, 16>::run(re, im, S, w16, st, ev, hs, em);
+        };
+        if (ntiles > 0) {
+            bar_wait(acc_full + 2 * e, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tmem_ld16(acc_of(0), reA);
+            tmem_ld16(acc_of(0) + kTcN, imA);
+        }
         for (int k = 0; k < ntiles; k++) {
             const int slot = k & 1;
-            const uint32_t acc = lane_base + (uint32_t)(kTcAccCol + 4 * kTcN * e + 2 * kTcN * slot);
-            bar_wait(acc_full + 2 * e + slot, (k >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int mt = m_start + kTcN * k;
-#pragma unroll 1
-            for (int h = 0; h < kTcN / 16; h++) {
-                float re[16], im[16];
-                tmem_ld16(acc + (uint32_t)(16 * h), re);
-                tmem_ld16(acc + (uint32_t)(kTcN + 16 * h), im);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (h == kTcN / 16 - 1) {
-                    // the tile is in registers: hand the accumulator slot back before doing the arithmetic
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    bar_arrive(acc_empty + 2 * e + slot);
-                }
-                if (((mt + 16 * h) & 31) == 0) S = seed_osc(ph0 + (unsigned long long)(long long)(16 * (mt + 16 * h) + 16) * p.inc);
-                TcStrip<NCR, NHB, 0, 16>::run(re, im, S, w16, st, ev, hs, em);
+            // group 0 of tile k is in flight (A registers): complete it, start group 1 (B registers)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_pin16(reA);
+            tmem_pin16(imA);
+            tmem_ld16(acc_of(k) + 16, reB);
+            tmem_ld16(acc_of(k) + kTcN + 16, imB);
+            group_math(reA, imA, mt);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_pin16(reB);
+            tmem_pin16(imB);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(acc_empty + 2 * e + slot);
+            if (k + 1 < ntiles) {
+                bar_wait(acc_full + 2 * e + ((k + 1) & 1), ((k + 1) >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tmem_ld16(acc_of(k + 1), reA);
+                tmem_ld16(acc_of(k + 1) + kTcN, imA);
             }
+            group_math(reB, imB, mt + 16);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -899,7 +961,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }
 
 typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const float*, const NcoDev*, const unsigned long long*,
-                      unsigned long long*, int, OutDesc, float);
+                      unsigned long long*, int, OutDesc, float, int);
 static K1TFn k1t_kernel(int ncr, int nhb)
 {
     static const K1TFn table[3][3] = {{k_mix_tc<0, 0>, k_mix_tc<0, 1>, k_mix_tc<0, 2>},
@@ -1351,7 +1413,7 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
         const int sl = std::min(tc_seg_len_, L);
         dim3 grid(((L + sl - 1) / sl + kTcSegs - 1) / kTcSegs, tc_groups_);
         k1t_kernel(ncic_ - 4, nhbf_)<<<grid, kTcThreads, kTcSmem, st_>>>(d_x, fmt, halo_cur, halo_next, L, sl, d_tc_coef_, d_nco_, pc, pn,
-                                                                          stride_, od, scale);
+                                                                          stride_, od, scale, getenv("CUTESDR_TC_DBG") ? atoi(getenv("CUTESDR_TC_DBG")) : 0);
     } else if (L % Q == 0) {
         const int threads = std::min(256, round_up(stride_, 32));
         dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);
