@@ -13,8 +13,9 @@ GPU (weak scaling: every GPU sees the same wideband stream and owns its own 1024
             blocks than fit in L2).
   e2e     : the same through cutesdr_bank_process with HOST buffers: H2D of the block (rank 0, then an
             NCCL broadcast when N > 1) and D2H of every channel's audio inside the timed region.
-  roofline: kernel 1 (k_mix_cic), algorithmic bytes = 8 B x samples x channels per launch (SURVEY 8d
-            per-channel streaming model) / its CUDA-event time, vs the measured HBM peak.
+  roofline: kernel 1. On the tensor-core path (k_mix_tc) bound = "tensor": the GEMM's algorithmic flops per launch /
+            its CUDA-event time vs the measured tf32 peak (bf16 sustained / 2); the SURVEY 8(d) HBM streaming-model
+            figure (8 B x samples x channels) rides along as roofline.hbm_model. CUDA-core path: bound = "hbm" (model).
   cpu_baseline / --impl reference : the UNMODIFIED reference dsp/*.cpp (oracle/_ref) on all host cores,
             one CDemodulator (+CFractResampler) per channel, on a bounded sample of the same workload.
 """
@@ -122,6 +123,19 @@ def measured_hbm_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tf32_peak():
+    """Dense tf32 tensor peak in TFLOP/s: half the bf16 figure (tcgen05 kind::tf32 runs at half the kind::f16 rate,
+    B200_PROFILING.md). Kernel 1T is timed inside a long step, so the SUSTAINED bf16 number is the one halved."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / 2.0, "measured bf16 sustained / 2 (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 2250.0 / 2.0, "fallback: nominal 2.25 PFLOP/s bf16 / 2 (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -326,10 +340,27 @@ def run_ours(args):
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[args.workload]["dram_bytes_per_launch"]
             except Exception:
                 pass
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "kernel": "k_mix_cic", "launch_ms": k1_ms / k1_n, "launches": k1_n, "peak_source": peak_src,
-                    "note": "per-channel streaming model (8 B per sample*channel); real DRAM traffic is far lower "
-                            "because every channel re-uses the staged tile -- the kernel is FP32-issue bound"}
+            hbm_model = {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                         "note": "SURVEY 8(d) per-channel streaming model (8 B per sample*channel); NOT a DRAM figure -- every "
+                                 "channel re-uses the staged samples, see traffic for the measured DRAM bytes"}
+            on_tc, flops_block = bank.kernel_model(0)
+            if on_tc and flops_block > 0:
+                tpeak, tsrc = measured_tf32_peak()
+                flops_launch = flops_block / groups
+                ach_t = flops_launch / per_launch_s / 1e12
+                roof = {"bound": "tensor", "achieved": ach_t, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_t / tpeak, "traffic": traffic,
+                        "kernel": "k_mix_tc", "launch_ms": k1_ms / k1_n, "launches": k1_n, "peak_source": tsrc,
+                        "flops_per_launch": flops_launch,
+                        "executed": {"tflops": 3.0 * ach_t, "frac": 3.0 * ach_t / tpeak,
+                                     "note": "every fp32 product is three tf32 MMAs (hi*hi + hi*lo + lo*hi): the tensor pipe "
+                                             "executes 3x the algorithmic flops"},
+                        "hbm_model": hbm_model,
+                        "note": "kernel 1T: NCO mix + 4 CIC3 stages as a complex GEMM [128 ch x 48 taps] x [48 x time] per channel "
+                                "group; algorithmic flops = 2 x (4 x 48 real MACs) per channel and fs/16 output"}
+            else:
+                roof = dict(hbm_model)
+                roof.update({"bound": "hbm", "traffic": traffic, "kernel": "k_mix_cic", "launch_ms": k1_ms / k1_n, "launches": k1_n,
+                             "note": hbm_model["note"] + "; the CUDA-core kernel is FP32-issue bound"})
         cpu = None
         try:
             r = cpu_reference_run(args.workload, steps=3, warmup=1)

@@ -712,6 +712,23 @@ int cutesdr_bank_kernel_time(cutesdr_bank* b, int which, double* ms_total, long 
     return CUTESDR_OK;
 }
 
+int cutesdr_bank_kernel_model(cutesdr_bank* b, int which, int* on_tensor_cores, double* flops_per_block)
+{
+    if (!b || which != 0) { set_error("kernel_model: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    int all = b->groups.empty() ? 0 : 1;
+    double fl = 0.0;
+    for (auto& g : b->groups) {
+        if (!g->dec.tensor_path()) all = 0;
+        fl += g->dec.tensor_flops_per_block();
+    }
+    if (on_tensor_cores) *on_tensor_cores = all;
+    if (flops_per_block) *flops_per_block = fl;
+    return CUTESDR_OK;
+}
+
 int cutesdr_bank_tap_enable(cutesdr_bank* b, int c, unsigned profile_mask)
 {
     if (!b || c < 0 || c >= b->nch) { set_error("tap_enable: bad arguments"); return CUTESDR_E_ARG; }

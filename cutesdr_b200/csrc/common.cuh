@@ -36,7 +36,7 @@ void set_error(const char* fmt, ...);
 constexpr double kTwoPi = 2.0 * 3.14159265358979323846;   // K_2PI, dsp/datatypes.h:42
 constexpr double kPi = 3.14159265358979323846;
 
-constexpr int kHaloMax = 1024;      // complex samples kept in front of every wideband block (kernel-1 halo)
+constexpr int kHaloMax = 2048;      // complex samples kept in front of every wideband block (kernel-1 halo)
 constexpr int kFirFft = 2048;       // CONV_FFT_SIZE, dsp/fastfir.cpp:55
 constexpr int kFirTaps = 1025;      // CONV_FIR_SIZE, dsp/fastfir.cpp:56
 constexpr int kBurst = 1024;        // samples CFastFIR emits per FFT

@@ -108,6 +108,7 @@ __device__ __forceinline__ float2 seed_osc(unsigned long long ph)
 }
 
 constexpr int kFuseHb = 1;      // a second fused stage costs kernel 1 more (registers, halo) than it saves in kernel 2
+constexpr int kFuseHbTc = 2;    // kernel 1T: every fused stage halves its HBM output and takes a pass off kernel 2
 
 static int k1_body(int ncic) { int g = 1 << ncic; return g < 32 ? 32 : g; }
 static int k1_halo(int ncic, int nhb)
@@ -964,9 +965,9 @@ typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const 
                       unsigned long long*, int, OutDesc, float, int);
 static K1TFn k1t_kernel(int ncr, int nhb)
 {
-    static const K1TFn table[3][3] = {{k_mix_tc<0, 0>, k_mix_tc<0, 1>, k_mix_tc<0, 2>},
-                                      {k_mix_tc<1, 0>, k_mix_tc<1, 1>, k_mix_tc<1, 2>},
-                                      {k_mix_tc<2, 0>, k_mix_tc<2, 1>, k_mix_tc<2, 2>}};
+    static const K1TFn table[3][4] = {{k_mix_tc<0, 0>, k_mix_tc<0, 1>, k_mix_tc<0, 2>, k_mix_tc<0, 3>},
+                                      {k_mix_tc<1, 0>, k_mix_tc<1, 1>, k_mix_tc<1, 2>, k_mix_tc<1, 3>},
+                                      {k_mix_tc<2, 0>, k_mix_tc<2, 1>, k_mix_tc<2, 2>, k_mix_tc<2, 3>}};
     return table[ncr][nhb];
 }
 
@@ -1214,11 +1215,19 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     }
     ncic_ = 0;
     while (ncic_ < (int)lens_.size() && lens_[ncic_] == 3 && ncic_ < 6) ncic_++;
-    // up to kFuseHb 11-tap half-bands that follow the CICs run inside kernel 1 as well
+    // kernel 1T (tensor cores): the ladder starts with >= 4 CIC3 stages and every legal block length is a whole
+    // number of 256-sample units (>= 8 stages), so the CUDA-core kernel never has to stand in for it
+    tc_ = ncic_ >= 4 && ncic_ <= 6 && lens_.size() >= 8 && block_len % 256 == 0 && block_len >= 4096 && !getenv("CUTESDR_NO_TC");
+    // up to kFuseHb 11-tap half-bands that follow the CICs run inside kernel 1 as well. Kernel 1T's epilogue has
+    // the issue slots for more of them (kFuseHbTc), as long as the segment priming stays small.
     nhbf_ = 0;
-    int fuse_max = kFuseHb;
-    if (const char* e = getenv("CUTESDR_FUSE_HB")) fuse_max = std::max(0, std::min(2, atoi(e)));     // tuning aid
+    int fuse_max = tc_ ? kFuseHbTc : kFuseHb;
+    if (const char* e = getenv("CUTESDR_FUSE_HB")) fuse_max = std::max(0, std::min(tc_ ? 3 : 2, atoi(e)));     // tuning aid
     while (nhbf_ < fuse_max && ncic_ + nhbf_ < (int)lens_.size() && lens_[ncic_ + nhbf_] == 11) nhbf_++;
+    if (tc_) {
+        while (nhbf_ > 0 && (16 * tc_pre(ncic_ - 4, nhbf_) + 32 > kHaloMax || tc_pre(ncic_ - 4, nhbf_) > 96)) nhbf_--;
+        if (16 * tc_pre(ncic_ - 4, nhbf_) + 32 > kHaloMax) tc_ = false;
+    }
     n_out_ = block_len >> lens_.size();
     if (n_out_ > kDecRing - kFirFft) { set_error("decimated block of %d samples exceeds the FIR ring", n_out_); return CUTESDR_E_ARG; }
     CSDR_TRY(upload_taps());
@@ -1248,64 +1257,64 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     CSDR_CK(cudaEventCreateWithFlags(&ev_k1_, cudaEventDisableTiming));
     CSDR_CK(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
 
-    // Time tile. Every CTA costs ~(tile + halo) samples per lane, and the grid runs in waves of
-    // (SMs x resident CTAs): pick the tile count that minimises waves x (tile + halo), i.e. avoid a
-    // mostly-empty last wave and keep the halo small, within the shared memory that still allows the
-    // same residency.
-    const int B = k1_body(ncic_);
-    const int Q = std::max((1 << ncic_) << nhbf_, B);
-    const int H = k1_halo(ncic_, nhbf_);
-    if (H > kHaloMax) { set_error("kernel-1 halo %d exceeds kHaloMax", H); return CUTESDR_E_ARG; }
-    const int cta_threads = std::min(256, round_up(stride_, 32));
-    const int chan_blocks = (stride_ + cta_threads - 1) / cta_threads;
-    int dev = 0, sms = 148;
-    CSDR_CK(cudaGetDevice(&dev));
-    CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    K1Fn fn = k1_kernel(ncic_, nhbf_);
-    CSDR_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    double best_cost = 1e300;
-    int best_tl = Q;
-    std::map<int, int> occ_cache;       // smem KB -> resident CTAs per SM
-    const int max_tiles = std::max(1, block_len / std::max(Q, 4 * H));
-    for (int tiles = 1; tiles <= max_tiles; tiles++) {
-        int tl = (block_len + tiles - 1) / tiles;
-        tl = (tl + Q - 1) / Q * Q;
-        const size_t smem = (size_t)(tl + H) * sizeof(float2);
-        if (smem > 200 * 1024) continue;
-        const int real_tiles = (block_len + tl - 1) / tl;
-        const int key = (int)(smem >> 10);
-        int occ;
-        auto it = occ_cache.find(key);
-        if (it != occ_cache.end()) occ = it->second;
-        else {
-            CSDR_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cta_threads, smem));
-            occ_cache[key] = occ;
+    if (!tc_) {
+        // Time tile. Every CTA costs ~(tile + halo) samples per lane, and the grid runs in waves of
+        // (SMs x resident CTAs): pick the tile count that minimises waves x (tile + halo), i.e. avoid a
+        // mostly-empty last wave and keep the halo small, within the shared memory that still allows the
+        // same residency.
+        const int B = k1_body(ncic_);
+        const int Q = std::max((1 << ncic_) << nhbf_, B);
+        const int H = k1_halo(ncic_, nhbf_);
+        if (H > kHaloMax) { set_error("kernel-1 halo %d exceeds kHaloMax", H); return CUTESDR_E_ARG; }
+        const int cta_threads = std::min(256, round_up(stride_, 32));
+        const int chan_blocks = (stride_ + cta_threads - 1) / cta_threads;
+        int dev = 0, sms = 148;
+        CSDR_CK(cudaGetDevice(&dev));
+        CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        K1Fn fn = k1_kernel(ncic_, nhbf_);
+        CSDR_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        double best_cost = 1e300;
+        int best_tl = Q;
+        std::map<int, int> occ_cache;       // smem KB -> resident CTAs per SM
+        const int max_tiles = std::max(1, block_len / std::max(Q, 4 * H));
+        for (int tiles = 1; tiles <= max_tiles; tiles++) {
+            int tl = (block_len + tiles - 1) / tiles;
+            tl = (tl + Q - 1) / Q * Q;
+            const size_t smem = (size_t)(tl + H) * sizeof(float2);
+            if (smem > 200 * 1024) continue;
+            const int real_tiles = (block_len + tl - 1) / tl;
+            const int key = (int)(smem >> 10);
+            int occ;
+            auto it = occ_cache.find(key);
+            if (it != occ_cache.end()) occ = it->second;
+            else {
+                CSDR_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cta_threads, smem));
+                occ_cache[key] = occ;
+            }
+            if (occ < 1) continue;
+            const long long grid = (long long)real_tiles * chan_blocks;
+            const long long slots = (long long)sms * occ;
+            const long long waves = (grid + slots - 1) / slots;
+            // fewer resident warps hide latency worse: charge a residency penalty below 16 warps/SM
+            const double warps = (double)std::min<long long>(grid, slots) / sms * (cta_threads / 32.0);
+            const double penalty = warps >= 16.0 ? 1.0 : (16.0 / std::max(warps, 1.0));
+            const double cost = (double)waves * (tl + H) * (warps >= 16.0 ? 1.0 : std::min(penalty, 4.0) * 0.5 + 0.5);
+            if (cost < best_cost * 0.999) { best_cost = cost; best_tl = tl; }
         }
-        if (occ < 1) continue;
-        const long long grid = (long long)real_tiles * chan_blocks;
-        const long long slots = (long long)sms * occ;
-        const long long waves = (grid + slots - 1) / slots;
-        // fewer resident warps hide latency worse: charge a residency penalty below 16 warps/SM
-        const double warps = (double)std::min<long long>(grid, slots) / sms * (cta_threads / 32.0);
-        const double penalty = warps >= 16.0 ? 1.0 : (16.0 / std::max(warps, 1.0));
-        const double cost = (double)waves * (tl + H) * (warps >= 16.0 ? 1.0 : std::min(penalty, 4.0) * 0.5 + 0.5);
-        if (cost < best_cost * 0.999) { best_cost = cost; best_tl = tl; }
-    }
-    tile_len_ = best_tl;
-    if (const char* e = getenv("CUTESDR_TILE")) tile_len_ = std::max(Q, atoi(e) / Q * Q);                    // tuning aid
-    if (getenv("CUTESDR_DEBUG_TIMING")) {
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cta_threads, (size_t)(tile_len_ + H) * sizeof(float2));
-        fprintf(stderr, "[cutesdr] kernel-1 <%d,%d>: tile %d + halo %d, grid %d x %d, %d CTAs/SM\n", ncic_, nhbf_, tile_len_, H,
-                (block_len + tile_len_ - 1) / tile_len_, chan_blocks, occ);
-    }
-    // kernel 1T: the ladder starts with >= 4 CIC3 stages and the block is a whole number of 256-sample units
-    tc_ = ncic_ >= 4 && ncic_ <= 6 && block_len % 256 == 0 && block_len >= 4096 && !getenv("CUTESDR_NO_TC");
-    if (tc_) {
-        const int ncr = ncic_ - 4;
-        if (16 * tc_pre(ncr, nhbf_) + 32 > kHaloMax) tc_ = false;
+        tile_len_ = best_tl;
+        if (const char* e = getenv("CUTESDR_TILE")) tile_len_ = std::max(Q, atoi(e) / Q * Q);                    // tuning aid
+        if (getenv("CUTESDR_DEBUG_TIMING")) {
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cta_threads, (size_t)(tile_len_ + H) * sizeof(float2));
+            fprintf(stderr, "[cutesdr] kernel-1 <%d,%d>: tile %d + halo %d, grid %d x %d, %d CTAs/SM\n", ncic_, nhbf_, tile_len_, H,
+                    (block_len + tile_len_ - 1) / tile_len_, chan_blocks, occ);
+        }
+        // kernel 1T: the ladder starts with >= 4 CIC3 stages and the block is a whole number of 256-sample units
     }
     if (tc_) {
+        int dev = 0, sms = 148;
+        CSDR_CK(cudaGetDevice(&dev));
+        CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         tc_groups_ = (stride_ + 127) / 128;
         CSDR_CK(cudaMalloc(&d_tc_coef_, (size_t)tc_groups_ * 128 * 192 * sizeof(float)));
         K1TFn tf = k1t_kernel(ncic_ - 4, nhbf_);

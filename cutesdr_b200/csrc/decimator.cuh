@@ -60,6 +60,10 @@ public:
     // CUDA-event timing of kernel 1 on the launching stream (bench.py's roofline line)
     void enable_timing(bool on) { timing_ = on; }
     int read_timing(double* ms_total, long long* launches);
+    // kernel 1T in use? and the real multiply-adds (MAC = 2 flop) of its GEMM per full block, counted ONCE per product
+    // (fp32-equivalent: the three tf32 partial products that emulate one fp32 product count as one)
+    bool tensor_path() const { return tc_; }
+    double tensor_flops_per_block() const { return tc_ ? 2.0 * (128.0 * tc_groups_) * (block_len_ / 16.0) * 192.0 : 0.0; }
 
     int nch() const { return nch_; }
     int stride() const { return stride_; }

@@ -119,6 +119,13 @@ class ReceiverBank:
     def kernel_timing(self, enable=True):
         check(self.L.cutesdr_bank_kernel_timing(self.h, int(bool(enable))))
 
+    def kernel_model(self, which=0):
+        """(kernel 1 runs on the tensor cores?, its GEMM flops per DSP block)."""
+        t = C.c_int()
+        f = C.c_double()
+        check(self.L.cutesdr_bank_kernel_model(self.h, int(which), C.byref(t), C.byref(f)))
+        return bool(t.value), f.value
+
     def kernel_time(self, which=0):
         ms, n = C.c_double(), C.c_longlong()
         check(self.L.cutesdr_bank_kernel_time(self.h, int(which), C.byref(ms), C.byref(n)))

@@ -148,6 +148,11 @@ int cutesdr_bank_launch_count(cutesdr_bank* b, long long* n);
  * kernel_time returns the accumulated milliseconds and launch count since the last read. */
 int cutesdr_bank_kernel_timing(cutesdr_bank* b, int enable);
 int cutesdr_bank_kernel_time(cutesdr_bank* b, int which, double* ms_total, long long* launches);
+/* What bounds kernel `which` (0): on_tensor_cores = 1 when every chain group runs kernel 1T (the NCO mix + first
+ * four CIC3 stages of dsp/downconvert.cpp:186-263,425-460 as a tcgen05 GEMM); flops_per_block = the GEMM's
+ * multiply-adds x 2 per DSP block, each real product counted once (the 3 tf32 partial products that emulate one
+ * fp32 product are one). bench.py's roofline line is built from this and cutesdr_bank_kernel_time. */
+int cutesdr_bank_kernel_model(cutesdr_bank* b, int which, int* on_tensor_cores, double* flops_per_block);
 
 /* Test-bench taps (the reference's PROFILE_1..4 display taps, gui/testbench.cpp:71-81,
  * dsp/demodulator.cpp:175,180,187,208): 1 = after CDownConvert (complex), 2 = after CFastFIR
