@@ -1040,6 +1040,70 @@ __global__ void __launch_bounds__(256) k_hb11_chain(const float2* __restrict__ i
 }
 
 // ------------------------------------------------------------------------------------------
+// K2b: the LAST stages of the ladder (any half-band lengths, up to 4) in one pass. Their data is small (a few
+// thousand rows per block) and as separate launches they are launch- and tail-latency bound; here a CTA owns CH
+// channels x T final outputs, stages c[0] = 2 c[1] + len[0] - 2 input rows in shared memory and runs the stages
+// out of it, exactly like K2a. Same operation order as k_halfband (centre tap, then the outermost pair inwards),
+// so either path gives the same bits.
+// ------------------------------------------------------------------------------------------
+struct TailCfg {
+    int ns;
+    int len[4];
+    int toff[4];
+    int c[5];          // rows: c[ns] = T, c[j] = 2 c[j+1] + len[j] - 2
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_hb_tail(const float2* __restrict__ in, unsigned in_mask, long long in_base, int stride, int n_out,
+                                                 TailCfg cfg, OutDesc od)
+{
+    constexpr int RPW = 32 / CH;
+    extern __shared__ float2 sm_rows[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / CH, l = lane % CH;
+    const int c = blockIdx.y * CH + l;
+    const int o0 = blockIdx.x * cfg.c[cfg.ns];
+    long long lo0 = o0;
+    for (int j = cfg.ns - 1; j >= 0; j--) lo0 = 2 * lo0 - (cfg.len[j] - 1);
+    float2* buf = sm_rows;
+    {
+        constexpr int LPR = CH / 2;                // lanes per row (16 bytes = 2 channels per lane)
+        constexpr int RPI = 32 / LPR;
+        const int rsub = lane / LPR, l2 = lane % LPR;
+        const int cbase = blockIdx.y * CH + 2 * l2;
+        for (int r = RPI * warp + rsub; r < cfg.c[0]; r += 8 * RPI) {
+            const float2* g = in + (size_t)((in_base + lo0 + r) & in_mask) * stride + cbase;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + r * CH + 2 * l2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    for (int j = 0; j < cfg.ns; j++) {
+        const int N = cfg.len[j], half = (N - 1) >> 1, n_j = cfg.c[j + 1];
+        const bool last = j + 1 == cfg.ns;
+        float2* nxt = buf + cfg.c[j] * CH;
+        for (int i = RPW * warp + sub; i < n_j; i += 8 * RPW) {
+            const float2* x = buf + (2 * i) * CH + l;          // oldest tap of output i
+            const float2 xc = x[half * CH];
+            float2 acc = make_float2(0.5f * xc.x, 0.5f * xc.y);
+            int t = cfg.toff[j];
+            for (int k = 0; k < half; k += 2, t++) {
+                const float h = c_hb_taps[t];
+                const float2 u = x[k * CH], v = x[(N - 1 - k) * CH];
+                acc.x = fmaf(h, u.x + v.x, acc.x);
+                acc.y = fmaf(h, u.y + v.y, acc.y);
+            }
+            if (!last) nxt[i * CH + l] = acc;
+            else if (o0 + i < n_out) store_out(od, o0 + i, c, acc);
+        }
+        if (!last) __syncthreads();
+        buf = nxt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K2: one decimate-by-2 stage, thread per (output row m, channel c)
 //   half-band : y[m] = sum_j h[j] x[2m-(N-1)+j]            (dsp/downconvert.cpp:286-320, 348-423)
 //   N == 3    : CIC3, y[m] = .125 (x[2m+1] + 3x[2m] + 3x[2m-1] + x[2m-2])          (:444-460)
@@ -1488,6 +1552,53 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
             CSDR_CK(cudaGetLastError());
             for (int s = 0; s < nchain; s++) stage_base_[s] += (L >> (k1_stages() + s));
             s_first = nchain;
+        }
+    }
+    {
+        // the remaining stages in one launch when there are 2..4 of them and the channel rows are whole 128-byte lines
+        const int ns = nhb - s_first;
+        bool ok = ns >= 2 && ns <= 4 && stride_ % 16 == 0 && !getenv("CUTESDR_NO_HBTAIL");
+        for (int s = s_first; ok && s < nhb; s++) ok = lens_[k1_stages() + s] != 3;
+        if (ok) {
+            constexpr int CH = 16;
+            TailCfg cfg;
+            cfg.ns = ns;
+            const int n_out = L >> lens_.size();
+            int T = 32;
+            while (T > 8 && (long long)((n_out + T - 1) / T) * (stride_ / CH) < 592) T >>= 1;       // keep >= ~4 CTAs per SM
+            cfg.c[ns] = T;
+            for (int j = ns - 1; j >= 0; j--) {
+                cfg.len[j] = lens_[k1_stages() + s_first + j];
+                cfg.toff[j] = tap_offset_for(cfg.len[j]);
+                cfg.c[j] = 2 * cfg.c[j + 1] + cfg.len[j] - 2;
+            }
+            size_t rows = 0;
+            for (int j = 0; j < ns; j++) rows += cfg.c[j];
+            const size_t smem = rows * CH * sizeof(float2);
+            // rows of history the first tile reaches back into the input ring (it persists between blocks)
+            long long hist = 0;
+            for (int j = ns - 1; j >= 0; j--) hist = 2 * hist + (cfg.len[j] - 1);
+            const int n_in0 = L >> (k1_stages() + s_first);
+            if (smem <= 160 * 1024 && hist + n_in0 <= stage_rows_[s_first]) {
+                static size_t attr_smem = 0;
+                if (smem > attr_smem) {
+                    CSDR_CK(cudaFuncSetAttribute(k_hb_tail<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    attr_smem = smem;
+                }
+                OutDesc o2;
+                o2.p = d_ring_;
+                o2.mask = 0;
+                o2.stride = stride_;
+                o2.transposed = 1;
+                o2.base = total_out_;
+                dim3 grid((n_out + T - 1) / T, stride_ / CH);
+                k_hb_tail<CH><<<grid, 256, smem, s2>>>(d_stage_[s_first], (unsigned)(stage_rows_[s_first] - 1), stage_base_[s_first], stride_,
+                                                       n_out, cfg, o2);
+                lc_->n++;
+                CSDR_CK(cudaGetLastError());
+                for (int s = s_first; s < nhb; s++) stage_base_[s] += (L >> (k1_stages() + s));
+                s_first = nhb;
+            }
         }
     }
     for (int s = s_first; s < nhb; s++) {
