@@ -1305,8 +1305,12 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     const int nhb = (int)lens_.size() - k1_stages();
     for (int s = 0; s < nhb; s++) {
         int n_rows = block_len >> (k1_stages() + s);       // rows this ring receives per block
+        // history a fused pass over stages s.. reaches back before the block (k_hb_tail recomputes the later stages'
+        // history from this ring instead of keeping their rings)
+        long long hist = 0;
+        for (int j = nhb - 1; j >= s; j--) hist = std::min<long long>(2 * hist + (lens_[k1_stages() + j] - 1), 8192);
         // ring 0 keeps two blocks so kernel 1 of block k+1 can fill it while kernel 2 still reads block k
-        int rows = next_pow2((long long)n_rows * (s == 0 ? 2 : 1) + 64);
+        int rows = next_pow2((long long)n_rows * (s == 0 ? 2 : 1) + 64 + (nhb - s <= 4 ? hist : 0));
         float2* p = nullptr;
         size_t bytes = (size_t)rows * stride_ * sizeof(float2);
         CSDR_CK(cudaMalloc(&p, bytes));
