@@ -61,7 +61,7 @@ __device__ __forceinline__ void average_bin(int k, float2 X, const AveParams& p,
 }
 
 // ---- N <= 4096: everything in one CTA
-__global__ void __launch_bounds__(512) k_dispfft_small(const float2* __restrict__ x, const float* __restrict__ win,
+__global__ void __launch_bounds__(512) k_dispfft_small(const float2* __restrict__ x, float2 dc, const float* __restrict__ win,
                                                        const float2* __restrict__ tw, AveParams p, double* sum,
                                                        double* pwr_ave, double* ave, int* overload)
 {
@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(512) k_dispfft_small(const float2* __restrict_
     float2* b = sm + p.N;
     int ov = 0;
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
-        const float2 v = x[i];
+        float2 v = x[i];
+        v.x -= dc.x;                           // I/Q DC-offset correction of the display copy, interface/sdrinterface.cpp:889-894
+        v.y -= dc.y;
         if (v.x > 32000.0f) ov = 1;            // OVER_LIMIT on I only, dsp/fft.cpp:275-276
         const float w = win[i];
         a[i] = make_float2(w * v.x, w * v.y);
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(512) k_dispfft_small(const float2* __restrict_
 }
 
 // ---- N > 4096, step A: column n2 -> FFT over n1 (length N1), times W_N^{n2 k1}; out[k1][n2]
-__global__ void __launch_bounds__(128) k_dispfft_cols(const float2* __restrict__ x, const float* __restrict__ win,
+__global__ void __launch_bounds__(128) k_dispfft_cols(const float2* __restrict__ x, float2 dc, const float* __restrict__ win,
                                                       const float2* __restrict__ tw, int N, int N1, int N2,
                                                       float2* __restrict__ mid, int* overload)
 {
@@ -93,7 +95,9 @@ __global__ void __launch_bounds__(128) k_dispfft_cols(const float2* __restrict__
     int ov = 0;
     for (int n1 = threadIdx.x; n1 < N1; n1 += blockDim.x) {
         const int n = n1 * N2 + n2;
-        const float2 v = x[n];
+        float2 v = x[n];
+        v.x -= dc.x;
+        v.y -= dc.y;
         if (v.x > 32000.0f) ov = 1;
         const float w = win[n];
         a[n1] = make_float2(w * v.x, w * v.y);
@@ -169,20 +173,36 @@ __global__ void __launch_bounds__(128) k_fft_plain_rows(const float2* __restrict
 }
 
 // ---- GetScreenIntegerFFTData, dsp/fft.cpp:365-407: one thread per pixel
+// out2 / max_height2 (optional): a second mapping of the same bins with another height, so the plotter's waterfall
+// row (255 levels) and its 2-D trace (gui/plotter.cpp:429-456) come out of one pass over the averaged spectrum.
 __global__ void k_screen(const double* __restrict__ ave, int N, int invert, int bin_min, int bin_max, int width,
-                         int max_height, double gain, double off, int32_t* __restrict__ out)
+                         int max_height, double gain, double off, int32_t* __restrict__ out, int max_height2,
+                         int32_t* __restrict__ out2)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= width) return;
     const int span = bin_max - bin_min;
-    auto ypix = [&](int i) {
+    auto ypix_h = [&](int i, int mh) {
         int idx = invert ? (N - i) : i;
         if (idx >= N) idx = N - 1;          // the reference reads one past the end here (i == 0)
-        int y = (int)((double)max_height * gain * (ave[idx] - off));
+        int y = (int)((double)mh * gain * (ave[idx] - off));
         if (y < 0) y = 0;
-        if (y > max_height) y = max_height;
+        if (y > mh) y = mh;
         return y;
     };
+    if (out2) {
+        if (span > width) {
+            const long long lo = ((long long)x * span + width - 1) / width;
+            long long hi = ((long long)(x + 1) * span + width - 1) / width - 1;
+            if (hi > span) hi = span;
+            int best = 0x7fffffff;
+            for (long long d = lo; d <= hi; d++) { const int y = ypix_h(bin_min + (int)d, max_height2); if (y < best) best = y; }
+            out2[x] = best == 0x7fffffff ? 0 : best;
+        } else {
+            out2[x] = ypix_h(bin_min + (x * span) / width, max_height2);
+        }
+    }
+    auto ypix = [&](int i) { return ypix_h(i, max_height); };
     if (span > width) {
         // bins i with ((i-bin_min)*width)/span == x are contiguous; the reference keeps the smallest
         // y (strongest signal) among them
@@ -210,6 +230,7 @@ struct cutesdr_fft {
     bool overload = false, invert = false;
     int ave_count = 0, total_count = 0, size = 1024, last_size = 0, ave_size = 1;
     double k_c = 0, k_b = 0, db_comp = 0, sample_freq = 1000;
+    float2 dc = {0.f, 0.f};      // m_NCOSpurOffsetI/Q applied to the display copy (interface/sdrinterface.cpp:889-894)
     // device
     float* d_win = nullptr;
     float2* d_tw = nullptr;
@@ -288,11 +309,11 @@ struct cutesdr_fft {
         if (size <= 4096) {
             size_t smem = 2 * (size_t)size * sizeof(float2);
             if (smem > 48 * 1024) CSDR_CK(cudaFuncSetAttribute(k_dispfft_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_dispfft_small<<<1, 512, smem, st>>>(d_in, d_win, d_tw, p, d_sum, d_pwr, d_ave, d_flag);
+            k_dispfft_small<<<1, 512, smem, st>>>(d_in, dc, d_win, d_tw, p, d_sum, d_pwr, d_ave, d_flag);
             lc.n++;
         } else {
             const int N1 = 256, N2 = size / 256;
-            k_dispfft_cols<<<N2, 128, 2 * N1 * sizeof(float2), st>>>(d_in, d_win, d_tw, size, N1, N2, d_mid, d_flag);
+            k_dispfft_cols<<<N2, 128, 2 * N1 * sizeof(float2), st>>>(d_in, dc, d_win, d_tw, size, N1, N2, d_mid, d_flag);
             k_dispfft_rows<<<N1, 128, 2 * N2 * sizeof(float2), st>>>(d_mid, d_tw, N1, N2, p, d_sum, d_pwr, d_ave);
             lc.n += 2;
         }
@@ -389,8 +410,8 @@ int cutesdr_fft_put_device(cutesdr_fft* h, int n, const void* d_in, int* total_c
     return h->put_device(reinterpret_cast<const float2*>(d_in), n, total_count);
 }
 
-int cutesdr_fft_get_screen(cutesdr_fft* h, int max_height, int max_width, double max_db, double min_db, int start_freq,
-                           int stop_freq, int32_t* out, int* overload)
+static int fft_screen(cutesdr_fft* h, int max_height, int max_width, double max_db, double min_db, int start_freq, int stop_freq,
+                      int32_t* out, int max_height2, int32_t* out2, int* overload)
 {
     if (!h || !out || max_width <= 0) { set_error("fft_get_screen: bad arguments"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(h->mu);
@@ -408,16 +429,38 @@ int cutesdr_fft_get_screen(cutesdr_fft* h, int max_height, int max_width, double
     if (max_width > h->screen_cap) {
         cudaFree(h->d_screen);
         h->d_screen = nullptr;
-        CSDR_CK(cudaMalloc(&h->d_screen, (size_t)max_width * sizeof(int32_t)));
+        CSDR_CK(cudaMalloc(&h->d_screen, 2 * (size_t)max_width * sizeof(int32_t)));
         h->screen_cap = max_width;
     }
     k_screen<<<(max_width + 127) / 128, 128, 0, h->st>>>(h->d_ave, N, h->invert ? 1 : 0, bin_min, bin_max, max_width, max_height,
-                                                         gain, off, h->d_screen);
+                                                         gain, off, h->d_screen, max_height2, out2 ? h->d_screen + max_width : nullptr);
     h->lc.n++;
     CSDR_CK(cudaGetLastError());
     CSDR_CK(cudaMemcpyAsync(out, h->d_screen, (size_t)max_width * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
+    if (out2) CSDR_CK(cudaMemcpyAsync(out2, h->d_screen + max_width, (size_t)max_width * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
     CSDR_CK(cudaStreamSynchronize(h->st));
     if (overload) *overload = h->overload ? 1 : 0;
+    return CUTESDR_OK;
+}
+
+int cutesdr_fft_get_screen(cutesdr_fft* h, int max_height, int max_width, double max_db, double min_db, int start_freq,
+                           int stop_freq, int32_t* out, int* overload)
+{
+    return fft_screen(h, max_height, max_width, max_db, min_db, start_freq, stop_freq, out, 0, nullptr, overload);
+}
+
+int cutesdr_fft_get_plot(cutesdr_fft* h, int trace_height, int width, double max_db, double min_db, int start_freq, int stop_freq,
+                         int32_t* waterfall_row, int32_t* trace, int* overload)
+{
+    if (!waterfall_row || !trace) { set_error("fft_get_plot: bad arguments"); return CUTESDR_E_ARG; }
+    return fft_screen(h, 255, width, max_db, min_db, start_freq, stop_freq, waterfall_row, trace_height, trace, overload);
+}
+
+int cutesdr_fft_set_dc_offset(cutesdr_fft* h, double off_i, double off_q)
+{
+    if (!h) { set_error("fft_set_dc_offset: bad handle"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->dc = make_float2((float)off_i, (float)off_q);
     return CUTESDR_OK;
 }
 

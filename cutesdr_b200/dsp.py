@@ -328,6 +328,19 @@ class CFft(_Handle):
                                             int(stop), out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ov)))
         return bool(ov.value), out
 
+    def GetPlot(self, trace_h, width, max_db, min_db, start, stop):
+        """CPlotter::draw's waterfall row (255 levels) and 2-D trace from one pass (gui/plotter.cpp:429-456)."""
+        wf = np.zeros(width, dtype=np.int32)
+        tr = np.zeros(width, dtype=np.int32)
+        ov = C.c_int()
+        check(self.L.cutesdr_fft_get_plot(self.h, int(trace_h), int(width), float(max_db), float(min_db), int(start), int(stop),
+                                          wf.ctypes.data_as(C.POINTER(C.c_int32)), tr.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ov)))
+        return bool(ov.value), wf, tr
+
+    def SetDcOffset(self, off_i, off_q):
+        """m_NCOSpurOffsetI/Q of the display copy (interface/sdrinterface.cpp:889-894)."""
+        check(self.L.cutesdr_fft_set_dc_offset(self.h, float(off_i), float(off_q)))
+
     def FwdFFT(self, x):
         buf = _cpx_to_f64(x)
         check(self.L.cutesdr_fft_fwd(self.h, _dptr(buf)))

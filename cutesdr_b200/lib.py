@@ -84,6 +84,8 @@ PROTOTYPES = {
     "cutesdr_fft_put_device": (C.c_int, [_vp, C.c_int, _vp, _ip]),
     "cutesdr_fft_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "cutesdr_fft_get_screen": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _i32, _ip]),
+    "cutesdr_fft_get_plot": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _i32, _i32, _ip]),
+    "cutesdr_fft_set_dc_offset": (C.c_int, [_vp, C.c_double, C.c_double]),
     "cutesdr_fft_fwd": (C.c_int, [_vp, _dp]),
     "cutesdr_fft_rev": (C.c_int, [_vp, _dp]),
     "cutesdr_fft_get_ave": (C.c_int, [_vp, _fp, C.c_int]),

@@ -212,6 +212,13 @@ int cutesdr_fft_launch_count(cutesdr_fft* h, long long* n);
 /* GetScreenIntegerFFTData(...) -> out[max_width], *overload   dsp/fft.cpp:308-410 */
 int cutesdr_fft_get_screen(cutesdr_fft* h, int max_height, int max_width, double max_db, double min_db,
                            int start_freq, int stop_freq, int32_t* out, int* overload);
+/* CPlotter::draw's two mappings of one spectrum (gui/plotter.cpp:429-456) from ONE pass: the 255-level waterfall row
+ * (GetScreenIntegerFFTData(255, w, ...)) and the 2-D trace (GetScreenIntegerFFTData(h, w, ...)) */
+int cutesdr_fft_get_plot(cutesdr_fft* h, int trace_height, int width, double max_db, double min_db, int start_freq,
+                         int stop_freq, int32_t* waterfall_row, int32_t* trace, int* overload);
+/* I/Q DC offset subtracted from the display copy of the samples before windowing and the overload test
+ * (m_NCOSpurOffsetI/Q, interface/sdrinterface.cpp:889-894) */
+int cutesdr_fft_set_dc_offset(cutesdr_fft* h, double off_i, double off_q);
 /* FwdFFT / RevFFT(TYPECPX* pInOutBuf): in-place complex transform of the object's size, unnormalised.
  * As in the reference, "forward" is the e^{+j 2 pi nk/N} kernel and "reverse" its conjugate
  *                                                              dsp/fft.cpp:416-426 */

@@ -723,3 +723,33 @@ def test_wire_format_ingest_is_bit_identical(lib):
     a24, n24 = make().ProcessRaw(packed.reshape(-1), 2)
     assert np.array_equal(n_ref, n24)
     assert np.array_equal(a_ref, a24)
+
+
+def test_plot_producer_and_display_dc_offset(lib, ref):
+    """CPlotter::draw's two mappings from one pass == two GetScreenIntegerFFTData calls (gui/plotter.cpp:429-456), and
+    the display copy's I/Q DC-offset correction (interface/sdrinterface.cpp:889-894) == subtracting it on the host."""
+    N, fs = 4096, 2e6
+    dc = (137.25, -88.5)
+    r, g, g2 = ref.RefFft(), cs.CFft(), cs.CFft()
+    for f in (r, g, g2):
+        f.SetFFTParams(N, False, 0.0, fs)
+        f.SetFFTAve(2)
+    g.SetDcOffset(*dc)
+    t = np.arange(N) / fs
+    for k in range(4):
+        x = (noise(N, 300.0) + 9000.0 * np.exp(2j * np.pi * 212345.0 * (t + k * N / fs)) + (dc[0] + 1j * dc[1]))
+        x = x.astype(np.complex64).astype(np.complex128)
+        xc = (x - (dc[0] + 1j * dc[1])).astype(np.complex64).astype(np.complex128)      # what the reference's loop feeds the FFT
+        r.PutInDisplayFFT(xc)
+        g.PutInDisplayFFT(x)
+        g2.PutInDisplayFFT(xc)
+    for (h, w, lo, hi) in ((300, 800, -1000000, 1000000), (180, 1000, -50000, 400000)):
+        ov, wf, tr = g.GetPlot(h, w, 0.0, -140.0, lo, hi)
+        ov_a, a = g.GetScreenIntegerFFTData(255, w, 0.0, -140.0, lo, hi)
+        ov_b, b = g.GetScreenIntegerFFTData(h, w, 0.0, -140.0, lo, hi)
+        assert np.array_equal(wf, a) and np.array_equal(tr, b) and ov == ov_a == ov_b
+        _, ra = r.GetScreenIntegerFFTData(255, w, 0.0, -140.0, lo, hi)
+        _, rb = r.GetScreenIntegerFFTData(h, w, 0.0, -140.0, lo, hi)
+        assert np.abs(wf - ra).max() <= 1 and np.abs(tr - rb).max() <= 1
+        _, wf2, tr2 = g2.GetPlot(h, w, 0.0, -140.0, lo, hi)
+        assert np.abs(wf - wf2).max() <= 1 and np.abs(tr - tr2).max() <= 1
