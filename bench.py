@@ -204,7 +204,7 @@ def run_reference(args):
             "cpu_baseline": {"value": r["value"], "unit": "Msps*ch", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "Msps*ch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -379,7 +379,7 @@ def run_ours(args):
                         "steps": e2e_steps},
                 "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -394,9 +394,25 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: everything native libraries print there (NCCL's version banner, ...) is
+    # sent to stderr for the duration of the run; emit() switches the real stdout back for the line itself
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
