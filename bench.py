@@ -296,20 +296,20 @@ def run_ours(args):
     # two host audio landing buffers: a step's D2H may still be in flight when the next step is queued
     h_audio2 = [h_audio, torch.zeros((nch, audio_stride), dtype=torch.float32).pin_memory()]
 
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+
     def step_e2e(i):
         if world == 1:
             # pipelined C-ABI call: H2D of block i overlaps the kernels of block i-1, D2H on its own stream
             return bank.process_async_ptr(L, h_pin[i % nblk].data_ptr(), h_audio2[i & 1].data_ptr(), audio_stride, n_out)
-        if rank == 0:
-            d_in.copy_(h_pin[i % nblk], non_blocking=True)
-        dist.broadcast(d_in, src=0)
-        torch.cuda.current_stream().synchronize()
-        m = bank.process_device(d_in.data_ptr(), L, d_audio.data_ptr(), audio_stride)
-        bank.synchronize()
-        if m > 0:
-            h_audio[:, :m].copy_(d_audio[:, :m], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return m
+        # N > 1: rank 0's H2D and the NCCL broadcast run on a communication stream; the bank takes the block over in
+        # stream order (cutesdr_bank_process_async_device), so block i+1 is in flight while block i is processed and
+        # the audio D2H runs on the bank's copy stream
+        with torch.cuda.stream(comm):
+            if rank == 0:
+                d_in.copy_(h_pin[i % nblk], non_blocking=True)
+            dist.broadcast(d_in, src=0)
+            return bank.process_async_device_ptr(L, d_in.data_ptr(), comm.cuda_stream, h_audio2[i & 1].data_ptr(), audio_stride, n_out)
 
     for i in range(3):
         step_e2e(i)

@@ -565,7 +565,8 @@ static int bank_process_host(cutesdr_bank* b, int n_in, const void* iq, int fmt,
     return nmax;
 }
 
-static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out);
+static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out,
+                              bool from_device = false, cudaStream_t src_stream = 0);
 
 int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out)
 {
@@ -578,7 +579,13 @@ int cutesdr_bank_process_async_raw(cutesdr_bank* b, int n_in, const void* data, 
     return bank_process_async(b, n_in, data, fmt, audio, audio_stride, n_out);
 }
 
-static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out)
+int cutesdr_bank_process_async_device(cutesdr_bank* b, int n_in, const void* d_iq, void* src_stream, float* audio, int audio_stride, int* n_out)
+{
+    return bank_process_async(b, n_in, d_iq, 0, audio, audio_stride, n_out, true, reinterpret_cast<cudaStream_t>(src_stream));
+}
+
+static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out,
+                              bool from_device, cudaStream_t src_stream)
 {
     if (!b || !iq || (audio && audio_stride <= 0)) { set_error("bank_process_async: bad arguments"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
@@ -602,8 +609,19 @@ static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt
     if (!b->d_xs[slot]) CSDR_CK(cudaMalloc(&b->d_xs[slot], (size_t)b->L * sizeof(float2)));
     // H2D of this block on the copy stream, as soon as the slot's previous block has been consumed
     if (b->async_blocks >= 2) CSDR_CK(cudaStreamWaitEvent(b->st_h2d, b->ev_free[slot], 0));
-    CSDR_CK(cudaMemcpyAsync(b->d_xs[slot], iq, (size_t)b->L * sample_bytes(fmt), cudaMemcpyHostToDevice, b->st_h2d));
-    CSDR_CK(cudaEventRecord(b->ev_h2d[slot], b->st_h2d));
+    if (from_device) {
+        // the block sits in the caller's device buffer and is read in stream order with respect to src_stream: the
+        // copy into the slot waits for everything queued there so far (an NCCL broadcast, ...), and src_stream
+        // waits for the copy, so the caller may queue the next write into the same buffer straight away
+        CSDR_CK(cudaEventRecord(b->ev_h2d[slot], src_stream));
+        CSDR_CK(cudaStreamWaitEvent(b->st_h2d, b->ev_h2d[slot], 0));
+        CSDR_CK(cudaMemcpyAsync(b->d_xs[slot], iq, (size_t)b->L * sizeof(float2), cudaMemcpyDeviceToDevice, b->st_h2d));
+        CSDR_CK(cudaEventRecord(b->ev_h2d[slot], b->st_h2d));
+        CSDR_CK(cudaStreamWaitEvent(src_stream, b->ev_h2d[slot], 0));
+    } else {
+        CSDR_CK(cudaMemcpyAsync(b->d_xs[slot], iq, (size_t)b->L * sample_bytes(fmt), cudaMemcpyHostToDevice, b->st_h2d));
+        CSDR_CK(cudaEventRecord(b->ev_h2d[slot], b->st_h2d));
+    }
     CSDR_CK(cudaStreamWaitEvent(b->st, b->ev_h2d[slot], 0));
     const void* dblk = nullptr;
     int dfmt = 0;

@@ -185,6 +185,11 @@ class ReceiverBank:
         p = n_out_arr.ctypes.data_as(C.POINTER(C.c_int)) if n_out_arr is not None else None
         return check(self.L.cutesdr_bank_process_async(self.h, int(n_in), iq_ptr, audio_ptr, int(audio_stride), p))
 
+    def process_async_device_ptr(self, n_in, d_iq_ptr, src_stream, audio_ptr, audio_stride, n_out_arr=None):
+        """Pipelined form for a block already in device memory (stream-ordered with src_stream, a cudaStream_t)."""
+        p = n_out_arr.ctypes.data_as(C.POINTER(C.c_int)) if n_out_arr is not None else None
+        return check(self.L.cutesdr_bank_process_async_device(self.h, int(n_in), d_iq_ptr, src_stream, audio_ptr, int(audio_stride), p))
+
     def process_device(self, d_iq_ptr, n_in, d_audio_ptr=None, audio_stride=0):
         m = C.c_int()
         check(self.L.cutesdr_bank_process_device(self.h, d_iq_ptr, int(n_in), d_audio_ptr, int(audio_stride), C.byref(m)))

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "cutesdr_bank_process_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_raw": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_async_raw": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip]),
+    "cutesdr_bank_process_async_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_synchronize": (C.c_int, [_vp]),
     "cutesdr_bank_join": (C.c_int, [_vp]),

@@ -113,6 +113,12 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
 #define CUTESDR_FMT_CS24 2
 int cutesdr_bank_process_raw(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out);
 int cutesdr_bank_process_async_raw(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out);
+/* Pipelined form for a block that is already in DEVICE memory (multi-GPU: the NCCL broadcast of rank 0's block lands
+ * there). d_iq (complex64[n_in]) is read in stream order with respect to src_stream (a cudaStream_t): the library
+ * waits for the work queued on it so far and makes it wait until the block has been taken over, so the caller can
+ * queue the next broadcast into the same buffer immediately. audio is a pinned HOST buffer as in process_async. */
+int cutesdr_bank_process_async_device(cutesdr_bank* b, int n_in, const void* d_iq, void* src_stream, float* audio,
+                                      int audio_stride, int* n_out);
 
 /* Pipelined form of cutesdr_bank_process for exactly one DSP block per call (n_in == block_length,
  * iq and audio in PINNED host memory): the call only queues work -- the H2D copy of this block runs on

@@ -594,6 +594,59 @@ def test_process_async_matches_process(lib):
     assert sum(int(n.max()) for n in n_outs) >= 4096
 
 
+def test_device_resident_entry_points_match_process(lib):
+    """cutesdr_bank_process_device and the stream-ordered pipelined cutesdr_bank_process_async_device (the multi-GPU
+    path: the block arrives in device memory on a communication stream) give the same bits as the host call."""
+    import torch
+    fs = 2e6
+    nch = 9
+    modes = [[M.DEMOD_AM, M.DEMOD_FM, M.DEMOD_USB][c % 3] for c in range(nch)]
+    carriers = carrier_grid(nch, 150e3)
+    infos = [M.demod_info(m, HiCut=2800, LowCut=100) if m == M.DEMOD_USB else M.demod_info(m) for m in modes]
+    banks = []
+    for _ in range(3):
+        b = cs.ReceiverBank(nch, fs)
+        for c in range(nch):
+            b.SetDemod(c, modes[c], infos[c])
+            b.SetDemodFreq(c, -carriers[c])
+        banks.append(b)
+    L = banks[0].block_length()
+    nblk = 12
+    iq = syn_iq(fs, nblk * L, modes, carriers, seed=78)
+    stride = 2304
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(device=dev)
+    d_in = torch.empty(2 * L, dtype=torch.float32, device=dev)            # ONE buffer, rewritten every block
+    d_in2 = torch.empty(2 * L, dtype=torch.float32, device=dev)
+    d_audio = torch.zeros((nch, stride), dtype=torch.float32, device=dev)
+    h_blk = [torch.from_numpy(iq[k * L:(k + 1) * L].view(np.float32).copy()).pin_memory() for k in range(nblk)]
+    h_aud = [torch.zeros((nch, stride), dtype=torch.float32).pin_memory() for _ in range(nblk)]
+    n_outs = [np.zeros(nch, dtype=np.int32) for _ in range(nblk)]
+    want, got_dev = [], []
+    for k in range(nblk):
+        audio, n_out = banks[0].ProcessData(iq[k * L:(k + 1) * L])
+        want.append([audio[c, :n_out[c]].copy() for c in range(nch)])
+        # synchronous device entry point
+        d_in2.copy_(h_blk[k])
+        torch.cuda.synchronize()
+        m = banks[1].process_device(d_in2.data_ptr(), L, d_audio.data_ptr(), stride)
+        banks[1].synchronize()
+        got_dev.append(d_audio[:, :m].cpu().numpy().copy() if m > 0 else np.zeros((nch, 0), np.float32))
+        # pipelined, stream-ordered: the "broadcast" is a copy on the side stream into the same buffer every block
+        with torch.cuda.stream(side):
+            d_in.copy_(h_blk[k], non_blocking=True)
+            banks[2].process_async_device_ptr(L, d_in.data_ptr(), side.cuda_stream, h_aud[k].data_ptr(), stride, n_outs[k])
+    banks[2].synchronize()
+    torch.cuda.synchronize()
+    for k in range(nblk):
+        for c in range(nch):
+            a = want[k][c]
+            assert got_dev[k].shape[1] >= len(a) and np.array_equal(got_dev[k][c, :len(a)], a)
+            assert n_outs[k][c] == len(a)
+            assert np.array_equal(h_aud[k][c, :len(a)].numpy(), a)
+    assert sum(int(n.max()) for n in n_outs) >= 4096
+
+
 @pytest.mark.parametrize("N", [2048, 4096, 65536])
 def test_fft_fwd_rev(lib, ref, N):
     """CFft::FwdFFT / RevFFT against the reference's Ooura transforms (same sign convention, unnormalised)."""
