@@ -467,17 +467,21 @@ static K1Fn k1_kernel(int ncic, int nhb)
 //   * A (per-channel coefficients, planes Ar/Ai x hi/lo, 48 columns each) lives in TMEM for the whole
 //     CTA: the MMAs read only B from shared memory (an SS-form MMA of this shape saturates the 128 B/clk
 //     shared-memory port with its A re-reads).
-//   * X is staged by 4 producer warps (one tile per warp, 4 tiles in flight) as 4 planes (re/im x hi/lo)
-//     in NATURAL time order with zero duplication: 16-byte chunk q (4 samples) of X-row m (16 samples) sits
-//     at byte 16 m + P q. K-major, no swizzle, LBO = P, SBO = 128: MMA row n reads row m0-2+n+shift, and the
-//     three 16-sample shifts of the Hankel matrix are just the descriptor start address + 16 * shift.
-//   * 4 independent time segments per CTA, interleaved tile by tile; segment e owns TMEM accumulator slot
-//     e and epilogue warp set e (4 warps, TMEM lane = channel). An epilogue thread pulls 16 consecutive
-//     outputs per tcgen05.ld, multiplies by the oscillator at the decimated rate (re-seeded exactly from
-//     the 64-bit phase every 32 outputs), and runs the remaining CIC3 / fused 11-tap half-band stages and
-//     the store exactly as kernel 1 does. 16 epilogue warps keep 4 warps per scheduler busy, which this
-//     dependent-chain code needs; the accumulator slot is released as soon as its values are in registers.
+//   * X is staged by 4 producer warps (a warp pair per segment, each warp half of a tile's chunks, the global
+//     loads of the next tile in flight while the current one is converted) as 4 planes (re/im x hi/lo) in
+//     NATURAL time order with zero duplication: 16-byte chunk q (4 samples) of X-row m (16 samples) sits at
+//     byte 16 m + P q. K-major, no swizzle, LBO = P, SBO = 128: MMA row n reads row m0-2+n+shift, and the three
+//     16-sample shifts of the Hankel matrix are just the descriptor start address + 16 * shift.
+//   * 2 independent time segments per CTA, interleaved tile by tile; segment e owns two TMEM accumulator slots
+//     (tile parity), an epilogue warp set (4 warps, TMEM lane = channel) and two MMA-issuing warps (one per
+//     re / im accumulator, so every accumulator has exactly one writer and a fixed MMA order). An epilogue thread
+//     pulls 16 consecutive outputs per tcgen05.ld -- the next 16 in flight under the arithmetic of the current
+//     16 --, multiplies by the oscillator at the decimated rate (re-seeded exactly from the 64-bit phase every
+//     32 outputs), and runs the remaining CIC3 / fused 11-tap half-band stages and the store exactly as kernel 1
+//     does. The accumulator slot is released as soon as the tile is in registers.
 //   * mbarriers + tcgen05.commit order producers -> MMA -> epilogue; B runs through an 8-stage ring.
+//   * `dbg` (CUTESDR_TC_DBG) switches roles off for ablation timing only: 1 = no epilogue arithmetic/stores,
+//     2 = no MMAs, 4 = no operand staging. Results are meaningless with it set.
 // Segments re-prime the feed-forward stages with a halo of PRE outputs, like kernel 1's tiles.
 // ------------------------------------------------------------------------------------------
 constexpr int kTcN = 32;                                  // outputs (fs/16) per MMA tile
