@@ -130,16 +130,17 @@ __global__ void __launch_bounds__(128) k_post_reset(PostBufs b)
 }
 
 // ---- S-meter dB, AGC log-magnitude and its sliding-window maximum; CTA per channel
-// dynamic smem: 2 x (kAgcBuf + max_n) doubles
+// dynamic smem: 2 x (window - 1 + n) doubles -- only indices [kAgcBuf - (window-1), kAgcBuf + n) of the two work
+// arrays are ever touched, so they are allocated compactly (3 -> 9 resident CTAs per SM at n = 1024)
 __global__ void __launch_bounds__(256) k_post_pre(PostBufs b, int n, int window)
 {
     extern __shared__ double sm_d[];
     const int c = blockIdx.x;
-    const int len_all = kAgcBuf + b.row;
-    double* A = sm_d;
-    double* B = sm_d + len_all;
     const int hn = window - 1;
     const int lo = kAgcBuf - hn;
+    const int len_cmp = hn + n;
+    double* A = sm_d - lo;                 // A[lo] is sm_d[0]
+    double* B = sm_d + len_cmp - lo;
     const int mode = b.mode[c];
     const float2* yrow = b.y + (size_t)c * b.y_row + kYHist;
     for (int i = threadIdx.x; i < hn; i += blockDim.x) A[lo + i] = b.magh[(size_t)c * kAgcBuf + i];
@@ -751,7 +752,7 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
     const size_t smem_pre = 2 * (size_t)(kAgcBuf + max_n_) * sizeof(double);
     const size_t smem_fir = (size_t)((uni_.stereo ? 2 : 1) * (kHist + max_n_) + kFirMax) * sizeof(double);
     const int seq_blocks = (nch_ + 31) / 32;
-    k_post_pre<<<nch_, 256, smem_pre, st_>>>(b, n, uni_.agc_window);
+    k_post_pre<<<nch_, 256, 2 * (size_t)(uni_.agc_window - 1 + n) * sizeof(double), st_>>>(b, n, uni_.agc_window);
     k_post_seq1<<<2 * seq_blocks, 32, 0, st_>>>(b, n, uni_);
     k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, uni_.stereo, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_seq2<<<seq_blocks, 32, 0, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
