@@ -158,3 +158,27 @@ def test_kernel1t_many_channel_groups_and_ragged_group():
         assert n1[0] == n[c] and n1[0] > 0
         assert np.array_equal(a1[0, :n1[0]], a[c, :n[c]])
         assert np.abs(a1[0, :n1[0]]).max() > 0
+
+
+def test_fused_tail_halfbands_are_bit_identical():
+    """CUTESDR_HBTAIL=1 runs the last half-band stages (15..51 taps) in one pass (k_hb_tail) instead of one launch per
+    stage; same operation order, so the audio must not change by a bit."""
+    fs = 100147200.0
+    nch = 64                                  # two chain groups of 32 channels (whole 128-byte channel rows)
+    modes = [[M.DEMOD_FM, M.DEMOD_AM][c // 32] for c in range(nch)]
+    carriers = carrier_grid(nch, 1.0e6)
+    outs = []
+    for tail in (None, "1"):
+        with _env(CUTESDR_HBTAIL=tail):
+            b = cs.ReceiverBank(nch, fs)
+            for c in range(nch):
+                b.SetDemod(c, modes[c], M.demod_info(modes[c]))
+                b.SetDemodFreq(c, -carriers[c])
+            L = b.block_length()
+            x = syn_iq(fs, 6 * L, modes, carriers, seed=31)
+            launches0 = b.launch_count()
+            a, n = b.ProcessData(x)
+            outs.append((a, n, b.launch_count() - launches0))
+    assert outs[0][1].max() > 0
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
+    assert outs[1][2] < outs[0][2]            # fewer launches: the fused pass really ran
