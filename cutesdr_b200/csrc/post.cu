@@ -481,22 +481,53 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
         return;
     }
     if (mode != POST_AM && mode != POST_FM) return;
-    double* v = sm_d;
-    double* h = sm_d + kHist + b.row;
+    // The input row (kHist samples of history + n new ones) is staged in shared memory as four residue planes,
+    // sample p at plane (p & 3), position (p >> 2). A thread computes FOUR consecutive outputs with a sliding
+    // register window, so every tap costs one conflict-free shared load of x (consecutive positions across the
+    // lanes) and one broadcast load of the coefficient per four multiply-adds -- a quarter of the shared-memory
+    // traffic of one load per product. Each output still sums its products in ascending tap order.
+    const int Q = ((kHist + n + 3) >> 2) + 1;           // plane stride (doubles)
+    double* v = sm_d;                                   // 4 * Q doubles  (<= kHist + row + 8)
+    double* h = sm_d + kHist + b.row + 8;
     const int ntaps = (int)PAR(P_NTAPS);
     double* vrow = b.v + (size_t)c * b.v_row;
-    for (int i = threadIdx.x; i < kHist + n; i += blockDim.x) v[i] = vrow[i];
+    for (int i = threadIdx.x; i < kHist + n; i += blockDim.x) v[(i & 3) * Q + (i >> 2)] = vrow[i];
     for (int i = threadIdx.x; i < kFirMax; i += blockDim.x) h[i] = b.taps[(size_t)c * kFirMax + i];
     __syncthreads();
-    for (int i = threadIdx.x; i < kHist; i += blockDim.x) vrow[i] = v[n + i];      // FIR history for the next burst
+    for (int i = threadIdx.x; i < kHist; i += blockDim.x) {       // FIR history for the next burst
+        const int p = n + i;
+        vrow[i] = v[(p & 3) * Q + (p >> 2)];
+    }
+    // acc[j] = sum_k h[k] x[kHist + 4g + j - k]   (CFir::ProcessFilter, dsp/fir.cpp:72-91)
+    auto fir4 = [&](int g, double* acc) {
+        const int p0 = kHist + 4 * g;
+        double w0 = v[((p0)&3) * Q + ((p0) >> 2)], w1 = v[((p0 + 1) & 3) * Q + ((p0 + 1) >> 2)],
+               w2 = v[((p0 + 2) & 3) * Q + ((p0 + 2) >> 2)], w3 = v[((p0 + 3) & 3) * Q + ((p0 + 3) >> 2)];
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+        for (int k = 0; k < ntaps; k++) {
+            const double hk = h[k];
+            acc[0] += hk * w0;
+            acc[1] += hk * w1;
+            acc[2] += hk * w2;
+            acc[3] += hk * w3;
+            const int p = p0 - (k + 1);                 // >= 0: k + 1 <= kFirMax - 1 + 1 <= kHist + 1 and p0 >= kHist ... guarded below
+            w3 = w2; w2 = w1; w1 = w0;
+            w0 = p >= 0 ? v[(p & 3) * Q + (p >> 2)] : 0.0;
+        }
+    };
     if (mode == POST_AM) {
-        // CFir::ProcessFilter, dsp/fir.cpp:72-91 (post filter of dsp/amdemod.cpp:80)
-        for (int t = threadIdx.x; t < n; t += blockDim.x) {
-            double acc = 0.0;
-            for (int k = 0; k < ntaps; k++) acc += h[k] * v[kHist + t - k];
+        // post filter of dsp/amdemod.cpp:80
+        for (int g = threadIdx.x; 4 * g < n; g += blockDim.x) {
+            double acc[4];
+            fir4(g, acc);
             if (aout) {
-                if (stereo) { aout[2 * t] = (float)acc; aout[2 * t + 1] = (float)acc; }   // dsp/amdemod.cpp:87-104
-                else aout[t] = (float)acc;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int t = 4 * g + j;
+                    if (t >= n) break;
+                    if (stereo) { aout[2 * t] = (float)acc[j]; aout[2 * t + 1] = (float)acc[j]; }   // dsp/amdemod.cpp:87-104
+                    else aout[t] = (float)acc[j];
+                }
             }
         }
         return;
@@ -505,10 +536,14 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
     // |high-passed audio|; only its value at the END of the burst is used, which is the weighted sum
     //   (1-a)^n s0 + a * sum_t (1-a)^(n-1-t) |hp[t]|
     double part = 0.0;
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        double acc = 0.0;
-        for (int k = 0; k < ntaps; k++) acc += h[k] * v[kHist + t - k];
-        part += fabs(acc) * b.qpow[n - 1 - t];
+    for (int g = threadIdx.x; 4 * g < n; g += blockDim.x) {
+        double acc[4];
+        fir4(g, acc);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int t = 4 * g + j;
+            if (t < n) part += fabs(acc[j]) * b.qpow[n - 1 - t];
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
@@ -640,7 +675,7 @@ int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream
     CSDR_CK(cudaMemsetAsync(d_y_, 0, rows * y_row_ * sizeof(float2), st_));
     CSDR_CK(cudaMemsetAsync(d_v_, 0, rows * v_row_ * sizeof(double), st_));
     const size_t smem_pre = 2 * (size_t)(kAgcBuf + max_n_) * sizeof(double);
-    const size_t smem_fir = (size_t)(2 * (kHist + max_n_) + kFirMax) * sizeof(double);
+    const size_t smem_fir = (size_t)(2 * (kHist + max_n_) + kFirMax + 16) * sizeof(double);
     if (smem_pre > 200 * 1024) { set_error("post: burst capacity %d too large", max_n_); return CUTESDR_E_ARG; }
     CSDR_CK(cudaFuncSetAttribute(k_post_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pre));
     CSDR_CK(cudaFuncSetAttribute(k_post_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_fir, 1024)));
@@ -750,7 +785,7 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
         need_reset_kernel_ = false;
     }
     const size_t smem_pre = 2 * (size_t)(kAgcBuf + max_n_) * sizeof(double);
-    const size_t smem_fir = (size_t)((uni_.stereo ? 2 : 1) * (kHist + max_n_) + kFirMax) * sizeof(double);
+    const size_t smem_fir = (size_t)((uni_.stereo ? 2 : 1) * (kHist + max_n_) + kFirMax + 16) * sizeof(double);
     const int seq_blocks = (nch_ + 31) / 32;
     k_post_pre<<<nch_, 256, 2 * (size_t)(uni_.agc_window - 1 + n) * sizeof(double), st_>>>(b, n, uni_.agc_window);
     k_post_seq1<<<2 * seq_blocks, 32, 0, st_>>>(b, n, uni_);
