@@ -1,7 +1,7 @@
 """Kernel 1T (tensor cores) vs kernel 1 (CUDA cores) vs the C oracle on one down-converter (debug aid)."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import cutesdr_b200 as cs
 from cutesdr_b200.synth import snr_db
 from oracle import oracle_binding as ob
