@@ -17,6 +17,7 @@
 // Reference: CDownConvert::ProcessData and the three DecBy2 classes, dsp/downconvert.cpp:186-460.
 #include "decimator.cuh"
 #include "halfband_tables.h"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace csdr {
@@ -526,6 +527,14 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -639,6 +648,52 @@ __device__ __noinline__ TcChunk tc_load_chunk_slow(const void* __restrict__ x, i
     return r;
 }
 
+// fp16 form of the same table: [channel][Ar_hi, Ar_lo, Ai_hi, Ai_lo][24 words], word j = (element 2j | element 2j+1 << 16),
+// which is how a 16-bit A operand sits in TMEM (one K pair per 32-bit column); the row stride stays 192 words
+__global__ void k_tc_coeffs_f16(const NcoDev* __restrict__ nco, int nch, int groups, uint32_t* __restrict__ tab)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= groups * 128 * 24) return;
+    const int kp = idx % 24, c = idx / 24;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int k = 2 * kp + h, j = 47 - k;
+        double ar = 0.0, ai = 0.0;
+        if (c < nch && j < 46) {
+            const unsigned long long ph = 0ull - nco[c].inc * (unsigned long long)j;
+            double sn, cs;
+            sincospi((double)(long long)ph * (1.0 / 9223372036854775808.0), &sn, &cs);
+            ar = (double)c_cic4[j] * cs;
+            ai = (double)c_cic4[j] * sn;
+        }
+        const __half rh = __double2half(ar), ih = __double2half(ai);
+        const __half rl = __double2half(ar - (double)__half2float(rh)), il = __double2half(ai - (double)__half2float(ih));
+        w[0] |= (uint32_t)__half_as_ushort(rh) << (16 * h);
+        w[1] |= (uint32_t)__half_as_ushort(rl) << (16 * h);
+        w[2] |= (uint32_t)__half_as_ushort(ih) << (16 * h);
+        w[3] |= (uint32_t)__half_as_ushort(il) << (16 * h);
+    }
+    uint32_t* row = tab + (size_t)c * 192;
+#pragma unroll
+    for (int pl = 0; pl < 4; pl++) row[24 * pl + kp] = w[pl];
+}
+
+// max(|re|, |im|) over [saved halo | block], as the bit pattern of a non-negative float (atomicMax on the word):
+// the power-of-two input scale of the fp16 form of kernel 1T comes from it, so that form is as scale-free as fp32
+__global__ void __launch_bounds__(256) k_absmax(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, int L,
+                                                unsigned* __restrict__ out)
+{
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x - kHaloMax; i < L; i += gridDim.x * blockDim.x) {
+        const float2 v = i < 0 ? halo_cur[kHaloMax + i] : fetch_sample(x, fmt, i);
+        m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
 template <int NCR, int NHB, int G0, int G1> struct TcStrip {
     static __device__ __forceinline__ void run(const float* re, const float* im, float2& S, float2 w, CicSt* st, float2* ev, Hb11St* hs,
                                                TcEmit& em)
@@ -653,13 +708,30 @@ template <int NCR, int NHB, int G1> struct TcStrip<NCR, NHB, G1, G1> {
     static __device__ __forceinline__ void run(const float*, const float*, float2&, float2, CicSt*, float2*, Hb11St*, TcEmit&) {}
 };
 
-template <int NCR, int NHB>
+template <int NCR, int NHB, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_mix_tc(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, float2* __restrict__ halo_next, int L, int seg_len,
-             const float* __restrict__ coef_tab, const NcoDev* __restrict__ nco, const unsigned long long* __restrict__ phase_cur,
-             unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale, int dbg)
+             const float* __restrict__ coef_tab, const unsigned* __restrict__ absmax_bits, const NcoDev* __restrict__ nco,
+             const unsigned long long* __restrict__ phase_cur, unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale,
+             int dbg)
 {
     typedef TcCfg<NCR, NHB> Cfg;
+    // F16: operands are fp16 hi + lo (same 11 significant bits as tf32, kind::f16 runs at twice the rate and takes K = 16):
+    // a 16-byte shared-memory chunk holds 8 samples, an X row is 2 chunks = ONE MMA K-step, an A plane is 24 TMEM columns.
+    constexpr int kPl = F16 ? 2 * kTcP : kTcPlane;            // bytes per B plane
+    constexpr int kACols = F16 ? 24 : 48;                     // TMEM columns per A plane
+    constexpr int kKSteps = F16 ? 3 : 6;
+    // power-of-two input scale (fp16 only): block maximum -> [2^9, 2^10); exact, undone at the output scale
+    float s_in = 1.f, s_out = 1.f;
+    if constexpr (F16) {
+        const float mx = __uint_as_float(*absmax_bits);
+        if (mx > 0.f && mx < 3.0e38f) {
+            int ex;
+            frexpf(mx, &ex);
+            s_in = ldexpf(1.f, 10 - ex);
+            s_out = ldexpf(1.f, ex - 10);
+        }
+    }
     extern __shared__ __align__(128) unsigned char tc_smem[];
     unsigned char* sB = tc_smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + kTcBarOff);
@@ -753,15 +825,38 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int idx = c_lo + lane + 32 * j;
                 if (idx < c_hi) {
                     const float4 a = va[j], b = vb[j];
-                    const float4 rh = make_float4(tf32_rn(a.x), tf32_rn(a.z), tf32_rn(b.x), tf32_rn(b.z));
-                    const float4 ih = make_float4(tf32_rn(a.y), tf32_rn(a.w), tf32_rn(b.y), tf32_rn(b.w));
-                    const float4 rl = make_float4(tf32_rn(a.x - rh.x), tf32_rn(a.z - rh.y), tf32_rn(b.x - rh.z), tf32_rn(b.z - rh.w));
-                    const float4 il = make_float4(tf32_rn(a.y - ih.x), tf32_rn(a.w - ih.y), tf32_rn(b.y - ih.z), tf32_rn(b.w - ih.w));
-                    const int off = 16 * (idx >> 2) + kTcP * (idx & 3);
-                    *reinterpret_cast<float4*>(pl + off) = rh;
-                    *reinterpret_cast<float4*>(pl + kTcPlane + off) = rl;
-                    *reinterpret_cast<float4*>(pl + 2 * kTcPlane + off) = ih;
-                    *reinterpret_cast<float4*>(pl + 3 * kTcPlane + off) = il;
+                    if constexpr (F16) {
+                        // 4 samples = half of a 16-byte chunk: row idx / 4, chunk (idx / 2) % 2, half idx % 2
+                        const float xr[4] = {a.x * s_in, a.z * s_in, b.x * s_in, b.z * s_in};
+                        const float xi[4] = {a.y * s_in, a.w * s_in, b.y * s_in, b.w * s_in};
+                        __half2 rh[2], rl[2], ih[2], il[2];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            rh[h] = __floats2half2_rn(xr[2 * h], xr[2 * h + 1]);
+                            ih[h] = __floats2half2_rn(xi[2 * h], xi[2 * h + 1]);
+                            const float2 rf = __half22float2(rh[h]), jf = __half22float2(ih[h]);
+                            rl[h] = __floats2half2_rn(xr[2 * h] - rf.x, xr[2 * h + 1] - rf.y);
+                            il[h] = __floats2half2_rn(xi[2 * h] - jf.x, xi[2 * h + 1] - jf.y);
+                        }
+                        const int off = 16 * (idx >> 2) + kTcP * ((idx >> 1) & 1) + 8 * (idx & 1);
+                        auto put = [&](int plane, const __half2* v) {
+                            uint2 u;
+                            u.x = *reinterpret_cast<const uint32_t*>(&v[0]);
+                            u.y = *reinterpret_cast<const uint32_t*>(&v[1]);
+                            *reinterpret_cast<uint2*>(pl + plane * kPl + off) = u;
+                        };
+                        put(0, rh); put(1, rl); put(2, ih); put(3, il);
+                    } else {
+                        const float4 rh = make_float4(tf32_rn(a.x), tf32_rn(a.z), tf32_rn(b.x), tf32_rn(b.z));
+                        const float4 ih = make_float4(tf32_rn(a.y), tf32_rn(a.w), tf32_rn(b.y), tf32_rn(b.w));
+                        const float4 rl = make_float4(tf32_rn(a.x - rh.x), tf32_rn(a.z - rh.y), tf32_rn(b.x - rh.z), tf32_rn(b.z - rh.w));
+                        const float4 il = make_float4(tf32_rn(a.y - ih.x), tf32_rn(a.w - ih.y), tf32_rn(b.y - ih.z), tf32_rn(b.w - ih.w));
+                        const int off = 16 * (idx >> 2) + kTcP * (idx & 3);
+                        *reinterpret_cast<float4*>(pl + off) = rh;
+                        *reinterpret_cast<float4*>(pl + kPl + off) = rl;
+                        *reinterpret_cast<float4*>(pl + 2 * kPl + off) = ih;
+                        *reinterpret_cast<float4*>(pl + 3 * kPl + off) = il;
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -799,7 +894,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     } else if (warp >= kMmaWarp) {
         // ===== MMA issuers: one warp per (segment, re | im accumulator); every accumulator has exactly one writer =====
         const int me = (warp - kMmaWarp) >> 1, half = (warp - kMmaWarp) & 1;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // instruction descriptor: D = fp32; A/B format tf32 (2) or fp16 (0); N, M
+        const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t idesc_na = idesc | (1u << 13);       // negate A
         const uint32_t b_hi32 = (128u >> 4) | (1u << 14);   // SBO = 128 B (8 rows of 16 B), descriptor version 1
         const uint32_t lo_lbo = ((uint32_t)kTcP >> 4) << 16;
@@ -833,10 +929,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         const int bp = half ? b_im[t] : b_re[t];
                         const uint32_t id = (!half && n_re[t]) ? idesc_na : idesc;
 #pragma unroll
-                        for (int ks = 0; ks < 6; ks++) {
-                            const uint32_t baddr = b0 + bp * kTcPlane + 16 * (ks >> 1) + kTcP * ((2 * ks) & 3);
+                        for (int ks = 0; ks < kKSteps; ks++) {
+                            // tf32: K-step = 8 samples = chunks 2 ks, 2 ks + 1 of the row pair; fp16: K-step = one whole row
+                            const uint32_t baddr = F16 ? b0 + bp * kPl + 16 * ks : b0 + bp * kPl + 16 * (ks >> 1) + kTcP * ((2 * ks) & 3);
                             const uint64_t bd = ((uint64_t)b_hi32 << 32) | (uint64_t)(((baddr >> 4) & 0x3fff) | lo_lbo);
-                            tc_mma_ts(d, tm + (uint32_t)(48 * ap + 8 * ks), bd, id, (t | ks) ? 1u : 0u);
+                            if constexpr (F16) tc_mma_ts_f16(d, tm + (uint32_t)(kACols * ap + 8 * ks), bd, id, (t | ks) ? 1u : 0u);
+                            else tc_mma_ts(d, tm + (uint32_t)(kACols * ap + 8 * ks), bd, id, (t | ks) ? 1u : 0u);
                         }
                     }
                     tc_commit(b_empty + st);
@@ -853,17 +951,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const bool valid = c < nch;
         const uint32_t lane_base = tm + ((uint32_t)((warp & 3) * 32) << 16);
         {
-            // set e puts A planes 2e, 2e+1 of its 128 rows into TMEM columns 96 e .. 96 e + 95
-            const float4* row = reinterpret_cast<const float4*>(coef_tab + (size_t)c * 192 + 96 * e);
+            // set e puts A planes 2e, 2e+1 of its 128 rows into TMEM columns 2 kACols e .. 2 kACols (e + 1) - 1
+            const float4* row = reinterpret_cast<const float4*>(coef_tab + (size_t)c * 192 + 2 * kACols * e);
 #pragma unroll
-            for (int blk = 0; blk < 6; blk++) {
+            for (int blk = 0; blk < 2 * kACols / 16; blk++) {
                 float v[16];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const float4 f = __ldg(row + 4 * blk + i);
                     v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
                 }
-                tmem_st16(lane_base + (uint32_t)(96 * e + 16 * blk), v);
+                tmem_st16(lane_base + (uint32_t)(2 * kACols * e + 16 * blk), v);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -901,7 +999,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         em.pos = (unsigned)((od.base + q_first) & (long long)em.mask);
         em.rel = (int)(q_first - row_lo);
         em.n_rows = valid ? (int)((long long)((t0 + n_seg) / (16 << SH)) - row_lo) : 0;
-        em.scale = scale;
+        em.scale = scale * s_out;
         em.h0 = c_hb_taps[0]; em.h2 = c_hb_taps[1]; em.h4 = c_hb_taps[2];
         // Oscillator at fs/16: output m is rotated by the phase of its newest input sample 16m+15, P + (16m+16) inc.
         // It is re-seeded exactly (sincospi of the 64-bit phase) at ABSOLUTE multiples of 32 outputs and rotated in
@@ -965,14 +1063,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
 }
 
-typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const float*, const NcoDev*, const unsigned long long*,
-                      unsigned long long*, int, OutDesc, float, int);
-static K1TFn k1t_kernel(int ncr, int nhb)
+typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const float*, const unsigned*, const NcoDev*,
+                      const unsigned long long*, unsigned long long*, int, OutDesc, float, int);
+static K1TFn k1t_kernel(int ncr, int nhb, bool f16)
 {
-    static const K1TFn table[3][4] = {{k_mix_tc<0, 0>, k_mix_tc<0, 1>, k_mix_tc<0, 2>, k_mix_tc<0, 3>},
-                                      {k_mix_tc<1, 0>, k_mix_tc<1, 1>, k_mix_tc<1, 2>, k_mix_tc<1, 3>},
-                                      {k_mix_tc<2, 0>, k_mix_tc<2, 1>, k_mix_tc<2, 2>, k_mix_tc<2, 3>}};
-    return table[ncr][nhb];
+    static const K1TFn t32[3][4] = {{k_mix_tc<0, 0, false>, k_mix_tc<0, 1, false>, k_mix_tc<0, 2, false>, k_mix_tc<0, 3, false>},
+                                    {k_mix_tc<1, 0, false>, k_mix_tc<1, 1, false>, k_mix_tc<1, 2, false>, k_mix_tc<1, 3, false>},
+                                    {k_mix_tc<2, 0, false>, k_mix_tc<2, 1, false>, k_mix_tc<2, 2, false>, k_mix_tc<2, 3, false>}};
+    static const K1TFn t16[3][4] = {{k_mix_tc<0, 0, true>, k_mix_tc<0, 1, true>, k_mix_tc<0, 2, true>, k_mix_tc<0, 3, true>},
+                                    {k_mix_tc<1, 0, true>, k_mix_tc<1, 1, true>, k_mix_tc<1, 2, true>, k_mix_tc<1, 3, true>},
+                                    {k_mix_tc<2, 0, true>, k_mix_tc<2, 1, true>, k_mix_tc<2, 2, true>, k_mix_tc<2, 3, true>}};
+    return f16 ? t16[ncr][nhb] : t32[ncr][nhb];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1253,6 +1354,7 @@ Decimator::~Decimator()
     for (auto& p : ev_pool_) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaFree(d_nco_);
     cudaFree(d_tc_coef_);
+    cudaFree(d_absmax_);
     cudaFree(d_phase_[0]);
     cudaFree(d_phase_[1]);
     for (float2* p : d_stage_) cudaFree(p);
@@ -1389,8 +1491,14 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
         CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         tc_groups_ = (stride_ + 127) / 128;
         CSDR_CK(cudaMalloc(&d_tc_coef_, (size_t)tc_groups_ * 128 * 192 * sizeof(float)));
-        K1TFn tf = k1t_kernel(ncic_ - 4, nhbf_);
+        // CUTESDR_TC_F16=1: fp16 hi/lo operands instead of tf32 (twice the tensor rate, same accuracy, scale-free through the
+        // block maximum). Opt-in: inside the step the kernel is not tensor-bound, so the halved MMA time does not pay for the
+        // extra k_absmax pass yet (alone 106 vs 120 us, tensor pipe 35 % vs 66 % active, issue slots 75 % either way; 0.336 vs 0.312 ms per step).
+        tc_f16_ = getenv("CUTESDR_TC_F16") != nullptr;
+        K1TFn tf = k1t_kernel(ncic_ - 4, nhbf_, tc_f16_);
         CSDR_CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+        CSDR_CK(cudaMalloc(&d_absmax_, sizeof(unsigned)));
+        CSDR_CK(cudaMemsetAsync(d_absmax_, 0, sizeof(unsigned), st_));
         // one persistent CTA per SM, kTcSegs interleaved time segments per CTA; every segment pays PRE priming
         // outputs and rounds up to whole MMA tiles
         const int pre = tc_pre(ncic_ - 4, nhbf_);
@@ -1486,14 +1594,21 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
     if (tc_ && L % 256 == 0) {
         if (tc_dirty_) {
             const int n = tc_groups_ * 128 * 48;
-            k_tc_coeffs<<<(n + 255) / 256, 256, 0, st_>>>(d_nco_, stride_, tc_groups_, d_tc_coef_);
+            if (tc_f16_) k_tc_coeffs_f16<<<(n / 2 + 255) / 256, 256, 0, st_>>>(d_nco_, stride_, tc_groups_, reinterpret_cast<uint32_t*>(d_tc_coef_));
+            else k_tc_coeffs<<<(n + 255) / 256, 256, 0, st_>>>(d_nco_, stride_, tc_groups_, d_tc_coef_);
             lc_->n++;
             CSDR_CK(cudaGetLastError());
             tc_dirty_ = false;
         }
+        if (tc_f16_) {
+            CSDR_CK(cudaMemsetAsync(d_absmax_, 0, sizeof(unsigned), st_));
+            k_absmax<<<296, 256, 0, st_>>>(d_x, fmt, halo_cur, L, d_absmax_);
+            lc_->n++;
+            CSDR_CK(cudaGetLastError());
+        }
         const int sl = std::min(tc_seg_len_, L);
         dim3 grid(((L + sl - 1) / sl + kTcSegs - 1) / kTcSegs, tc_groups_);
-        k1t_kernel(ncic_ - 4, nhbf_)<<<grid, kTcThreads, kTcSmem, st_>>>(d_x, fmt, halo_cur, halo_next, L, sl, d_tc_coef_, d_nco_, pc, pn,
+        k1t_kernel(ncic_ - 4, nhbf_, tc_f16_)<<<grid, kTcThreads, kTcSmem, st_>>>(d_x, fmt, halo_cur, halo_next, L, sl, d_tc_coef_, d_absmax_, d_nco_, pc, pn,
                                                                           stride_, od, scale, getenv("CUTESDR_TC_DBG") ? atoi(getenv("CUTESDR_TC_DBG")) : 0);
     } else if (L % Q == 0) {
         const int threads = std::min(256, round_up(stride_, 32));

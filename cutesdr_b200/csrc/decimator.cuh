@@ -85,9 +85,10 @@ private:
     std::vector<NcoDev> h_nco_;
     bool dirty_ = true;
     // kernel 1T (tensor-core form of kernel 1, used when the ladder starts with >= 4 CIC3 stages)
-    bool tc_ = false, tc_dirty_ = true;
+    bool tc_ = false, tc_dirty_ = true, tc_f16_ = false;
     int tc_seg_len_ = 0, tc_groups_ = 0;
     float* d_tc_coef_ = nullptr;
+    unsigned* d_absmax_ = nullptr;     // max |sample| of [halo | block] as float bits (input scale of the fp16 form)
     NcoDev* d_nco_ = nullptr;
     unsigned long long* d_phase_[2] = {nullptr, nullptr};
     int phase_cur_ = 0;

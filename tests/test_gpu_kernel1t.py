@@ -182,3 +182,31 @@ def test_fused_tail_halfbands_are_bit_identical():
     assert outs[0][1].max() > 0
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
     assert outs[1][2] < outs[0][2]            # fewer launches: the fused pass really ran
+
+
+def test_kernel1t_fp16_operand_form(orc):
+    """CUTESDR_TC_F16=1: fp16 hi/lo operands (kind::f16) with the block-maximum input scale. Same accuracy bar as the
+    tf32 form, exact under a power-of-two change of the input scale, and independent of the segmentation."""
+    rate, bw, freq = 100147200.0, 5000.0, -12.5e6
+    a = orc.DownConvert()
+    a.SetDataRate(rate, bw)
+    a.SetFrequency(freq)
+    n = _block_len(rate, len(a.stages()))
+    blocks = [_signal(rate, n, k, freq) for k in range(2)]
+    ya = np.concatenate([a.ProcessData(x) for x in blocks])
+
+    def run(scale, seg=None):
+        with _env(CUTESDR_TC_F16="1", CUTESDR_TC_SEG=seg):
+            b = cs.CDownConvert()
+            b.SetDataRate(rate, bw)
+            b.SetFrequency(freq)
+            return np.concatenate([b.ProcessData(x * scale) for x in blocks])
+
+    y1 = run(1.0)
+    assert snr_db(ya, y1) > 100.0
+    # scale-free: 2^-20 x input -> exactly 2^-20 x output (fp16 alone would underflow at this level)
+    y2 = run(2.0 ** -20)
+    assert np.array_equal(y2, y1 * 2.0 ** -20)
+    y3 = run(2.0 ** 12)          # beyond the fp16 range without the scale
+    assert np.array_equal(y3, y1 * 2.0 ** 12)
+    assert np.array_equal(run(1.0, seg=8192), y1)

@@ -225,6 +225,108 @@ __global__ void __launch_bounds__(128, 1) k_probe2(const float* __restrict__ A, 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256));
 }
 
+// ---- probe 3: kind::f16 (fp16 hi/lo split), A in TMEM as packed half pairs (column j = elements 2j, 2j+1), B natural order
+// with 8-sample chunks: chunk (m, q) at 16 m + P q, q in {0,1}; one X row (16 samples) per K=16 MMA, row shift = 16 B ----
+#include <cuda_fp16.h>
+constexpr int N3 = 32, ROWS3 = N3 + 2, P3 = ROWS3 * 16;
+__global__ void __launch_bounds__(128, 1) k_probe3(const float* __restrict__ A, const float* __restrict__ X, float* __restrict__ D)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* b_hi = smem;                 // 2 q-subplanes of P3 bytes
+    unsigned char* b_lo = smem + 2 * P3;
+    __shared__ uint32_t tmem_base;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 16 * ROWS3; i += 128) {
+        const float v = X[i];
+        const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+        const int m = i >> 4, q = (i >> 3) & 1, e = i & 7;
+        const int off = 16 * m + P3 * q + 2 * e;
+        *reinterpret_cast<__half*>(b_hi + off) = hi;
+        *reinterpret_cast<__half*>(b_lo + off) = lo;
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = tmem_base;
+    {
+        // A row -> columns 0..23 (hi pairs) and 24..47 (lo pairs): 48 columns = 3 x16 stores
+        const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16);
+        uint32_t packed[48];
+        for (int j = 0; j < 24; j++) {
+            const float v0 = A[tid * K + 2 * j], v1 = A[tid * K + 2 * j + 1];
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+            packed[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            packed[24 + j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        for (int blk = 0; blk < 3; blk++) {
+            const uint32_t* r = packed + 16 * blk;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+                             lane_base + (uint32_t)(16 * blk)),
+                         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                         : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        // c_format F32 (1 << 4), a_format = b_format = F16 (0)
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N3 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        uint32_t acc = 0;
+        for (int term = 0; term < 3; term++) {
+            const uint32_t a_col = term == 0 ? 24 : 0;                       // lo*hi, hi*lo, hi*hi
+            const unsigned char* bp = term == 1 ? b_lo : b_hi;
+            for (int s = 0; s < K / 16; s++) {
+                const uint64_t bd = make_desc(smem_u32(bp) + 16 * s, P3, 128);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tm + 128),
+                    "r"(tm + a_col + 8 * s), "l"(bd), "r"(idesc), "r"(acc)
+                    : "memory");
+                acc = 1;
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(smem_u32(&bar)), "r"(0)
+                : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t lane_base = tm + ((uint32_t)(warp * 32) << 16) + 128;
+    for (int half = 0; half < 2; half++) {
+        uint32_t r[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                       "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(lane_base + 16 * half));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 16; j++) D[(size_t)tid * N3 + 16 * half + j] = __uint_as_float(r[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256));
+}
+
 int main()
 {
     std::vector<float> A(M * K), Xs(8 * 288), D(M * N);
@@ -289,6 +391,30 @@ int main()
             printf("probe2 (A in TMEM, natural-order B, N=32, x16 ld) neg=%d: SNR %.1f dB\n", neg, snr);
             if (!(snr > 110.0)) bad++;
         }
+    }
+    {
+        std::vector<float> X(16 * ROWS3), D3(M * N3);
+        for (auto& v : X) v = ((float)rand() / RAND_MAX * 2.f - 1.f) * 1000.f;
+        float *dX3, *dD3;
+        CK(cudaMalloc(&dX3, X.size() * 4));
+        CK(cudaMalloc(&dD3, D3.size() * 4));
+        CK(cudaMemcpy(dX3, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+        k_probe3<<<1, 128, 4 * P3>>>(dA, dX3, dD3);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(D3.data(), dD3, D3.size() * 4, cudaMemcpyDeviceToHost));
+        double err2 = 0, ref2 = 0;
+        for (int m = 0; m < M; m++)
+            for (int n = 0; n < N3; n++) {
+                double acc = 0;
+                for (int k = 0; k < K; k++) acc += (double)A[m * K + k] * (double)X[16 * n + k];
+                const double e = (double)D3[m * N3 + n] - acc;
+                err2 += e * e;
+                ref2 += acc * acc;
+            }
+        const double snr = 10 * log10(ref2 / (err2 + 1e-300));
+        printf("probe3 (kind::f16 hi/lo, A packed in TMEM, 8-sample chunks, N=32): SNR %.1f dB\n", snr);
+        if (!(snr > 110.0)) bad++;
     }
     printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
     return bad;
