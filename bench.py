@@ -373,7 +373,9 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "in_rate_sps": in_rate, "channels_per_gpu": nch, "block_length": L,
                            "l2": "cycles %d distinct %d-sample blocks (%.0f MB > 126 MB L2)" % (nblk, L, nblk * L * 8 / 1e6),
-                           "realtime_factor": value / (in_rate * nch * world / 1e6)},
+                           "realtime_factor": value / (in_rate * nch * world / 1e6),
+                           "arithmetic": "float32 chain; kernel 1 on tensor cores = every fp32 product as 3 tf32 MMAs, fp32 accumulation"
+                                         if (roof and roof.get("bound") == "tensor") else "float32 chain (CUDA cores)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Msps*ch", "h2d_bytes_per_step": 8 * L, "d2h_bytes_per_step": d2h // e2e_steps,
                         "steps": e2e_steps},
