@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the receive-chain bank: input Msps x channels per B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg5|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg5|cfg5full|cfg3]
 
 One STEP = one DSP block (block_length wideband samples, ~10 ms of signal) pushed through the whole
 chain -- NCO mix + CIC/half-band cascade, overlap-save FIR, S-meter, AGC, demodulator (+ resampler)
@@ -41,6 +41,8 @@ WORKLOADS = {
              "cfg4: 1024-ch NBFM (+LP biquad, CFractResampler->48 kHz) on 100.1472 Msps, 1024 ch per GPU"),
     "cfg5": (200294400.0, 1024, lambda c: (M.DEMOD_AM, M.DEMOD_SAM, M.DEMOD_FM, M.DEMOD_USB)[c % 4], 39000.0, 0.0,
              "cfg5 slice: 1024-ch mixed AM/SAM/FM/USB with AGC on 200.2944 Msps, 1024 ch per GPU"),
+    "cfg5full": (200294400.0, 4096, lambda c: (M.DEMOD_AM, M.DEMOD_SAM, M.DEMOD_FM, M.DEMOD_USB)[c % 4], 39000.0, 0.0,
+                 "cfg5 at full width: 4096-ch mixed AM/SAM/FM/USB with AGC on 200.2944 Msps, 4096 ch per GPU"),
     "cfg3": (20000000.0, 256, lambda c: M.DEMOD_USB if c % 2 == 0 else M.DEMOD_LSB, 62500.0, 0.0,
              "cfg3: 256-ch USB/LSB SSB bank on 20 Msps, 256 ch per GPU"),
 }
