@@ -1,29 +1,36 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the receive-chain bank: input Msps x channels per B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg5|cfg5full|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg4|cfg5|cfg5q|cfg3|cfg1|cfg2] [--ingest cf32|cs16] [--scaling weak|strong]
 
-One STEP = one DSP block (block_length wideband samples, ~10 ms of signal) pushed through the whole
-chain -- NCO mix + CIC/half-band cascade, overlap-save FIR, S-meter, AGC, demodulator (+ resampler)
--- for every channel of the rank's bank. Default workload: BASELINE config 4, 1024-channel NBFM +
-CFractResampler to 48 kHz on the "100 Msps" stream (100 147 200 sps), 1024 channels PER
-GPU (weak scaling: every GPU sees the same wideband stream and owns its own 1024-channel slice).
+One STEP = 0.2 s of the wideband stream = 20 DSP blocks (every config is defined on 0.2 s of signal; one
+DSP block is m_InBufLimit samples, ~10 ms) pushed through the whole chain -- NCO mix + CIC/half-band cascade,
+overlap-save FIR, S-meter, AGC, demodulator (+ resampler; + noise blanker and the concurrent 65536-point spectrum at
+10 frames/s for config 5) -- for every channel of the rank's bank. Default workload: BASELINE config 4, 1024-channel
+NBFM + CFractResampler to 48 kHz on the "100 Msps" stream (100 147 200 sps), 1024 channels PER GPU (weak
+scaling: every GPU sees the same wideband stream and owns its own channel slice; --scaling strong splits the
+config's channel count over the GPUs instead).
 
-  value   : device-timed, wideband blocks already resident in HBM (cycled through more distinct
-            blocks than fit in L2).
-  e2e     : the same through cutesdr_bank_process with HOST buffers: H2D of the block (rank 0, then an
-            NCCL broadcast when N > 1) and D2H of every channel's audio inside the timed region.
-  roofline: kernel 1. On the tensor-core path (k_mix_tc) bound = "tensor": the GEMM's algorithmic flops per launch /
-            its CUDA-event time vs the measured tf32 peak (bf16 sustained / 2); the SURVEY 8(d) HBM streaming-model
-            figure (8 B x samples x channels) rides along as roofline.hbm_model. CUDA-core path: bound = "hbm" (model).
-  cpu_baseline / --impl reference : the UNMODIFIED reference dsp/*.cpp (oracle/_ref) on all host cores,
-            one CDemodulator (+CFractResampler) per channel, on a bounded sample of the same workload.
+  value   : device-timed (CUDA events on the bank's stream), the stream's 20 distinct blocks resident in HBM (160 MB
+            of complex64, more than the 126 MB L2) and cycled.
+  e2e     : the same through the C ABI with HOST buffers: cutesdr_bank_process_async[_raw] (N = 1) or
+            cutesdr_bank_process_async_bcast (N > 1: rank 0's H2D in chunks + NCCL broadcast inside the library); the
+            H2D of every block and the D2H of every channel's audio are inside the timed region.
+  roofline: kernel 1, timed with CUDA events around every launch on the bank's stream. Tensor-core path (k_mix_tc):
+            bound "tensor", algorithmic GEMM flops / launch time vs MEASURED_PEAKS.json's dense bf16 figure (burst when the
+            SM clock stayed at its maximum through the timed region, else sustained), halved for kind::tf32; the
+            tcgen05 / FP32-FMA peaks measured live by cutesdr_microbench ride along. CUDA-core path (k_mix_cic): bound
+            "fp32": algorithmic FP32 ops / launch time vs the measured FMA issue peak. The SURVEY 8(d)
+            per-channel streaming model (8 B per sample*channel vs HBM) is reported as hbm_model, never as the bound.
+  cpu_baseline / --impl reference : the UNMODIFIED reference dsp/*.cpp (oracle/_ref) on all host cores, persistent
+            CDemodulator (+CFractResampler) objects built OUTSIDE the timed region, one step = the same 0.2 s of the same
+            stream over a bounded channel sample.
 """
 import argparse
 import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -35,177 +42,316 @@ sys.path.insert(0, ROOT)
 
 from cutesdr_b200 import modes as M  # noqa: E402
 
+BLOCKS_PER_STEP = 20
+
+
+def _mixed(c):
+    return (M.DEMOD_AM, M.DEMOD_SAM, M.DEMOD_FM, M.DEMOD_USB)[c % 4]
+
+
 WORKLOADS = {
-    # name: (in_rate, channels per GPU, mode picker, carrier spacing, audio_rate, description)
-    "cfg4": (100147200.0, 1024, lambda c: M.DEMOD_FM, 78125.0, 48000.0,
-             "cfg4: 1024-ch NBFM (+LP biquad, CFractResampler->48 kHz) on 100.1472 Msps, 1024 ch per GPU"),
-    "cfg5": (200294400.0, 1024, lambda c: (M.DEMOD_AM, M.DEMOD_SAM, M.DEMOD_FM, M.DEMOD_USB)[c % 4], 39000.0, 0.0,
-             "cfg5 slice: 1024-ch mixed AM/SAM/FM/USB with AGC on 200.2944 Msps, 1024 ch per GPU"),
-    "cfg5full": (200294400.0, 4096, lambda c: (M.DEMOD_AM, M.DEMOD_SAM, M.DEMOD_FM, M.DEMOD_USB)[c % 4], 39000.0, 0.0,
-                 "cfg5 at full width: 4096-ch mixed AM/SAM/FM/USB with AGC on 200.2944 Msps, 4096 ch per GPU"),
-    "cfg3": (20000000.0, 256, lambda c: M.DEMOD_USB if c % 2 == 0 else M.DEMOD_LSB, 62500.0, 0.0,
-             "cfg3: 256-ch USB/LSB SSB bank on 20 Msps, 256 ch per GPU"),
+    "cfg4": dict(in_rate=100147200.0, nch=1024, pick=lambda c: M.DEMOD_FM, spacing=78125.0, audio_rate=48000.0, decim=2048,
+                 desc="cfg4: 1024-ch NBFM (+LP biquad, CFractResampler->48 kHz) on 100.1472 Msps"),
+    "cfg5": dict(in_rate=200294400.0, nch=4096, pick=_mixed, spacing=39000.0, audio_rate=0.0, decim=8192, blanker=True,
+                 spectrum=True, impulses=20,
+                 desc="cfg5: 4096-ch mixed AM/SAM/FM/USB with AGC (hang on every 8th), noise blanker (50, 50 us) and a concurrent "
+                      "65536-pt spectrum (ave 4, 10 frames/s) on 200.2944 Msps"),
+    "cfg5q": dict(in_rate=200294400.0, nch=1024, pick=_mixed, spacing=39000.0, audio_rate=0.0, decim=8192, blanker=True,
+                  spectrum=True, impulses=20,
+                  desc="cfg5 quarter: 1024-ch mixed AM/SAM/FM/USB with AGC, noise blanker and concurrent 65536-pt spectrum on 200.2944 Msps"),
+    "cfg3": dict(in_rate=20000000.0, nch=256, pick=lambda c: M.DEMOD_USB if c % 2 == 0 else M.DEMOD_LSB, spacing=62500.0,
+                 audio_rate=0.0, decim=512, desc="cfg3: 256-ch USB/LSB SSB bank (CDownConvert + CFastFIR + CSsbDemod + CAgc) on 20 Msps"),
+    "cfg1": dict(in_rate=2000000.0, nch=1, pick=lambda c: M.DEMOD_AM, spacing=0.0, audio_rate=48000.0, decim=64, carrier0=250000.0,
+                 desc="cfg1: single-channel AM (10 kHz BW, 48 kHz audio) on 2.0 Msps"),
 }
 
 
-def channel_plan(name, rank, world):
-    in_rate, nch, pick, spacing, audio_rate, desc = WORKLOADS[name]
-    total = nch * world
-    modes = [pick(c) for c in range(rank * nch, (rank + 1) * nch)]
-    carriers = (np.arange(rank * nch, (rank + 1) * nch) - total / 2 + 0.5) * spacing
-    infos = []
-    for m in modes:
-        if m == M.DEMOD_USB:
-            infos.append(M.demod_info(m, HiCut=2800, LowCut=100))
-        elif m == M.DEMOD_LSB:
-            infos.append(M.demod_info(m, HiCut=-100, LowCut=-2800))
-        else:
-            infos.append(M.demod_info(m))
-    return in_rate, nch, modes, carriers, infos, audio_rate, desc
+def demod_info_for(m, c):
+    if m == M.DEMOD_USB:
+        return M.demod_info(m, HiCut=2800, LowCut=100, AgcHangOn=(c % 8 == 3))
+    if m == M.DEMOD_LSB:
+        return M.demod_info(m, HiCut=-100, LowCut=-2800)
+    return M.demod_info(m, AgcHangOn=(c % 8 == 0))
 
 
-def synth_blocks(L, nblocks, seed):
-    """Cheap synthetic wideband stream: Gaussian noise floor + 64 AM/FM carriers, int16 full scale."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    n = L * nblocks
-    x = (300.0 * (rng.standard_normal(n, dtype=np.float32) + 1j * rng.standard_normal(n, dtype=np.float32))).astype(np.complex64)
-    t = np.arange(n, dtype=np.float64)
-    for k in range(8):
-        f = (k - 3.5) * 0.031
-        x += (1500.0 * (1.0 + 0.5 * np.cos(2 * np.pi * 2e-5 * (k + 1) * t)) * np.exp(2j * np.pi * f * t)).astype(np.complex64)
-    return x.reshape(nblocks, L)
+def channel_plan(name, rank, world, scaling):
+    """Global channel list of the job and this rank's slice of it."""
+    from cutesdr_b200.dsp import channel_slice
+    w = WORKLOADS[name]
+    total = w["nch"] * (world if scaling == "weak" else 1)
+    first, count = channel_slice(total, rank, world)
+    modes = [w["pick"](c) for c in range(total)]
+    spacing = w["spacing"]
+    if total > 1 and spacing * total > 0.95 * w["in_rate"]:
+        spacing = 0.95 * w["in_rate"] / total          # weak scaling at N > 1: keep every carrier inside the stream's band
+    carriers = (np.arange(total) - total / 2 + 0.5) * spacing if total > 1 else np.array([w.get("carrier0", 0.0)])
+    infos = [demod_info_for(m, c) for c, m in enumerate(modes)]
+    return w, total, first, count, modes, carriers, infos
 
 
+def block_length(in_rate):
+    return int(in_rate / 100) & ~0xFF          # m_InBufLimit, dsp/demodulator.cpp:145-146
+
+
+def make_stream(w, modes, carriers, ingest):
+    """The job's 0.2 s of SYN-IQ: every channel's carrier is present. cf32: A = 16000/sqrt(Nch); cs16: a
+    quarter of that, so the sum of a thousand carriers stays inside int16."""
+    from cutesdr_b200.synth import syn_iq_fft
+    L = block_length(w["in_rate"])
+    n = BLOCKS_PER_STEP * L
+    amp = 16000.0 if ingest == "cf32" else 4000.0
+    iq, snapped = syn_iq_fft(w["in_rate"], n, modes, carriers, seed=20260 + len(modes), decim=w["decim"], total_amp=amp,
+                             impulses=w.get("impulses", 0))
+    return iq, snapped, L
+
+
+def common_config(name, w, world, scaling, ingest, L, total):
+    """`config` of the JSON line: identical keys and values in both arms."""
+    return {"workload": w["desc"], "in_rate_sps": w["in_rate"], "channels_total": total,
+            "channels_per_gpu": total // world, "block_length": L, "blocks_per_step": BLOCKS_PER_STEP,
+            "samples_per_step": BLOCKS_PER_STEP * L, "ingest": ingest,
+            "l2": "cycles %d distinct %d-sample blocks (%.0f MB > 126 MB L2)" % (BLOCKS_PER_STEP, L, BLOCKS_PER_STEP * L * (8 if ingest == "cf32" else 4) / 1e6),
+            "parallelism": "channels sharded over %d GPU(s), wideband block broadcast from rank 0" % world if world > 1 else "1 GPU"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / power / throttle reasons sampled through NVML every ~2 ms DURING the timed region (nvidia-smi's
+    100 ms loop cannot see a sub-second region); one more sample is taken right at stop so the record is never empty."""
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
         self.idx = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.thr = None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = None
+            try:        # CUDA_VISIBLE_DEVICES may renumber the devices: find the NVML handle by UUID
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+            self.rows.append((sm, reasons, pw))
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self.stop_flag:
+            self._sample()
+            time.sleep(0.002)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
-            self.thr.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([v.strip() for v in line.split(",")])
+        if self.nv is None:
+            return
+        self.thr = threading.Thread(target=self._loop, daemon=True)
+        self.thr.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.stop_flag = True
+        if self.thr:
+            self.thr.join(timeout=1.0)
+        self._sample()
+        nv = self.nv
         try:
-            self.proc.wait(timeout=2)
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+            mx = None
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "hw_power_brake_slowdown": 0x80}
+        seen = 0
+        for r in self.rows:
+            seen |= int(r[1])
+        reasons = [k for k, b in bits.items() if seen & b]
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                "sm_max_mhz": float(mx) if mx else None, "power_w_max": max((r[2] for r in self.rows), default=None),
+                "reasons": reasons, "samples": len(sm), "how": "NVML, 2 ms period, inside the timed region"}
 
 
-def measured_hbm_peak():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return json.load(open(p))
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def measured_tf32_peak():
-    """Dense tf32 tensor peak in TFLOP/s: half the bf16 figure (tcgen05 kind::tf32 runs at half the kind::f16 rate,
-    B200_PROFILING.md). Kernel 1T is timed inside a long step, so the SUSTAINED bf16 number is the one halved."""
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        try:
-            d = json.load(open(p))
-            return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / 2.0, "measured bf16 sustained / 2 (MEASURED_PEAKS.json)"
-        except Exception:
-            pass
-    return 2250.0 / 2.0, "fallback: nominal 2.25 PFLOP/s bf16 / 2 (B200_PROFILING.md)"
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(workload, steps, warmup, ch_per_core=4):
-    """The reference's own CPU implementation on all host cores: one CDemodulator (+resampler) per
-    channel, channels spread over std::threads; each step = one DSP block over a bounded channel count."""
-    from oracle import ref_binding as rb
-    in_rate, nch, modes, carriers, infos, audio_rate, desc = channel_plan(workload, 0, 1)
-    big = in_rate > 30e6
-    if not rb.ref_available(big=big):
-        return None
-    cores = os.cpu_count() or 1
-    n_cpu_ch = min(nch, cores * ch_per_cpu_core(ch_per_core))
-    sel = np.linspace(0, nch - 1, n_cpu_ch).astype(int)
-    L = (int(in_rate / 100) & ~0xFF)
-    blocks = synth_blocks(L, 1, seed=7)
-    infos_by_mode = {}
-    for c in sel:
-        infos_by_mode[modes[c]] = infos[c]
-    times = []
+class CpuReference:
+    """The reference's own CPU implementation (oracle/_ref = the unmodified dsp/*.cpp) on all host cores: persistent
+    CDemodulator (+CFractResampler) objects, channels spread over std::threads, every step = the same 0.2 s stream."""
+
+    def __init__(self, name, ch_per_core=1):
+        from oracle import ref_binding as rb
+        self.rb = rb
+        w, total, first, count, modes, carriers, infos = channel_plan(name, 0, 1, "weak")
+        self.w, self.total = w, total
+        self.big = w["in_rate"] > 30e6
+        if not rb.ref_available(big=self.big):
+            raise RuntimeError("oracle/_ref not built")
+        self.cores = os.cpu_count() or 1
+        self.iq, snapped, self.L = make_stream(w, modes, carriers, "cf32")
+        n_cpu = min(total, self.cores * int(os.environ.get("CUTESDR_BENCH_CPU_CH_PER_CORE", ch_per_core)))
+        self.sel = [int(v) for v in np.linspace(0, total - 1, n_cpu).astype(int)]
+        t0 = time.perf_counter()
+        self.chains = rb.RefChainSet([modes[c] for c in self.sel], [-snapped[c] for c in self.sel], [infos[c] for c in self.sel],
+                                     w["in_rate"], audio_rate=w["audio_rate"], keep_output=False, big=self.big)
+        self.nb = self.fft = None
+        if w.get("blanker"):
+            self.nb = rb.RefNoiseProc(big=self.big)
+            self.nb.SetupBlanker(True, 50.0, 50.0, w["in_rate"])
+        if w.get("spectrum"):
+            self.fft = rb.RefFft(big=self.big)
+            self.fft.SetFFTParams(65536, False, 0.0, w["in_rate"])
+            self.fft.SetFFTAve(4)
+        self.setup_s = time.perf_counter() - t0
+
+    def step(self):
+        """one step; returns (seconds the whole job would take on these cores, raw seconds measured)"""
+        iq = self.iq
+        shared = 0.0
+        if self.nb is not None:
+            iq = self.iq.copy()
+            shared += self.rb.blank_stream_f32(self.nb, iq)
+        if self.fft is not None:
+            t0 = time.perf_counter()
+            for k in (0, BLOCKS_PER_STEP // 2):            # 10 frames/s
+                self.fft.PutInDisplayFFT(iq[k * self.L + 100000:k * self.L + 100000 + 65536].astype(np.complex128))
+                self.fft.GetScreenIntegerFFTData(255, 1024, 0.0, -140.0, int(-self.w["in_rate"] / 2), int(self.w["in_rate"] / 2))
+            shared += time.perf_counter() - t0
+        t = self.chains.run(iq, self.cores)
+        # the per-stream work (blanker, spectrum) is paid once per stream, the chains scale with the channel count
+        return shared + t * (self.total / len(self.sel)), shared + t
+
+    def describe(self, steps):
+        return ("%d of %d channels x %d samples (0.2 s of stream, %d blocks) per step, %d steps, %d threads; objects and "
+                "CFractResampler::Init built outside the timed region (%.2f s); channel time scaled to the full bank%s"
+                % (len(self.sel), self.total, len(self.iq), BLOCKS_PER_STEP, steps, self.cores, self.setup_s,
+                   ", blanker + spectrum counted once per stream" if self.nb is not None else ""))
+
+
+def cpu_reference_run(name, steps, warmup):
+    ref = CpuReference(name)
+    full, raw = [], []
     for it in range(warmup + steps):
-        # state is rebuilt per call (object construction is inside the timed call but negligible vs 1e6 samples)
-        t, _ = rb.bench_chains([modes[c] for c in sel], [-carriers[c] for c in sel], infos_by_mode, in_rate, blocks[0], cores,
-                               resample48k=audio_rate > 0, big=big)
+        f, r = ref.step()
         if it >= warmup:
-            times.append(t)
-    sec = float(np.sum(times))
-    value = (L * n_cpu_ch * steps) / sec / 1e6
-    return {"value": value, "cores": cores, "kind": "reference", "ms_per_step": 1e3 * sec / steps,
-            "sample": "%d of %d channels x %d-sample block per step, %d steps, %d threads" % (n_cpu_ch, nch, L, steps, cores)}
-
-
-def ch_per_cpu_core(default):
-    return int(os.environ.get("CUTESDR_BENCH_CPU_CH_PER_CORE", default))
+            full.append(f)
+            raw.append(r)
+    sec = float(np.sum(full))
+    value = (len(ref.iq) * ref.total * steps) / sec / 1e6
+    return ref, {"value": value, "cores": ref.cores, "kind": "reference", "ms_per_step": 1e3 * sec / steps,
+                 "measured_s_per_step": float(np.mean(raw)), "sample": ref.describe(steps)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 20))
-    warm = min(args.warmup, 2)
-    r = cpu_reference_run(args.workload, steps, warm)
-    in_rate, nch, modes, carriers, infos, audio_rate, desc = channel_plan(args.workload, 0, 1)
-    if r is None:
-        # oracle/_ref did not travel: fall back to the C restatement on one core
-        from oracle import oracle_binding as ob
-        L = (int(in_rate / 100) & ~0xFF)
-        blocks = synth_blocks(L, 1, seed=7)
-        d = ob.Demodulator()
-        d.SetInputSampleRate(in_rate)
-        d.SetDemod(modes[0], infos[0])
-        d.SetDemodFreq(-carriers[0])
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            d.run(blocks[0])
-        sec = time.perf_counter() - t0
-        r = {"value": L * steps / sec / 1e6, "cores": 1, "kind": "port", "ms_per_step": 1e3 * sec / steps,
-             "sample": "1 channel x %d-sample block per step, %d steps, 1 thread (oracle port)" % (L, steps)}
+    steps = max(1, args.steps)
+    warm = max(1, min(args.warmup, 3))
+    # bounded: the whole run stays within a few minutes whatever K the driver asks for
+    budget_steps = int(os.environ.get("CUTESDR_BENCH_REF_MAX_STEPS", "24"))
+    steps_run = min(steps, budget_steps)
+    ref, r = cpu_reference_run(args.workload, steps_run, warm)
+    w = ref.w
+    cfg = common_config(args.workload, w, args.gpus, args.scaling, args.ingest, ref.L, ref.total * (args.gpus if args.scaling == "weak" else 1))
     line = {"impl": "reference", "metric": "input_msps_x_channels", "value": r["value"], "unit": "Msps*ch", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "note": "reference CPU chain (dsp/*.cpp compiled headless), all host cores"},
+            "steps": steps_run, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": r["value"], "unit": "Msps*ch", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "Msps*ch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "note": "reference CPU chain (unmodified dsp/*.cpp compiled headless, oracle/_ref), all host cores; value = samples x "
+                    "channels of the full bank / time the full bank would take at the measured per-channel rate"}
+    emit(line)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# display FFT (config 2)
+# ------------------------------------------------------------------------------------------------
+def run_cfg2(args):
+    """4096-point display FFT with window, averaging and integer screen mapping on 2.0 Msps IQ: one step = 256 frames
+    through CFft::PutInDisplayFFT + GetScreenIntegerFFTData(255, 800, ...), each frame from a host buffer."""
+    import cutesdr_b200 as cs
+    from cutesdr_b200.synth import carrier_grid, syn_iq
+    fs, N, frames = 2e6, 4096, 256
+    modes = [M.DEMOD_AM] * 16
+    iq = syn_iq(fs, N * frames, modes, carrier_grid(16, 100e3), seed=20262)
+    cfg = {"workload": "cfg2: 4096-point display FFT with window, averaging (4) and integer screen mapping on 2.0 Msps IQ",
+           "in_rate_sps": fs, "fft_size": N, "frames_per_step": frames, "samples_per_step": N * frames, "ingest": "cf32",
+           "l2": "n/a (one 32 KB frame per call, host buffers)", "parallelism": "1 GPU"}
+    if args.impl == "reference":
+        from oracle import ref_binding as rb
+        f = rb.RefFft()
+        f.SetFFTParams(N, False, 0.0, fs)
+        f.SetFFTAve(4)
+        x = iq.astype(np.complex128)
+
+        def step():
+            for k in range(frames):
+                f.PutInDisplayFFT(x[k * N:(k + 1) * N])
+                f.GetScreenIntegerFFTData(255, 800, 0.0, -140.0, -1000000, 1000000)
+        launches = 0
+    else:
+        f = cs.CFft()
+        f.SetFFTParams(N, False, 0.0, fs)
+        f.SetFFTAve(4)
+        x = iq.astype(np.complex128)
+
+        def step():
+            for k in range(frames):
+                f.PutInDisplayFFT(x[k * N:(k + 1) * N])
+                f.GetScreenIntegerFFTData(255, 800, 0.0, -140.0, -1000000, 1000000)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    sec = time.perf_counter() - t0
+    value = N * frames * args.steps / sec / 1e6
+    line = {"metric": "input_msps_x_channels", "value": value, "unit": "Msps*ch", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.impl == "ours" else "f64", "data": "synthetic", "config": cfg,
+            "e2e": {"value": value, "unit": "Msps*ch", "h2d_bytes_per_step": 8 * N * frames if args.impl == "ours" else 0,
+                    "d2h_bytes_per_step": 4 * 800 * frames if args.impl == "ours" else 0},
+            "frames_per_s": frames * args.steps / sec, "realtime_factor": value / (fs / 1e6),
+            "note": "host-timed through the C ABI (every frame: H2D 32 KB, one fused kernel, screen kernel, D2H 3.2 KB, two syncs): "
+                    "latency-bound by design, a display refreshes at 10-50 frames/s"}
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": value, "unit": "Msps*ch", "cores": 1, "kind": "reference", "sample": "%d frames per step, 1 thread" % frames}
+        line["gpu_launches"] = 0
+    else:
+        n = C.c_longlong()
+        f.L.cutesdr_fft_launch_count(f.h, C.byref(n))
+        line["gpu_launches"] = int(n.value)
     emit(line)
     return 0
 
@@ -213,10 +359,20 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def fp32_ops_per_sample(lens):
+    """NCO rotate 4 + complex mix 4 + sum over stages of cost / 2^s (CIC3 3, N-tap half-band (N+3)/2)."""
+    ops, div = 8.0, 1.0
+    for n in lens:
+        ops += (3.0 if n == 3 else (n + 3) / 2.0) / div
+        div *= 2.0
+    return ops
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import cutesdr_b200 as cs
+    from cutesdr_b200.sharding import open_multi_gpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -225,31 +381,51 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    in_rate, nch, modes, carriers, infos, audio_rate, desc = channel_plan(args.workload, rank, world)
-    bank = cs.ReceiverBank(nch, in_rate, device=local)
-    if audio_rate > 0:
-        bank.SetAudioRate(audio_rate)
-    for c in range(nch):
-        bank.SetDemod(c, modes[c], infos[c])
-        bank.SetDemodFreq(c, -carriers[c])
-    L = bank.block_length()
+    name = args.workload
+    w, total, first, nch, modes, carriers, infos = channel_plan(name, rank, world, args.scaling)
+    iq, snapped, L = make_stream(w, modes, carriers, args.ingest)
+    fmt = 0 if args.ingest == "cf32" else 1
+    bank = cs.ReceiverBank(nch, w["in_rate"], device=local)
+    if w["audio_rate"] > 0:
+        bank.SetAudioRate(w["audio_rate"])
+    if w.get("blanker"):
+        bank.SetupNoiseProc(True, 50.0, 50.0)
+    for i in range(nch):
+        c = first + i
+        bank.SetDemod(i, modes[c], infos[c])
+        bank.SetDemodFreq(i, -snapped[c])
+    assert bank.block_length() == L
+    fft = None
+    if w.get("spectrum") and rank == 0:
+        fft = cs.CFft(device=local)
+        fft.SetFFTParams(65536, False, 0.0, w["in_rate"])
+        fft.SetFFTAve(4)
+    mg = open_multi_gpu(rank, world, local)          # cutesdr_mgpu_*: the NCCL communicator lives inside the library
     stream = torch.cuda.ExternalStream(bank.stream(), device=dev)
+    nblk = BLOCKS_PER_STEP
 
-    # distinct resident blocks: more than the 126 MB L2 can hold
-    nblk = max(4, int(np.ceil(160e6 / (8.0 * L))))
-    host_blocks = synth_blocks(L, nblk, seed=20260 + 4)
-    h_pin = torch.from_numpy(host_blocks.view(np.float32).reshape(nblk, 2 * L)).pin_memory()
-    d_blocks = h_pin.to(dev)
+    # the 0.2 s stream: pinned on the host, resident on the device
+    if fmt == 0:
+        host = torch.from_numpy(iq.view(np.float32).reshape(nblk, 2 * L)).pin_memory()
+    else:
+        i16 = np.empty((nblk, 2 * L), dtype=np.int16)
+        v = iq.view(np.float32).reshape(nblk, 2 * L)
+        np.clip(np.rint(v), -32767, 32767, out=v)
+        i16[:] = v
+        host = torch.from_numpy(i16).pin_memory()
+    del iq
+    d_blocks = host.to(dev)
+    sample_bytes = 8 if fmt == 0 else 4
     audio_stride = 2304
     d_audio = torch.zeros((nch, audio_stride), dtype=torch.float32, device=dev)
-    h_audio = torch.zeros((nch, audio_stride), dtype=torch.float32).pin_memory()
+    h_audio2 = [torch.zeros((nch, audio_stride), dtype=torch.float32).pin_memory() for _ in range(2)]
     n_out = np.zeros(nch, dtype=np.int32)
+    spec_args = (600, 1024, 0.0, -140.0, int(-w["in_rate"] / 2), int(w["in_rate"] / 2))
+    bank_stream = bank.stream()
 
     def barrier():
         torch.cuda.synchronize()
@@ -257,13 +433,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(i):
-        b = d_blocks[i % nblk]
-        return bank.process_device(b.data_ptr(), L, d_audio.data_ptr(), audio_stride)
+    def spectrum(k):
+        # the concurrent 65536-point spectrum at 10 frames/s: one frame every 10 blocks, taken from the block the
+        # channels saw (after the blanker), plus both plot mappings of CPlotter::draw
+        if fft is not None and k % (nblk // 2) == 0:
+            ptr, n = bank.last_block()
+            fft.put_device_async(ptr + 8 * 100000, 65536, bank_stream)
+            fft.GetPlot(*spec_args)
+
+    def step_device():
+        got = 0
+        for k in range(nblk):
+            got += bank.process_device(d_blocks[k].data_ptr(), L, d_audio.data_ptr(), audio_stride, fmt=fmt)
+            spectrum(k)
+        return got
 
     # ---- device-timed value
-    for i in range(args.warmup):
-        step_device(i)
+    for _ in range(args.warmup):
+        step_device()
     barrier()
     bank.kernel_timing(True)
     bank.kernel_time(0)
@@ -272,11 +459,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    produced = 0
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        for i in range(args.steps):
-            produced += step_device(args.warmup + i)
+        for _ in range(args.steps):
+            step_device()
         bank.join()             # main stream waits for the burst side streams: ev1 covers all work
         ev1.record(stream)
     barrier()
@@ -289,121 +475,149 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = (L * nch * world * args.steps) / (ms_max * 1e-3) / 1e6
+    samples_per_step = nblk * L
+    value = (samples_per_step * total * args.steps) / (ms_max * 1e-3) / 1e6
 
-    # ---- end to end: host block -> (rank 0 H2D -> NCCL broadcast) -> bank -> D2H audio
-    e2e_steps = max(3, min(args.steps, 60))
-    d_in = torch.empty(2 * L, dtype=torch.float32, device=dev)
+    # ---- end to end through the C ABI: host block -> (rank 0 H2D -> NCCL broadcast inside the library) -> bank -> D2H audio
+    e2e_steps = max(1, min(args.steps, 10))
+    d2h = [0]
 
-    # two host audio landing buffers: a step's D2H may still be in flight when the next step is queued
-    h_audio2 = [h_audio, torch.zeros((nch, audio_stride), dtype=torch.float32).pin_memory()]
+    def step_e2e():
+        for k in range(nblk):
+            hp = host[k].data_ptr()
+            if world == 1:
+                m = bank.process_async_raw_ptr(L, hp, fmt, h_audio2[k & 1].data_ptr(), audio_stride, n_out)
+            else:
+                m = bank.process_async_bcast_ptr(mg, L, hp if rank == 0 else None, fmt, h_audio2[k & 1].data_ptr(), audio_stride, n_out)
+            d2h[0] += int(m) * nch * 4
+            spectrum(k)
 
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-
-    def step_e2e(i):
-        if world == 1:
-            # pipelined C-ABI call: H2D of block i overlaps the kernels of block i-1, D2H on its own stream
-            return bank.process_async_ptr(L, h_pin[i % nblk].data_ptr(), h_audio2[i & 1].data_ptr(), audio_stride, n_out)
-        # N > 1: rank 0's H2D and the NCCL broadcast run on a communication stream; the bank takes the block over in
-        # stream order (cutesdr_bank_process_async_device), so block i+1 is in flight while block i is processed and
-        # the audio D2H runs on the bank's copy stream
-        with torch.cuda.stream(comm):
-            if rank == 0:
-                d_in.copy_(h_pin[i % nblk], non_blocking=True)
-            dist.broadcast(d_in, src=0)
-            return bank.process_async_device_ptr(L, d_in.data_ptr(), comm.cuda_stream, h_audio2[i & 1].data_ptr(), audio_stride, n_out)
-
-    for i in range(3):
-        step_e2e(i)
+    step_e2e()
+    bank.synchronize()
     barrier()
+    d2h[0] = 0
     t0 = time.perf_counter()
-    d2h = 0
-    for i in range(e2e_steps):
-        m = step_e2e(3 + i)
-        d2h += int(m) * nch * 4
+    for _ in range(e2e_steps):
+        step_e2e()
     bank.synchronize()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = (L * nch * world * e2e_steps) / float(te.item()) / 1e6
+    e2e_value = (samples_per_step * total * e2e_steps) / float(te.item()) / 1e6
+    mg_info = mg.info()
 
     if rank == 0:
-        peak, peak_src = measured_hbm_peak()
-        k1_bytes = 8.0 * L * nch           # per launch (one launch per chain group per block)
+        peaks = measured_peaks()
+        hbm_peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
+        hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        live = {}
+        for key, which in (("fp32_fma_tflops", 0), ("tcgen05_tf32_tflops", 1), ("tcgen05_f16_tflops", 2), ("hbm_copy_gbs", 3)):
+            try:
+                live[key] = cs.microbench(which, local)
+            except Exception as e:  # noqa: BLE001
+                live[key] = None
+                live[key + "_error"] = repr(e)
         roof = None
         if k1_n > 0 and k1_ms > 0:
             per_launch_s = (k1_ms / k1_n) * 1e-3
-            groups = max(1, round(k1_n / max(1, args.steps)))
-            ach = (k1_bytes / groups) / per_launch_s / 1e9
+            groups = max(1, round(k1_n / max(1, args.steps * nblk)))
+            units = float(L) * nch / groups                     # sample*channels one launch processes
+            ach = 8.0 * units / per_launch_s / 1e9
             traffic = None
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[args.workload]["dram_bytes_per_launch"]
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[name]["dram_bytes_per_launch"]
             except Exception:
                 pass
-            hbm_model = {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                         "note": "SURVEY 8(d) per-channel streaming model (8 B per sample*channel); NOT a DRAM figure -- every "
-                                 "channel re-uses the staged samples, see traffic for the measured DRAM bytes"}
+            hbm_model = {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
+                         "note": "SURVEY 8(d) per-channel streaming MODEL (8 B per sample*channel); not a DRAM figure and not the "
+                                 "bound -- all channels share the staged samples; see traffic for the measured DRAM bytes"}
             on_tc, flops_block = bank.kernel_model(0)
+            at_max = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
             if on_tc and flops_block > 0:
-                tpeak, tsrc = measured_tf32_peak()
+                f16 = bank.kernel_model(1)[0]          # which = 1: fp16 hi/lo operand form in use?
+                if peaks:
+                    dense = float(peaks["bf16_tflops"] if at_max else peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+                    psrc = "MEASURED_PEAKS.json dense bf16 %s figure%s" % ("burst" if at_max else "sustained", "" if f16 else " / 2 (kind::tf32)")
+                else:
+                    dense, psrc = 2250.0, "fallback: nominal 2.25 PFLOP/s bf16%s (B200_PROFILING.md)" % ("" if f16 else " / 2")
+                tpeak = dense if f16 else dense / 2.0
                 flops_launch = flops_block / groups
                 ach_t = flops_launch / per_launch_s / 1e12
                 roof = {"bound": "tensor", "achieved": ach_t, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_t / tpeak, "traffic": traffic,
-                        "kernel": "k_mix_tc", "launch_ms": k1_ms / k1_n, "launches": k1_n, "peak_source": tsrc,
-                        "flops_per_launch": flops_launch,
+                        "kernel": "k_mix_tc (%s operands)" % ("fp16 hi/lo" if f16 else "tf32 hi/lo"), "launch_ms": k1_ms / k1_n,
+                        "launches": k1_n, "peak_source": psrc + ("; SM clock at max through the timed region" if at_max else ""),
+                        "flops_per_launch": flops_launch, "units_per_launch": units, "flops_per_unit": flops_launch / units,
                         "executed": {"tflops": 3.0 * ach_t, "frac": 3.0 * ach_t / tpeak,
-                                     "note": "every fp32 product is three tf32 MMAs (hi*hi + hi*lo + lo*hi): the tensor pipe "
-                                             "executes 3x the algorithmic flops"},
-                        "hbm_model": hbm_model,
-                        "note": "kernel 1T: NCO mix + 4 CIC3 stages as a complex GEMM [128 ch x 48 taps] x [48 x time] per channel "
-                                "group; algorithmic flops = 2 x (4 x 48 real MACs) per channel and fs/16 output"}
+                                     "note": "every fp32 product is three hi/lo partial-product MMAs: the tensor pipe executes 3x the algorithmic flops"},
+                        "peaks_measured_live": live, "hbm_model": hbm_model}
             else:
-                roof = dict(hbm_model)
-                roof.update({"bound": "hbm", "traffic": traffic, "kernel": "k_mix_cic", "launch_ms": k1_ms / k1_n, "launches": k1_n,
-                             "note": hbm_model["note"] + "; the CUDA-core kernel is FP32-issue bound"})
+                ops = fp32_ops_per_sample(bank_stage_list(cs, w, modes[first], infos[first]))
+                fpeak = live.get("fp32_fma_tflops") or 2.0 * 148 * 128 * 1.965e9 / 1e12
+                ach_f = 2.0 * ops * units / per_launch_s / 1e12       # FMA = 2 flop
+                roof = {"bound": "fp32", "achieved": ach_f, "peak": fpeak, "unit": "TFLOP/s", "frac": ach_f / fpeak, "traffic": traffic,
+                        "kernel": "k_mix_cic", "launch_ms": k1_ms / k1_n, "launches": k1_n,
+                        "peak_source": "FP32 FMA issue peak measured live (cutesdr_microbench 0), FMA = 2 flop",
+                        "ops_per_unit": ops, "units_per_launch": units,
+                        "note": "algorithmic FP32 ops per sample*channel of the whole decimation ladder (SURVEY 8d) attributed to kernel 1 "
+                                "(it executes the NCO, the mixer and every CIC3 + the first half-band: > 90 % of them)",
+                        "peaks_measured_live": live, "hbm_model": hbm_model}
         cpu = None
-        try:
-            r = cpu_reference_run(args.workload, steps=3, warmup=1)
-            if r:
+        if not args.no_cpu_baseline:
+            try:
+                _, r = cpu_reference_run(name, steps=1, warmup=1)
                 cpu = {"value": r["value"], "unit": "Msps*ch", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-        except Exception as e:  # the baseline is reported, never required
-            cpu = {"value": None, "unit": "Msps*ch", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+            except Exception as e:  # the baseline is reported, never required
+                cpu = {"value": None, "unit": "Msps*ch", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+        cfg = common_config(name, w, world, args.scaling, args.ingest, L, total)
         line = {"metric": "input_msps_x_channels", "value": value, "unit": "Msps*ch", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "in_rate_sps": in_rate, "channels_per_gpu": nch, "block_length": L,
-                           "l2": "cycles %d distinct %d-sample blocks (%.0f MB > 126 MB L2)" % (nblk, L, nblk * L * 8 / 1e6),
-                           "realtime_factor": value / (in_rate * nch * world / 1e6),
-                           "arithmetic": "float32 chain; kernel 1 on tensor cores = every fp32 product as 3 tf32 MMAs, fp32 accumulation"
-                                         if (roof and roof.get("bound") == "tensor") else "float32 chain (CUDA cores)"},
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "realtime_factor": value / (w["in_rate"] * total / 1e6), "ms_per_block": ms_max / args.steps / nblk,
+                "arithmetic": ("float32 chain; kernel 1 on tensor cores = every fp32 product as 3 hi/lo MMAs, fp32 accumulation"
+                               if (roof and roof.get("bound") == "tensor") else "float32 chain (CUDA cores)"),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "Msps*ch", "h2d_bytes_per_step": 8 * L, "d2h_bytes_per_step": d2h // e2e_steps,
-                        "steps": e2e_steps},
-                "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu}
+                "e2e": {"value": e2e_value, "unit": "Msps*ch", "h2d_bytes_per_step": sample_bytes * L * nblk,
+                        "d2h_bytes_per_step": d2h[0] // e2e_steps, "steps": e2e_steps,
+                        "api": "cutesdr_bank_process_async_raw" if world == 1 else "cutesdr_bank_process_async_bcast (NCCL inside libcutesdr_cuda)",
+                        "mgpu": mg_info},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
         emit(line)
+    del mg
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def bank_stage_list(cs, w, mode, info):
+    d = cs.CDownConvert()
+    d.SetDataRate(w["in_rate"], M.max_bandwidth(mode, info))
+    return d.stages()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS) + ["cfg2"])
+    ap.add_argument("--ingest", default="cf32", choices=["cf32", "cs16"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    # stdout carries exactly one JSON line: everything native libraries print there (NCCL's version banner, ...) is
-    # sent to stderr for the duration of the run; emit() switches the real stdout back for the line itself
+    # stdout carries exactly one JSON line: everything native libraries print there (NCCL's banner, ...) is sent to
+    # stderr for the duration of the run; emit() switches the real stdout back for the line itself
     sys.stdout.flush()
     global _REAL_STDOUT
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+    if args.workload == "cfg2":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        return run_cfg2(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

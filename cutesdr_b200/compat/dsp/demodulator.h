@@ -34,8 +34,8 @@ public:
     virtual ~CDemodulator() { cutesdr_demodulator_destroy(m_h); }
     void SetInputSampleRate(TYPEREAL InputRate) { cutesdr_shim_check(cutesdr_demodulator_set_input_sample_rate(m_h, InputRate), "SetInputSampleRate"); }
     double GetOutputRate() { double r = 0; cutesdr_shim_check(cutesdr_demodulator_get_output_rate(m_h, &r), "GetOutputRate"); return r; }
-    double GetSMeterPeak() { double p = 0, a = 0; cutesdr_shim_check(cutesdr_demodulator_get_smeter(m_h, &p, &a), "GetSMeterPeak"); return p; }
-    double GetSMeterAve() { double p = 0, a = 0; cutesdr_shim_check(cutesdr_demodulator_get_smeter(m_h, &p, &a), "GetSMeterAve"); return a; }
+    double GetSMeterPeak() { double p = 0; cutesdr_shim_check(cutesdr_demodulator_get_smeter(m_h, &p, 0), "GetSMeterPeak"); return p; }
+    double GetSMeterAve() { double a = 0; cutesdr_shim_check(cutesdr_demodulator_get_smeter(m_h, 0, &a), "GetSMeterAve"); return a; }   // does not reset the held peak
     void SetDemod(int Mode, tDemodInfo CurrentDemodInfo)
     {
         cutesdr_demod_info d;

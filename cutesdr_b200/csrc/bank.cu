@@ -1,6 +1,7 @@
 // bank.cu -- receiver bank (N x CDemodulator) and its C ABI.
 // Sequencing mirrors CDemodulator::SetDemod / ProcessData, dsp/demodulator.cpp:107-215.
 #include "bank.cuh"
+#include "mgpu.cuh"
 
 #include <algorithm>
 #include <stdlib.h>
@@ -566,7 +567,7 @@ static int bank_process_host(cutesdr_bank* b, int n_in, const void* iq, int fmt,
 }
 
 static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out,
-                              bool from_device = false, cudaStream_t src_stream = 0);
+                              bool from_device = false, cudaStream_t src_stream = 0, cutesdr_mgpu* mg = nullptr);
 
 int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out)
 {
@@ -584,10 +585,19 @@ int cutesdr_bank_process_async_device(cutesdr_bank* b, int n_in, const void* d_i
     return bank_process_async(b, n_in, d_iq, 0, audio, audio_stride, n_out, true, reinterpret_cast<cudaStream_t>(src_stream));
 }
 
-static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out,
-                              bool from_device, cudaStream_t src_stream)
+int cutesdr_bank_process_async_bcast(cutesdr_bank* b, cutesdr_mgpu* m, int n_in, const void* iq_rank0, int fmt, float* audio,
+                                     int audio_stride, int* n_out)
 {
-    if (!b || !iq || (audio && audio_stride <= 0)) { set_error("bank_process_async: bad arguments"); return CUTESDR_E_ARG; }
+    if (!m || fmt < 0 || fmt > 2) { set_error("bank_process_async_bcast: bad arguments"); return CUTESDR_E_ARG; }
+    if (b && b->device != m->device) { set_error("bank_process_async_bcast: bank and communicator live on different devices"); return CUTESDR_E_ARG; }
+    return bank_process_async(b, n_in, iq_rank0, fmt, audio, audio_stride, n_out, false, 0, m);
+}
+
+static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out,
+                              bool from_device, cudaStream_t src_stream, cutesdr_mgpu* mg)
+{
+    const bool need_iq = !mg || mg->rank == 0;
+    if (!b || (need_iq && !iq) || (audio && audio_stride <= 0)) { set_error("bank_process_async: bad arguments"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     CSDR_CK(cudaSetDevice(b->device));
     if (b->layout_dirty) CSDR_TRY(b->rebuild());
@@ -608,8 +618,20 @@ static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt
     const int slot = (int)(b->async_blocks & 1);
     if (!b->d_xs[slot]) CSDR_CK(cudaMalloc(&b->d_xs[slot], (size_t)b->L * sizeof(float2)));
     // H2D of this block on the copy stream, as soon as the slot's previous block has been consumed
-    if (b->async_blocks >= 2) CSDR_CK(cudaStreamWaitEvent(b->st_h2d, b->ev_free[slot], 0));
-    if (from_device) {
+    if (b->async_blocks >= 2) {
+        // The header's promise ("iq must stay unchanged until the second following call") is enforced here: the copy
+        // that read the host buffer handed in two calls ago used this slot; the host waits for it before the call
+        // returns, so a producer that runs ahead of the GPU can never overwrite samples the DMA has not read yet.
+        if (!from_device && need_iq) CSDR_CK(cudaEventSynchronize(b->ev_h2d[slot]));
+        CSDR_CK(cudaStreamWaitEvent(b->st_h2d, b->ev_free[slot], 0));
+        if (mg) CSDR_CK(cudaStreamWaitEvent(mg->st_comm, b->ev_free[slot], 0));
+    }
+    if (mg) {
+        // multi-GPU: rank 0's pinned host block goes H2D in chunks, every chunk is broadcast over NVLink as soon as it
+        // has landed, straight into this slot on every rank; ev_h2d[slot] fires when the whole block is here
+        std::lock_guard<std::mutex> lk2(mg->mu);
+        CSDR_TRY(mgpu_bcast_block(mg, iq, b->d_xs[slot], (size_t)b->L * sample_bytes(fmt), b->st_h2d, b->ev_h2d[slot]));
+    } else if (from_device) {
         // the block sits in the caller's device buffer and is read in stream order with respect to src_stream: the
         // copy into the slot waits for everything queued there so far (an NCCL broadcast, ...), and src_stream
         // waits for the copy, so the caller may queue the next write into the same buffer straight away
@@ -646,14 +668,19 @@ static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt
 
 int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, void* d_audio, int audio_stride, int* n_out_max)
 {
-    if (!b || !d_iq) { set_error("bank_process_device: bad arguments"); return CUTESDR_E_ARG; }
+    return cutesdr_bank_process_device_raw(b, d_iq, 0, n_in, d_audio, audio_stride, n_out_max);
+}
+
+int cutesdr_bank_process_device_raw(cutesdr_bank* b, const void* d_iq, int fmt, int n_in, void* d_audio, int audio_stride, int* n_out_max)
+{
+    if (!b || !d_iq || fmt < 0 || fmt > 2) { set_error("bank_process_device: bad arguments"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     CSDR_CK(cudaSetDevice(b->device));
     if (b->layout_dirty) CSDR_TRY(b->rebuild());
     if (n_in != b->L) { set_error("bank_process_device: n_in %d must equal the block length %d", n_in, b->L); return CUTESDR_E_ARG; }
     const void* dblk = nullptr;
     int dfmt = 0;
-    CSDR_TRY(stage_block(b, d_iq, 0, cudaMemcpyDeviceToDevice, &dblk, &dfmt));
+    CSDR_TRY(stage_block(b, d_iq, fmt, cudaMemcpyDeviceToDevice, &dblk, &dfmt));
     int m = 0;
     CSDR_TRY(b->run_block(dblk, dfmt, reinterpret_cast<float*>(d_audio), audio_stride, nullptr, &m));
     CSDR_TRY(b->collect_taps());
@@ -732,14 +759,14 @@ int cutesdr_bank_kernel_time(cutesdr_bank* b, int which, double* ms_total, long 
 
 int cutesdr_bank_kernel_model(cutesdr_bank* b, int which, int* on_tensor_cores, double* flops_per_block)
 {
-    if (!b || which != 0) { set_error("kernel_model: bad arguments"); return CUTESDR_E_ARG; }
+    if (!b || which < 0 || which > 1) { set_error("kernel_model: bad arguments"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     CSDR_CK(cudaSetDevice(b->device));
     if (b->layout_dirty) CSDR_TRY(b->rebuild());
     int all = b->groups.empty() ? 0 : 1;
     double fl = 0.0;
     for (auto& g : b->groups) {
-        if (!g->dec.tensor_path()) all = 0;
+        if (!g->dec.tensor_path() || (which == 1 && !g->dec.tensor_f16())) all = 0;
         fl += g->dec.tensor_flops_per_block();
     }
     if (on_tensor_cores) *on_tensor_cores = all;

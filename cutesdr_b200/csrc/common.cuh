@@ -50,6 +50,61 @@ struct LaunchCounter {
     long long n = 0;
 };
 
+// Small parameter updates travel host -> device through a ring of PINNED buffers: the host fills a slot and queues
+// an async copy; nothing ever synchronises a stream (a cudaMemcpyAsync from pageable memory first waits for the
+// stream's earlier work). A slot is reused only after its previous copy has completed (host-side event wait, which
+// in practice never blocks: the ring is deeper than the run-ahead of the pipeline).
+class PinnedStage {
+public:
+    PinnedStage() {}
+    ~PinnedStage()
+    {
+        for (auto& s : slots_) { if (s.ev) cudaEventDestroy(s.ev); if (s.p) cudaFreeHost(s.p); }
+    }
+    PinnedStage(const PinnedStage&) = delete;
+    PinnedStage& operator=(const PinnedStage&) = delete;
+    // returns a pinned buffer of at least `bytes`; the caller fills it and hands it to push()
+    int acquire(size_t bytes, void** out)
+    {
+        if (slots_.empty()) slots_.resize(kDepth);
+        Slot& s = slots_[cur_];
+        if (s.ev && s.used) { CSDR_CK(cudaEventSynchronize(s.ev)); s.used = false; }
+        if (bytes > s.cap) {
+            if (s.p) cudaFreeHost(s.p);
+            s.p = nullptr; s.cap = 0;
+            size_t cap = 4096;
+            while (cap < bytes) cap <<= 1;
+            CSDR_CK(cudaHostAlloc(&s.p, cap, cudaHostAllocDefault));
+            s.cap = cap;
+        }
+        if (!s.ev) CSDR_CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        *out = s.p;
+        return CUTESDR_OK;
+    }
+    // async copy of the acquired buffer to dst on st
+    int push(void* dst, size_t bytes, cudaStream_t st)
+    {
+        Slot& s = slots_[cur_];
+        CSDR_CK(cudaMemcpyAsync(dst, s.p, bytes, cudaMemcpyHostToDevice, st));
+        CSDR_CK(cudaEventRecord(s.ev, st));
+        s.used = true;
+        cur_ = (cur_ + 1) % kDepth;
+        return CUTESDR_OK;
+    }
+    int upload(void* dst, const void* src, size_t bytes, cudaStream_t st)
+    {
+        void* p = nullptr;
+        CSDR_TRY(acquire(bytes, &p));
+        memcpy(p, src, bytes);
+        return push(dst, bytes, st);
+    }
+private:
+    static constexpr int kDepth = 8;
+    struct Slot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
+    std::vector<Slot> slots_;
+    int cur_ = 0;
+};
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline int next_pow2(long long v) { int p = 1; while (p < v) p <<= 1; return p; }
 

@@ -25,6 +25,21 @@ namespace csdr {
 // ------------------------------------------------------------------------------------------
 // host: stage ladder (dsp/downconvert.cpp:127-166)
 // ------------------------------------------------------------------------------------------
+Tuning Tuning::from_env()
+{
+    Tuning t;
+    t.no_tc = getenv("CUTESDR_NO_TC") != nullptr;
+    t.tc_f16 = getenv("CUTESDR_TC_F16") != nullptr;
+    t.no_hbchain = getenv("CUTESDR_NO_HBCHAIN") != nullptr;
+    t.hbtail = getenv("CUTESDR_HBTAIL") != nullptr;
+    t.no_overlap = getenv("CUTESDR_NO_OVERLAP") != nullptr;
+    t.debug_timing = getenv("CUTESDR_DEBUG_TIMING") != nullptr;
+    if (const char* e = getenv("CUTESDR_FUSE_HB")) t.fuse_hb = atoi(e);
+    if (const char* e = getenv("CUTESDR_TILE")) t.tile = atoi(e);
+    if (const char* e = getenv("CUTESDR_TC_SEG")) t.tc_seg = atoi(e);
+    return t;
+}
+
 double plan_stages(double in_rate, double max_bw, std::vector<int>& lens)
 {
     lens.clear();
@@ -481,8 +496,6 @@ static K1Fn k1_kernel(int ncic, int nhb)
 //     32 outputs), and runs the remaining CIC3 / fused 11-tap half-band stages and the store exactly as kernel 1
 //     does. The accumulator slot is released as soon as the tile is in registers.
 //   * mbarriers + tcgen05.commit order producers -> MMA -> epilogue; B runs through an 8-stage ring.
-//   * `dbg` (CUTESDR_TC_DBG) switches roles off for ablation timing only: 1 = no epilogue arithmetic/stores,
-//     2 = no MMAs, 4 = no operand staging. Results are meaningless with it set.
 // Segments re-prime the feed-forward stages with a halo of PRE outputs, like kernel 1's tiles.
 // ------------------------------------------------------------------------------------------
 constexpr int kTcN = 32;                                  // outputs (fs/16) per MMA tile
@@ -712,8 +725,7 @@ template <int NCR, int NHB, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_mix_tc(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, float2* __restrict__ halo_next, int L, int seg_len,
              const float* __restrict__ coef_tab, const unsigned* __restrict__ absmax_bits, const NcoDev* __restrict__ nco,
-             const unsigned long long* __restrict__ phase_cur, unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale,
-             int dbg)
+             const unsigned long long* __restrict__ phase_cur, unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
 {
     typedef TcCfg<NCR, NHB> Cfg;
     // F16: operands are fp16 hi + lo (same 11 significant bits as tf32, kind::f16 runs at twice the rate and takes K = 16):
@@ -876,7 +888,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int my = cnt++;
                 if ((my & 1) != (pw >> 1)) continue;
                 const Pending now = {my % kTcStages, my};
-                if (dbg & 4) { bar_wait(b_empty + now.st, ((my / kTcStages) & 1) ^ 1); bar_arrive(b_full + now.st); continue; }
                 if ((mine++ & 1) == 0) {
                     issue_loads(m0 + kTcN * k, va0, vb0);
                     p0 = now;
@@ -922,7 +933,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     constexpr int a_pl[6] = {1, 0, 3, 2, 0, 2};
                     constexpr int b_re[6] = {0, 1, 2, 3, 0, 2}, n_re[6] = {0, 0, 1, 1, 0, 1};
                     constexpr int b_im[6] = {2, 3, 0, 1, 2, 0};
-                    if (!(dbg & 2))
 #pragma unroll
                     for (int t = 0; t < 6; t++) {
                         const int ap = a_pl[t];
@@ -1019,13 +1029,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         auto acc_of = [&](int k) { return lane_base + (uint32_t)(kTcAccCol + 4 * kTcN * e + 2 * kTcN * (k & 1)); };
         auto group_math = [&](const float* re, const float* im, int m_first) {
             if ((m_first & 31) == 0) S = seed_osc(ph0 + (unsigned long long)(long long)(16 * m_first + 16) * p.inc);
-            if (dbg & 1) {
-                float a2 = 0.f;
-#pragma unroll
-                for (int i = 0; i < 16; i++) a2 += re[i] * im[i];
-                if (a2 == 1.2345f) em.rel++;
-                return;
-            }
             TcStrip<NCR, NHB, 0, 16>::run(re, im, S, w16, st, ev, hs, em);
         };
         if (ntiles > 0) {
@@ -1064,7 +1067,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }
 
 typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const float*, const unsigned*, const NcoDev*,
-                      const unsigned long long*, unsigned long long*, int, OutDesc, float, int);
+                      const unsigned long long*, unsigned long long*, int, OutDesc, float);
 static K1TFn k1t_kernel(int ncr, int nhb, bool f16)
 {
     static const K1TFn t32[3][4] = {{k_mix_tc<0, 0, false>, k_mix_tc<0, 1, false>, k_mix_tc<0, 2, false>, k_mix_tc<0, 3, false>},
@@ -1085,6 +1088,9 @@ static K1TFn k1t_kernel(int ncr, int nhb, bool f16)
 // one writing HBM. Only the first stage's input and the last stage's output touch HBM.
 // Row counts: c[NS] = T, c[j] = 2 c[j+1] + 9 (an output needs inputs 2m-10 .. 2m).
 // ------------------------------------------------------------------------------------------
+constexpr int kHbcCh = 16;        // channels per CTA of the fused half-band kernels
+constexpr int kHbc2T = 96;        // final outputs per CTA, two fused stages
+constexpr int kHbc3T = 48;        // three fused stages
 template <int NS, int T> struct HbcCfg {
     static constexpr int c(int j) { return j >= NS ? T : 2 * c(j + 1) + 9; }
     static constexpr int smem_rows() { return NS == 2 ? c(0) + c(1) : c(0) + c(1) + c(2); }
@@ -1309,7 +1315,7 @@ int Decimator::read_timing(double* ms_total, long long* launches)
             gap += ms;
         }
     }
-    if (getenv("CUTESDR_DEBUG_TIMING") && ev_used_ > 1)
+    if (tun_.debug_timing && ev_used_ > 1)
         fprintf(stderr, "[cutesdr] kernel-1: %zu launches, mean %.3f ms, mean gap to next launch %.3f ms\n", ev_used_,
                 k1_ms_ / (double)k1_n_, gap / (double)(ev_used_ - 1));
     ev_used_ = 0;
@@ -1328,7 +1334,7 @@ int Decimator::set_overlap(bool on)
         CSDR_CK(cudaStreamCreateWithPriority(&st_hb_, cudaStreamNonBlocking, hi));
         for (auto& e : ev_k2_) CSDR_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    overlap_ = on && (int)lens_.size() > k1_stages() && !getenv("CUTESDR_NO_OVERLAP");
+    overlap_ = on && (int)lens_.size() > k1_stages() && !tun_.no_overlap;
     return CUTESDR_OK;
 }
 
@@ -1377,6 +1383,7 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     block_len_ = block_len;
     st_ = st;
     lc_ = lc;
+    tun_ = Tuning::from_env();
     out_rate_ = plan_stages(in_rate, max_bw, lens_);
     if ((int)lens_.size() > kMaxStages) { set_error("too many decimation stages (%d)", (int)lens_.size()); return CUTESDR_E_ARG; }
     if (block_len % (1 << lens_.size()) != 0) {
@@ -1387,12 +1394,12 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
     while (ncic_ < (int)lens_.size() && lens_[ncic_] == 3 && ncic_ < 6) ncic_++;
     // kernel 1T (tensor cores): the ladder starts with >= 4 CIC3 stages and every legal block length is a whole
     // number of 256-sample units (>= 8 stages), so the CUDA-core kernel never has to stand in for it
-    tc_ = ncic_ >= 4 && ncic_ <= 6 && lens_.size() >= 8 && block_len % 256 == 0 && block_len >= 4096 && !getenv("CUTESDR_NO_TC");
+    tc_ = ncic_ >= 4 && ncic_ <= 6 && lens_.size() >= 8 && block_len % 256 == 0 && block_len >= 4096 && !tun_.no_tc;
     // up to kFuseHb 11-tap half-bands that follow the CICs run inside kernel 1 as well. Kernel 1T's epilogue has
     // the issue slots for more of them (kFuseHbTc), as long as the segment priming stays small.
     nhbf_ = 0;
     int fuse_max = tc_ ? kFuseHbTc : kFuseHb;
-    if (const char* e = getenv("CUTESDR_FUSE_HB")) fuse_max = std::max(0, std::min(tc_ ? 3 : 2, atoi(e)));     // tuning aid
+    if (tun_.fuse_hb >= 0) fuse_max = std::max(0, std::min(tc_ ? 3 : 2, tun_.fuse_hb));     // tuning aid
     while (nhbf_ < fuse_max && ncic_ + nhbf_ < (int)lens_.size() && lens_[ncic_ + nhbf_] == 11) nhbf_++;
     if (tc_) {
         while (nhbf_ > 0 && (16 * tc_pre(ncic_ - 4, nhbf_) + 32 > kHaloMax || tc_pre(ncic_ - 4, nhbf_) > 96)) nhbf_--;
@@ -1476,8 +1483,8 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
             if (cost < best_cost * 0.999) { best_cost = cost; best_tl = tl; }
         }
         tile_len_ = best_tl;
-        if (const char* e = getenv("CUTESDR_TILE")) tile_len_ = std::max(Q, atoi(e) / Q * Q);                    // tuning aid
-        if (getenv("CUTESDR_DEBUG_TIMING")) {
+        if (tun_.tile > 0) tile_len_ = std::max(Q, tun_.tile / Q * Q);                    // tuning aid
+        if (tun_.debug_timing) {
             int occ = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cta_threads, (size_t)(tile_len_ + H) * sizeof(float2));
             fprintf(stderr, "[cutesdr] kernel-1 <%d,%d>: tile %d + halo %d, grid %d x %d, %d CTAs/SM\n", ncic_, nhbf_, tile_len_, H,
@@ -1494,7 +1501,7 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
         // CUTESDR_TC_F16=1: fp16 hi/lo operands instead of tf32 (twice the tensor rate, same accuracy, scale-free through the
         // block maximum). Opt-in: inside the step the kernel is not tensor-bound, so the halved MMA time does not pay for the
         // extra k_absmax pass yet (alone 106 vs 120 us, tensor pipe 35 % vs 66 % active, issue slots 75 % either way; 0.336 vs 0.312 ms per step).
-        tc_f16_ = getenv("CUTESDR_TC_F16") != nullptr;
+        tc_f16_ = tun_.tc_f16;
         K1TFn tf = k1t_kernel(ncic_ - 4, nhbf_, tc_f16_);
         CSDR_CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
         CSDR_CK(cudaMalloc(&d_absmax_, sizeof(unsigned)));
@@ -1507,12 +1514,19 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
             int sl = (block_len + kTcSegs * ctas_x - 1) / (kTcSegs * ctas_x);
             tc_seg_len_ = std::max(256, (sl + 255) / 256 * 256);
         }
-        if (const char* e = getenv("CUTESDR_TC_SEG")) tc_seg_len_ = std::max(256, atoi(e) / 256 * 256);           // tuning aid
+        if (tun_.tc_seg > 0) tc_seg_len_ = std::max(256, tun_.tc_seg / 256 * 256);           // tuning aid
         tc_dirty_ = true;
-        if (getenv("CUTESDR_DEBUG_TIMING"))
+        if (tun_.debug_timing)
             fprintf(stderr, "[cutesdr] kernel-1T <%d,%d>: segment %d (+%d priming), grid %d x %d\n", ncic_ - 4, nhbf_, tc_seg_len_,
                     16 * pre, ((block_len + tc_seg_len_ - 1) / tc_seg_len_ + kTcSegs - 1) / kTcSegs, tc_groups_);
     }
+    // Opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: set it for the device this
+    // object lives on, every time (a process may hold banks on several GPUs).
+    CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<2, kHbc2T, kHbcCh>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)HbcCfg<2, kHbc2T>::smem_rows() * kHbcCh * sizeof(float2))));
+    CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<3, kHbc3T, kHbcCh>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)HbcCfg<3, kHbc3T>::smem_rows() * kHbcCh * sizeof(float2))));
+    CSDR_CK(cudaFuncSetAttribute(k_hb_tail<kHbcCh>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     dirty_ = true;
     return CUTESDR_OK;
 }
@@ -1541,9 +1555,8 @@ void Decimator::set_frequency(int i, double nco_freq)
 int Decimator::upload_dirty()
 {
     if (!dirty_) return CUTESDR_OK;
-    CSDR_CK(cudaMemcpyAsync(d_nco_, h_nco_.data(), stride_ * sizeof(NcoDev), cudaMemcpyHostToDevice, st_));
-    // the async copy reads pageable host memory synchronously with respect to the host, so
-    // h_nco_ may be modified again as soon as this returns
+    // pinned snapshot: no stream synchronisation, and h_nco_ may be modified again as soon as this returns
+    CSDR_TRY(stage_.upload(d_nco_, h_nco_.data(), stride_ * sizeof(NcoDev), st_));
     dirty_ = false;
     return CUTESDR_OK;
 }
@@ -1609,7 +1622,7 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
         const int sl = std::min(tc_seg_len_, L);
         dim3 grid(((L + sl - 1) / sl + kTcSegs - 1) / kTcSegs, tc_groups_);
         k1t_kernel(ncic_ - 4, nhbf_, tc_f16_)<<<grid, kTcThreads, kTcSmem, st_>>>(d_x, fmt, halo_cur, halo_next, L, sl, d_tc_coef_, d_absmax_, d_nco_, pc, pn,
-                                                                          stride_, od, scale, getenv("CUTESDR_TC_DBG") ? atoi(getenv("CUTESDR_TC_DBG")) : 0);
+                                                                          stride_, od, scale);
     } else if (L % Q == 0) {
         const int threads = std::min(256, round_up(stride_, 32));
         dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);
@@ -1636,7 +1649,7 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
         // leading run of 11-tap stages -> one fused pass
         int nchain = 0;
         while (nchain < 3 && nchain < nhb && lens_[k1_stages() + nchain] == 11) nchain++;
-        if (nchain >= 2 && stride_ % 32 == 0 && !getenv("CUTESDR_NO_HBCHAIN")) {
+        if (nchain >= 2 && stride_ % 32 == 0 && !tun_.no_hbchain) {
             const int n_in = L >> k1_stages();
             const int n_out = n_in >> nchain;
             OutDesc o2;
@@ -1654,20 +1667,16 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
                 o2.base = total_out_;
             }
             const unsigned mask0 = (unsigned)(stage_rows_[0] - 1);
-            constexpr int CH = 16;
+            constexpr int CH = kHbcCh;
             const int chan_blocks = stride_ / CH;
             if (nchain == 2) {
-                constexpr int T = 96;
+                constexpr int T = kHbc2T;
                 const size_t smem = (size_t)HbcCfg<2, T>::smem_rows() * CH * sizeof(float2);
-                static bool attr2 = false;
-                if (!attr2) { CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<2, T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr2 = true; }
                 dim3 grid((n_out + T - 1) / T, chan_blocks);
                 k_hb11_chain<2, T, CH><<<grid, 256, smem, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, o2);
             } else {
-                constexpr int T = 48;
+                constexpr int T = kHbc3T;
                 const size_t smem = (size_t)HbcCfg<3, T>::smem_rows() * CH * sizeof(float2);
-                static bool attr3 = false;
-                if (!attr3) { CSDR_CK(cudaFuncSetAttribute(k_hb11_chain<3, T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr3 = true; }
                 dim3 grid((n_out + T - 1) / T, chan_blocks);
                 k_hb11_chain<3, T, CH><<<grid, 256, smem, s2>>>(d_stage_[0], mask0, stage_base_[0], stride_, n_out, o2);
             }
@@ -1682,10 +1691,10 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
         const int ns = nhb - s_first;
         // opt-in (CUTESDR_HBTAIL=1): measured neutral inside the step (0.322 vs 0.320 ms, cfg4) -- the three small launches it
         // replaces already overlap with the burst chain, and its deep halo recomputes ~1.8x of the first two stages
-        bool ok = ns >= 2 && ns <= 4 && stride_ % 16 == 0 && getenv("CUTESDR_HBTAIL") != nullptr;
+        bool ok = ns >= 2 && ns <= 4 && stride_ % 16 == 0 && tun_.hbtail;
         for (int s = s_first; ok && s < nhb; s++) ok = lens_[k1_stages() + s] != 3;
         if (ok) {
-            constexpr int CH = 16;
+            constexpr int CH = kHbcCh;
             TailCfg cfg;
             cfg.ns = ns;
             const int n_out = L >> lens_.size();
@@ -1705,11 +1714,6 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
             for (int j = ns - 1; j >= 0; j--) hist = 2 * hist + (cfg.len[j] - 1);
             const int n_in0 = L >> (k1_stages() + s_first);
             if (smem <= 160 * 1024 && hist + n_in0 <= stage_rows_[s_first]) {
-                static size_t attr_smem = 0;
-                if (smem > attr_smem) {
-                    CSDR_CK(cudaFuncSetAttribute(k_hb_tail<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    attr_smem = smem;
-                }
                 OutDesc o2;
                 o2.p = d_ring_;
                 o2.mask = 0;

@@ -19,6 +19,14 @@ int apply_nco_startup_gain(float2* d_x, long long stream_pos, int n, cudaStream_
 int unpack_samples(const void* d_raw, int fmt, float2* d_out, int n, cudaStream_t st, LaunchCounter* lc);
 inline int sample_bytes(int fmt) { return fmt == 0 ? 8 : (fmt == 1 ? 4 : 6); }
 
+// Tuning / ablation knobs, read from the environment ONCE per Decimator::init (never on the launch path).
+// None is needed for correctness; DESIGN.md section 7 lists them.
+struct Tuning {
+    bool no_tc = false, tc_f16 = false, no_hbchain = false, hbtail = false, no_overlap = false, debug_timing = false;
+    int fuse_hb = -1, tile = 0, tc_seg = 0;
+    static Tuning from_env();
+};
+
 struct NcoDev {
     unsigned long long inc;   // phase increment per input sample, turns * 2^64
     float w1c, w1s;           // e^{j inc}
@@ -63,6 +71,7 @@ public:
     // kernel 1T in use? and the real multiply-adds (MAC = 2 flop) of its GEMM per full block, counted ONCE per product
     // (fp32-equivalent: the three tf32 partial products that emulate one fp32 product count as one)
     bool tensor_path() const { return tc_; }
+    bool tensor_f16() const { return tc_ && tc_f16_; }        // fp16 hi/lo operands (kind::f16) instead of tf32
     double tensor_flops_per_block() const { return tc_ ? 2.0 * (128.0 * tc_groups_) * (block_len_ / 16.0) * 192.0 : 0.0; }
 
     int nch() const { return nch_; }
@@ -83,6 +92,7 @@ private:
     cudaStream_t st_ = 0;
     LaunchCounter* lc_ = nullptr;
     std::vector<NcoDev> h_nco_;
+    PinnedStage stage_;
     bool dirty_ = true;
     // kernel 1T (tensor-core form of kernel 1, used when the ladder starts with >= 4 CIC3 stages)
     bool tc_ = false, tc_dirty_ = true, tc_f16_ = false;
@@ -99,6 +109,7 @@ private:
     std::vector<int> stage_rows_;      // power of two
     float2* d_ring_ = nullptr;
     bool overlap_ = false;
+    Tuning tun_;
     cudaStream_t st_hb_ = 0;
     cudaEvent_t ev_k1_ = nullptr, ev_done_ = nullptr;
     cudaEvent_t ev_k2_[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -242,6 +242,10 @@ struct cutesdr_fft {
     int32_t* d_screen = nullptr;
     int screen_cap = 0;
     float2* h_x = nullptr;      // pinned
+    int* h_flag = nullptr;      // pinned landing spot of the overload flag
+    bool flag_pending = false;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;   // put_device_async: frame copied / frame's kernels finished
+    bool async_used = false;
 
     void free_bufs()
     {
@@ -254,6 +258,9 @@ struct cutesdr_fft {
         if (st) cudaStreamSynchronize(st);
         free_bufs();
         cudaFree(d_tw); cudaFree(d_flag); cudaFree(d_screen); cudaFree(d_plain);
+        if (h_flag) cudaFreeHost(h_flag);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_done) cudaEventDestroy(ev_done);
         if (st) cudaStreamDestroy(st);
     }
     int reset()
@@ -300,6 +307,16 @@ struct cutesdr_fft {
     }
     int put_device(const float2* d_in, int n, int* total)
     {
+        CSDR_TRY(put_kernels(d_in, n, total));
+        CSDR_CK(cudaStreamSynchronize(st));
+        overload = *h_flag != 0;
+        flag_pending = false;
+        return CUTESDR_OK;
+    }
+    // the frame's kernels, queued on st; the overload flag lands in pinned memory and is picked up by the next
+    // synchronising call (put_device, GetScreenIntegerFFTData)
+    int put_kernels(const float2* d_in, int n, int* total)
+    {
         // PutInDisplayFFT, dsp/fft.cpp:267-288
         if (n != size) { set_error("PutInDisplayFFT needs exactly %d samples (got %d)", size, n); return CUTESDR_E_ARG; }
         total_count++;
@@ -318,10 +335,8 @@ struct cutesdr_fft {
             lc.n += 2;
         }
         CSDR_CK(cudaGetLastError());
-        int flag = 0;
-        CSDR_CK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CSDR_CK(cudaStreamSynchronize(st));
-        overload = flag != 0;
+        CSDR_CK(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        flag_pending = true;
         if (total) *total = total_count;
         return CUTESDR_OK;
     }
@@ -342,6 +357,10 @@ int cutesdr_fft_create(cutesdr_fft** out, int device)
     CSDR_CK(cudaMalloc(&f->d_tw, kTwLen * sizeof(float2)));
     CSDR_CK(cudaMemcpy(f->d_tw, tw.data(), kTwLen * sizeof(float2), cudaMemcpyHostToDevice));
     CSDR_CK(cudaMalloc(&f->d_flag, sizeof(int)));
+    CSDR_CK(cudaHostAlloc(&f->h_flag, sizeof(int), cudaHostAllocDefault));
+    *f->h_flag = 0;
+    CSDR_CK(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
+    CSDR_CK(cudaEventCreateWithFlags(&f->ev_done, cudaEventDisableTiming));
     // CFft::CFft(): SetFFTParams(2048, FALSE, 0.0, 1000); SetFFTAve(1)  (dsp/fft.cpp:29-50)
     CSDR_TRY(f->set_params(2048, false, 0.0, 1000));
     *out = f.release();
@@ -410,6 +429,25 @@ int cutesdr_fft_put_device(cutesdr_fft* h, int n, const void* d_in, int* total_c
     return h->put_device(reinterpret_cast<const float2*>(d_in), n, total_count);
 }
 
+int cutesdr_fft_put_device_async(cutesdr_fft* h, int n, const void* d_in, void* src_stream, int* total_count)
+{
+    if (!h || !d_in) { set_error("fft_put_device_async: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    CSDR_CK(cudaSetDevice(h->device));
+    if (n != h->size) { set_error("PutInDisplayFFT needs exactly %d samples (got %d)", h->size, n); return CUTESDR_E_ARG; }
+    cudaStream_t src = reinterpret_cast<cudaStream_t>(src_stream);
+    // the frame is copied on the producer's stream (stream-ordered with whatever wrote it, and it may be overwritten
+    // right after), the transform runs on this object's own stream beside the producer's later work
+    if (h->async_used) CSDR_CK(cudaStreamWaitEvent(src, h->ev_done, 0));
+    CSDR_CK(cudaMemcpyAsync(h->d_x, d_in, (size_t)n * sizeof(float2), cudaMemcpyDeviceToDevice, src));
+    CSDR_CK(cudaEventRecord(h->ev_in, src));
+    CSDR_CK(cudaStreamWaitEvent(h->st, h->ev_in, 0));
+    CSDR_TRY(h->put_kernels(h->d_x, n, total_count));
+    CSDR_CK(cudaEventRecord(h->ev_done, h->st));
+    h->async_used = true;
+    return CUTESDR_OK;
+}
+
 static int fft_screen(cutesdr_fft* h, int max_height, int max_width, double max_db, double min_db, int start_freq, int stop_freq,
                       int32_t* out, int max_height2, int32_t* out2, int* overload)
 {
@@ -439,6 +477,7 @@ static int fft_screen(cutesdr_fft* h, int max_height, int max_width, double max_
     CSDR_CK(cudaMemcpyAsync(out, h->d_screen, (size_t)max_width * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
     if (out2) CSDR_CK(cudaMemcpyAsync(out2, h->d_screen + max_width, (size_t)max_width * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
     CSDR_CK(cudaStreamSynchronize(h->st));
+    if (h->flag_pending) { h->overload = *h->h_flag != 0; h->flag_pending = false; }
     if (overload) *overload = h->overload ? 1 : 0;
     return CUTESDR_OK;
 }

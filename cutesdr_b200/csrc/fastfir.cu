@@ -8,72 +8,12 @@
 // Layout: input windows come from the per-channel ring [c][kDecRing] the decimator fills;
 // H lives as complex64 [n_filters][2048] (channels with equal (lo,hi,offset,rate) share a row);
 // output goes channel-major [c][row_stride] (one contiguous 1024-sample run per burst and channel).
+// Filters are designed on the device (k_fir_design) and the first burst of a stream is computed in direct form
+// (k_fir_first).
 // The FFT is a shared-memory Stockham autosort (five radix-4 passes + one radix-2, ping-pong buffers).
 #include "fastfir.cuh"
 
 namespace csdr {
-
-// ------------------------------------------------------------------------------------------
-// host-side filter design (double precision)
-// ------------------------------------------------------------------------------------------
-namespace {
-struct cd { double re, im; };
-
-void fft_host(std::vector<cd>& a, int sign)
-{
-    const int n = (int)a.size();
-    for (int i = 1, j = 0; i < n; i++) {
-        int bit = n >> 1;
-        for (; j & bit; bit >>= 1) j ^= bit;
-        j ^= bit;
-        if (i < j) std::swap(a[i], a[j]);
-    }
-    for (int len = 2; len <= n; len <<= 1) {
-        const double ang = sign * kTwoPi / len;
-        const int half = len >> 1;
-        for (int k = 0; k < half; k++) {
-            const double wr = cos(ang * k), wi = sin(ang * k);
-            for (int i = k; i < n; i += len) {
-                cd u = a[i], v = a[i + half];
-                double tr = v.re * wr - v.im * wi, ti = v.re * wi + v.im * wr;
-                a[i] = {u.re + tr, u.im + ti};
-                a[i + half] = {u.re - tr, u.im - ti};
-            }
-        }
-    }
-}
-}  // namespace
-
-// Frequency response of the band-pass designed by CFastFIR::SetupParameters
-// (Blackman-Nuttall windowed sinc, shifted to the band centre, scaled by 1/2048).
-static void design_filter(double lo, double hi, double rate, std::vector<float2>& H)
-{
-    static std::vector<double> window;
-    static std::once_flag once;
-    std::call_once(once, []() {
-        window.resize(kFirTaps);
-        for (int i = 0; i < kFirTaps; i++)
-            window[i] = (0.3635819 - 0.4891775 * cos((kTwoPi * i) / (kFirTaps - 1)) +
-                         0.1365995 * cos((2.0 * kTwoPi * i) / (kFirTaps - 1)) -
-                         0.0106411 * cos((3.0 * kTwoPi * i) / (kFirTaps - 1)));
-    });
-    const double nFL = lo / rate, nFH = hi / rate;
-    const double nFc = (nFH - nFL) / 2.0;
-    const double nFs = kTwoPi * (nFH + nFL) / 2.0;
-    const double centre = 0.5 * (double)(kFirTaps - 1);
-    std::vector<cd> a(kFirFft, cd{0.0, 0.0});
-    for (int i = 0; i < kFirTaps; i++) {
-        const double x = (double)i - centre;
-        double z;
-        if ((double)i == centre) z = 2.0 * nFc;
-        else z = sin(kTwoPi * x * nFc) / (kPi * x) * window[i];
-        a[i].re = z * cos(nFs * x) / (double)kFirFft;
-        a[i].im = z * sin(nFs * x) / (double)kFirFft;
-    }
-    fft_host(a, -1);
-    H.resize(kFirFft);
-    for (int k = 0; k < kFirFft; k++) H[k] = make_float2((float)a[k].re, (float)a[k].im);
-}
 
 // ------------------------------------------------------------------------------------------
 // device
@@ -182,31 +122,153 @@ __global__ void __launch_bounds__(256) k_fastfir(const float2* __restrict__ ring
 }
 
 // ------------------------------------------------------------------------------------------
+// Start-up burst. The very first overlap-save window of a stream is [1024 zeros | x[0..1023]]: output k is
+// sum_{m<=k} h[m] x[k-m], i.e. the filter's leading tail (taps of 1e-7 relative size) applied to full-size
+// samples. A float32 FFT convolution has an ABSOLUTE error floor of ~1e-7 x the window's peak, which swamps those
+// outputs -- and the SAM/FM PLLs acquire on exactly these samples (atan2 only looks at the ratio im/re), so the
+// whole acquisition transient would differ from the reference's double-precision one. This burst is therefore
+// computed in direct form with double accumulation from the time-domain taps: every output is accurate RELATIVE
+// TO ITS OWN size, and the demodulators can be compared with the reference from the first sample on.
+// One CTA per channel; thread t owns outputs t, 511-t, 512+t, 1023-t (equal work per thread).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fir_first(const float2* __restrict__ ring, const float2* __restrict__ taps,
+                                                   const int* __restrict__ filt_id, float2* __restrict__ y, int stride)
+{
+    __shared__ float2 xs[kBurst];
+    __shared__ float2 hs[kBurst];
+    const int c = blockIdx.x;
+    const float2* r = ring + (size_t)c * kDecRing;
+    const float2* h = taps + (size_t)filt_id[c] * kFirTapRow;
+    for (int i = threadIdx.x; i < kBurst; i += 256) { xs[i] = r[i]; hs[i] = h[i]; }
+    __syncthreads();
+    float2* yo = y + (size_t)c * stride;
+    const int t = threadIdx.x;
+    const int ks[4] = {t, 511 - t, 512 + t, 1023 - t};
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int k = ks[q];
+        double ar = 0.0, ai = 0.0;
+        for (int m = 0; m <= k; m++) {          // ascending m: the small leading taps first
+            const float2 hh = hs[m], x = xs[k - m];
+            ar += (double)hh.x * (double)x.x - (double)hh.y * (double)x.y;
+            ai += (double)hh.x * (double)x.y + (double)hh.y * (double)x.x;
+        }
+        yo[k] = make_float2((float)ar, (float)ai);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Filter design on the device: CFastFIR::SetupParameters, dsp/fastfir.cpp:207-254 -- 1025-tap Blackman-Nuttall
+// windowed sinc, shifted to the band centre, scaled by 1/2048, zero-padded and transformed. One CTA per filter,
+// double precision throughout (taps and a radix-2 Stockham FFT in shared memory), rounded to float32 at the end.
+// ------------------------------------------------------------------------------------------
+struct FirJob { double lo, hi, rate; int row, pad; };
+
+__global__ void __launch_bounds__(256) k_fir_design(const FirJob* __restrict__ jobs, float2* __restrict__ H, float2* __restrict__ taps)
+{
+    extern __shared__ double2 fd_sm[];
+    double2* a = fd_sm;
+    double2* b = fd_sm + kFirFft;
+    const FirJob job = jobs[blockIdx.x];
+    const double nFL = job.lo / job.rate, nFH = job.hi / job.rate;
+    const double nFc = (nFH - nFL) / 2.0;
+    const double nFs = kTwoPi * (nFH + nFL) / 2.0;
+    const double centre = 0.5 * (double)(kFirTaps - 1);
+    float2* trow = taps + (size_t)job.row * kFirTapRow;
+    for (int i = threadIdx.x; i < kFirFft; i += 256) {
+        double re = 0.0, im = 0.0;
+        if (i < kFirTaps) {
+            const double x = (double)i - centre;
+            double z;
+            if ((double)i == centre) z = 2.0 * nFc;
+            else {
+                const double w = (0.3635819 - 0.4891775 * cos((kTwoPi * i) / (kFirTaps - 1)) +
+                                  0.1365995 * cos((2.0 * kTwoPi * i) / (kFirTaps - 1)) -
+                                  0.0106411 * cos((3.0 * kTwoPi * i) / (kFirTaps - 1)));
+                z = sin(kTwoPi * x * nFc) / (kPi * x) * w;
+            }
+            re = z * cos(nFs * x);
+            im = z * sin(nFs * x);
+            trow[i] = make_float2((float)re, (float)im);
+        } else if (i < kFirTapRow) trow[i] = make_float2(0.f, 0.f);
+        a[i] = make_double2(re / (double)kFirFft, im / (double)kFirFft);
+    }
+    __syncthreads();
+    // radix-2 Stockham, e^{-j 2 pi nk/N}
+    double2* src = a;
+    double2* dst = b;
+    for (int ns = 1; ns < kFirFft; ns <<= 1) {
+        for (int j = threadIdx.x; j < kFirFft / 2; j += 256) {
+            const int k = j & (ns - 1);
+            double sn, cs;
+            sincospi(-(double)k / (double)ns, &sn, &cs);
+            const double2 u = src[j], v = src[j + kFirFft / 2];
+            const double2 tv = make_double2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+            const int j0 = ((j - k) << 1) + k;
+            dst[j0] = make_double2(u.x + tv.x, u.y + tv.y);
+            dst[j0 + ns] = make_double2(u.x - tv.x, u.y - tv.y);
+        }
+        __syncthreads();
+        double2* t = src; src = dst; dst = t;
+    }
+    float2* hrow = H + (size_t)job.row * kFirFft;
+    for (int i = threadIdx.x; i < kFirFft; i += 256) hrow[i] = make_float2((float)src[i].x, (float)src[i].y);
+}
+
+// ------------------------------------------------------------------------------------------
 // FirBank
 // ------------------------------------------------------------------------------------------
 FirBank::~FirBank()
 {
     cudaFree(d_H_);
+    cudaFree(d_h_);
+    cudaFree(d_jobs_);
     cudaFree(d_id_);
     cudaFree(d_tw_);
 }
 
 int FirBank::init(int nch, int stride, cudaStream_t st, LaunchCounter* lc)
 {
+    static_assert(sizeof(FirJob) == sizeof(Job), "job layout");
     nch_ = nch; stride_ = stride; st_ = st; lc_ = lc;
     cur_.assign(nch, Params{-1.0, 1.0, 1.0, 1.0});        // CFastFIR ctor, dsp/fastfir.cpp:126-129
     h_id_.assign(stride, 0);
-    // filter 0 = all zeros (a channel that never had a valid SetupParameters)
-    h_H_.assign(kFirFft, make_float2(0.f, 0.f));
-    nfilt_ = 1;
+    // row 0 = all zeros (a channel that never had a valid SetupParameters); every other row is referenced by at
+    // least one channel, so nch + 1 rows always suffice
+    cap_ = nch + 1;
+    refs_.assign(cap_, 0);
+    row_key_.assign(cap_, Key{0, 0, 0});
+    free_.clear();
+    for (int r = cap_ - 1; r >= 1; r--) free_.push_back(r);
+    rows_in_use_ = 1;
+    CSDR_CK(cudaMalloc(&d_H_, (size_t)cap_ * kFirFft * sizeof(float2)));
+    CSDR_CK(cudaMalloc(&d_h_, (size_t)cap_ * kFirTapRow * sizeof(float2)));
+    CSDR_CK(cudaMemsetAsync(d_H_, 0, (size_t)kFirFft * sizeof(float2), st_));
+    CSDR_CK(cudaMemsetAsync(d_h_, 0, (size_t)kFirTapRow * sizeof(float2), st_));
+    CSDR_CK(cudaMalloc(&d_jobs_, (size_t)cap_ * sizeof(Job)));
     CSDR_CK(cudaMalloc(&d_id_, stride * sizeof(int)));
     std::vector<float2> tw(1024);
     for (int m = 0; m < 1024; m++) tw[m] = make_float2((float)cos(-kTwoPi * m / 2048.0), (float)sin(-kTwoPi * m / 2048.0));
     CSDR_CK(cudaMalloc(&d_tw_, 1024 * sizeof(float2)));
-    CSDR_CK(cudaMemcpyAsync(d_tw_, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice, st_));
-    CSDR_CK(cudaStreamSynchronize(st_));
-    dirty_ = true;
+    CSDR_TRY(stage_.upload(d_tw_, tw.data(), 1024 * sizeof(float2), st_));
+    CSDR_CK(cudaFuncSetAttribute(k_fir_design, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kFirFft * sizeof(double2))));
+    ids_dirty_ = true;
     return CUTESDR_OK;
+}
+
+void FirBank::release(int i)
+{
+    const int old = h_id_[i];
+    if (old > 0 && --refs_[old] == 0) {
+        ids_.erase(row_key_[old]);
+        free_.push_back(old);
+        rows_in_use_--;
+        // a design job that is still queued for this row would be wasted work but harmless; drop it
+        for (size_t k = 0; k < jobs_.size(); k++) if (jobs_[k].row == old) { jobs_.erase(jobs_.begin() + k); break; }
+    }
+    h_id_[i] = 0;
+    cur_[i] = Params{-1.0, 1.0, 1.0, 1.0};
+    ids_dirty_ = true;
 }
 
 int FirBank::setup(int i, double lo, double hi, double offset, double rate)
@@ -226,36 +288,66 @@ int FirBank::setup(int i, double lo, double hi, double offset, double rate)
     int id;
     if (it != ids_.end()) id = it->second;
     else {
-        std::vector<float2> H;
-        design_filter(lo, hi, rate, H);
-        id = nfilt_++;
-        h_H_.insert(h_H_.end(), H.begin(), H.end());
+        if (free_.empty()) {
+            // cannot happen while every row but 0 is referenced by a channel; release this channel's own row first
+            const Params keep = p;
+            release(i);
+            cur_[i] = keep;
+            if (free_.empty()) { set_error("FirBank: filter table exhausted"); return CUTESDR_E_STATE; }
+        }
+        id = free_.back();
+        free_.pop_back();
+        rows_in_use_++;
+        row_key_[id] = key;
         ids_[key] = id;
+        jobs_.push_back(Job{lo, hi, rate, id, 0});
     }
-    h_id_[i] = id;
-    dirty_ = true;
+    if (id != h_id_[i]) {
+        refs_[id]++;
+        const int old = h_id_[i];
+        if (old > 0 && --refs_[old] == 0) {
+            ids_.erase(row_key_[old]);
+            free_.push_back(old);
+            rows_in_use_--;
+            for (size_t k = 0; k < jobs_.size(); k++) if (jobs_[k].row == old) { jobs_.erase(jobs_.begin() + k); break; }
+        }
+        h_id_[i] = id;
+        ids_dirty_ = true;
+    }
     return CUTESDR_OK;
 }
 
-int FirBank::upload()
+// queue pending designs and the channel -> row table in stream order (no synchronisation)
+int FirBank::flush()
 {
-    if (!dirty_) return CUTESDR_OK;
-    if (nfilt_ > cap_) {
-        cudaFree(d_H_);
-        cap_ = std::max(nfilt_, cap_ * 2);
-        CSDR_CK(cudaMalloc(&d_H_, (size_t)cap_ * kFirFft * sizeof(float2)));
+    if (!jobs_.empty()) {
+        const int n = (int)jobs_.size();
+        CSDR_TRY(stage_.upload(d_jobs_, jobs_.data(), (size_t)n * sizeof(Job), st_));
+        k_fir_design<<<n, 256, 2 * kFirFft * sizeof(double2), st_>>>(reinterpret_cast<const FirJob*>(d_jobs_), d_H_, d_h_);
+        lc_->n++;
+        CSDR_CK(cudaGetLastError());
+        jobs_.clear();
     }
-    CSDR_CK(cudaMemcpyAsync(d_H_, h_H_.data(), (size_t)nfilt_ * kFirFft * sizeof(float2), cudaMemcpyHostToDevice, st_));
-    CSDR_CK(cudaMemcpyAsync(d_id_, h_id_.data(), stride_ * sizeof(int), cudaMemcpyHostToDevice, st_));
-    CSDR_CK(cudaStreamSynchronize(st_));
-    dirty_ = false;
+    if (ids_dirty_) {
+        CSDR_TRY(stage_.upload(d_id_, h_id_.data(), (size_t)stride_ * sizeof(int), st_));
+        ids_dirty_ = false;
+    }
     return CUTESDR_OK;
 }
 
 int FirBank::run(const float2* d_ring, long long first_burst, int nb, float2* d_y, int y_stride)
 {
     if (nb <= 0) return CUTESDR_OK;
-    CSDR_TRY(upload());
+    CSDR_TRY(flush());
+    if (first_burst == 0) {
+        k_fir_first<<<nch_, 256, 0, st_>>>(d_ring, d_h_, d_id_, d_y, y_stride);
+        lc_->n++;
+        CSDR_CK(cudaGetLastError());
+        first_burst++;
+        nb--;
+        d_y += kBurst;
+        if (nb == 0) return CUTESDR_OK;
+    }
     dim3 grid(nch_, nb);
     k_fastfir<<<grid, 256, 0, st_>>>(d_ring, first_burst, d_H_, d_id_, d_tw_, d_y, y_stride);
     lc_->n++;

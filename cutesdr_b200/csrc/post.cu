@@ -736,6 +736,7 @@ void PostBank::set_am_bandwidth(int i, double bw)
     h_par_[(size_t)P_NTAPS * stride_ + i] = n;
     h_reset_[i] |= R_FIR;
     dirty_ = true;
+    taps_dirty_ = true;
 }
 
 void PostBank::set_fm(int i, int squelch_value, double fm_bw)
@@ -748,6 +749,7 @@ void PostBank::set_fm(int i, int squelch_value, double fm_bw)
         for (int k = 0; k < kFirMax; k++) h_taps_[(size_t)i * kFirMax + k] = k < n ? coef[k] : 0.0;
         h_par_[(size_t)P_NTAPS * stride_ + i] = n;
         h_reset_[i] |= R_FIR;
+        taps_dirty_ = true;
     }
     dirty_ = true;
 }
@@ -755,13 +757,15 @@ void PostBank::set_fm(int i, int squelch_value, double fm_bw)
 int PostBank::upload()
 {
     if (!dirty_) return CUTESDR_OK;
-    CSDR_CK(cudaMemcpyAsync(d_par_, h_par_.data(), h_par_.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
-    CSDR_CK(cudaMemcpyAsync(d_taps_, h_taps_.data(), h_taps_.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
-    CSDR_CK(cudaMemcpyAsync(d_mode_, h_mode_.data(), stride_ * sizeof(int), cudaMemcpyHostToDevice, st_));
+    // snapshots go through pinned staging buffers: no stream synchronisation, and the host vectors may be edited
+    // again right away
+    CSDR_TRY(stage_.upload(d_par_, h_par_.data(), h_par_.size() * sizeof(double), st_));
+    if (taps_dirty_) CSDR_TRY(stage_.upload(d_taps_, h_taps_.data(), h_taps_.size() * sizeof(double), st_));
+    taps_dirty_ = false;
+    CSDR_TRY(stage_.upload(d_mode_, h_mode_.data(), stride_ * sizeof(int), st_));
     bool any_reset = false;
     for (int r : h_reset_) any_reset |= (r != 0);
-    if (any_reset) CSDR_CK(cudaMemcpyAsync(d_reset_, h_reset_.data(), stride_ * sizeof(int), cudaMemcpyHostToDevice, st_));
-    CSDR_CK(cudaStreamSynchronize(st_));      // the host vectors may be edited again right away
+    if (any_reset) CSDR_TRY(stage_.upload(d_reset_, h_reset_.data(), stride_ * sizeof(int), st_));
     if (any_reset) {
         std::fill(h_reset_.begin(), h_reset_.end(), 0);
         need_reset_kernel_ = true;
@@ -802,8 +806,9 @@ int PostBank::read_smeter(int i, double* peak, double* ave)
     double pk = 0, av = 0;
     CSDR_CK(cudaMemcpyAsync(&pk, d_state_ + (size_t)S_SM_PEAK * stride_ + i, sizeof(double), cudaMemcpyDeviceToHost, st_));
     CSDR_CK(cudaMemcpyAsync(&av, d_state_ + (size_t)S_SM_AVE * stride_ + i, sizeof(double), cudaMemcpyDeviceToHost, st_));
-    // GetPeak resets the held peak (dsp/smeter.cpp:99-104)
-    CSDR_CK(cudaMemsetAsync(d_state_ + (size_t)S_SM_PEAK * stride_ + i, 0, sizeof(double), st_));
+    // GetPeak resets the held peak (dsp/smeter.cpp:99-104); GetAve does not (:109-112), so the reset only happens
+    // when the caller asks for the peak
+    if (peak) CSDR_CK(cudaMemsetAsync(d_state_ + (size_t)S_SM_PEAK * stride_ + i, 0, sizeof(double), st_));
     CSDR_CK(cudaStreamSynchronize(st_));
     if (peak) *peak = pk + 5.0;     // SMETER_CALIBRATION, dsp/smeter.cpp:45
     if (ave) *ave = av + 5.0;

@@ -74,7 +74,8 @@ private:
     std::vector<double> h_par_;     // [P_COUNT][stride]
     std::vector<double> h_taps_;    // [stride][kFirMax]
     std::vector<int> h_mode_, h_reset_;
-    bool dirty_ = true, need_reset_kernel_ = false;
+    bool dirty_ = true, taps_dirty_ = true, need_reset_kernel_ = false;
+    PinnedStage stage_;
     double* d_par_ = nullptr;
     double* d_taps_ = nullptr;
     int* d_mode_ = nullptr;

@@ -93,9 +93,15 @@ class ReceiverBank:
         return r.value
 
     def GetSMeter(self, ch):
+        """(peak, ave); reading the peak resets it (CSMeter::GetPeak, dsp/smeter.cpp:99-104)"""
         p, a = C.c_double(), C.c_double()
         check(self.L.cutesdr_bank_get_smeter(self.h, int(ch), C.byref(p), C.byref(a)))
         return p.value, a.value
+
+    def GetSMeterAve(self, ch):
+        a = C.c_double()
+        check(self.L.cutesdr_bank_get_smeter(self.h, int(ch), None, C.byref(a)))
+        return a.value
 
     def SetupNoiseProc(self, on, threshold, width_us):
         check(self.L.cutesdr_bank_set_noiseproc(self.h, int(bool(on)), float(threshold), float(width_us)))
@@ -190,9 +196,20 @@ class ReceiverBank:
         p = n_out_arr.ctypes.data_as(C.POINTER(C.c_int)) if n_out_arr is not None else None
         return check(self.L.cutesdr_bank_process_async_device(self.h, int(n_in), d_iq_ptr, src_stream, audio_ptr, int(audio_stride), p))
 
-    def process_device(self, d_iq_ptr, n_in, d_audio_ptr=None, audio_stride=0):
+    def process_async_raw_ptr(self, n_in, data_ptr, fmt, audio_ptr, audio_stride, n_out_arr=None):
+        """Pipelined one-block form for wire-format samples (fmt 1 = int16 pairs, 2 = packed int24)."""
+        p = n_out_arr.ctypes.data_as(C.POINTER(C.c_int)) if n_out_arr is not None else None
+        return check(self.L.cutesdr_bank_process_async_raw(self.h, int(n_in), data_ptr, int(fmt), audio_ptr, int(audio_stride), p))
+
+    def process_async_bcast_ptr(self, mgpu, n_in, iq_ptr_rank0, fmt, audio_ptr, audio_stride, n_out_arr=None):
+        """Multi-GPU pipelined form: rank 0 hands in the pinned host block, the library broadcasts it (NCCL)."""
+        p = n_out_arr.ctypes.data_as(C.POINTER(C.c_int)) if n_out_arr is not None else None
+        return check(self.L.cutesdr_bank_process_async_bcast(self.h, mgpu.h, int(n_in), iq_ptr_rank0, int(fmt), audio_ptr,
+                                                             int(audio_stride), p))
+
+    def process_device(self, d_iq_ptr, n_in, d_audio_ptr=None, audio_stride=0, fmt=0):
         m = C.c_int()
-        check(self.L.cutesdr_bank_process_device(self.h, d_iq_ptr, int(n_in), d_audio_ptr, int(audio_stride), C.byref(m)))
+        check(self.L.cutesdr_bank_process_device_raw(self.h, d_iq_ptr, int(fmt), int(n_in), d_audio_ptr, int(audio_stride), C.byref(m)))
         return m.value
 
     # --- test-bench taps (PROFILE_1..4)
@@ -211,6 +228,57 @@ class ReceiverBank:
         if profile < 4:
             return out[0::2].astype(np.complex64) + 1j * out[1::2].astype(np.complex64)
         return out
+
+
+class MultiGpu:
+    """cutesdr_mgpu: this process's rank in the multi-GPU receiver (one process per GPU). The 128-byte NCCL id is
+    created by rank 0 (`MultiGpu.unique_id()`) and handed to the other processes by the host application."""
+
+    def __init__(self, id_bytes, rank, world, device):
+        self.L = load_library()
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(id_bytes), 128) if id_bytes is not None else None
+        check(self.L.cutesdr_mgpu_init(C.byref(h), buf, int(rank), int(world), int(device)))
+        self.h = h
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def unique_id():
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        check(L.cutesdr_mgpu_unique_id(buf))
+        return buf.raw
+
+    def info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        nb, by = C.c_longlong(), C.c_longlong()
+        check(self.L.cutesdr_mgpu_info(self.h, C.byref(r), C.byref(w), C.byref(v), C.byref(nb), C.byref(by)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value, "blocks": nb.value, "bytes_broadcast": by.value}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cutesdr_mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def channel_slice(n_channels, rank, world):
+    """(first, count) of the contiguous channel slice rank `rank` owns (cutesdr_mgpu_channel_slice)."""
+    f, n = C.c_int(), C.c_int()
+    check(load_library().cutesdr_mgpu_channel_slice(int(n_channels), int(rank), int(world), C.byref(f), C.byref(n)))
+    return f.value, n.value
+
+
+def microbench(which, device=0):
+    """0 FP32 FMA TFLOP/s, 1 tcgen05 tf32 TFLOP/s, 2 tcgen05 f16 TFLOP/s, 3 HBM copy GB/s (cutesdr_microbench)."""
+    v = C.c_double()
+    check(load_library().cutesdr_microbench(int(device), int(which), C.byref(v)))
+    return v.value
 
 
 class CDemodulator(_Handle):
@@ -233,14 +301,13 @@ class CDemodulator(_Handle):
         return r.value
 
     def GetSMeterPeak(self):
-        p, a = C.c_double(), C.c_double()
-        check(self.L.cutesdr_demodulator_get_smeter(self.h, C.byref(p), C.byref(a)))
+        p = C.c_double()
+        check(self.L.cutesdr_demodulator_get_smeter(self.h, C.byref(p), None))
         return p.value
 
     def GetSMeterAve(self):
-        # NOTE: reads (and therefore resets) the held peak as well, unlike the reference's GetAve
-        p, a = C.c_double(), C.c_double()
-        check(self.L.cutesdr_demodulator_get_smeter(self.h, C.byref(p), C.byref(a)))
+        a = C.c_double()        # a NULL peak pointer leaves the held peak alone, like the reference's GetAve
+        check(self.L.cutesdr_demodulator_get_smeter(self.h, None, C.byref(a)))
         return a.value
 
     def ProcessData(self, iq, stereo=False):
@@ -324,6 +391,12 @@ class CFft(_Handle):
     def put_device(self, d_ptr, n):
         t = C.c_int()
         check(self.L.cutesdr_fft_put_device(self.h, int(n), d_ptr, C.byref(t)))
+        return t.value
+
+    def put_device_async(self, d_ptr, n, src_stream):
+        """stream-ordered PutInDisplayFFT of a device frame (no host synchronisation); src_stream: cudaStream_t"""
+        t = C.c_int()
+        check(self.L.cutesdr_fft_put_device_async(self.h, int(n), d_ptr, src_stream, C.byref(t)))
         return t.value
 
     def GetScreenIntegerFFTData(self, max_h, max_w, max_db, min_db, start, stop):

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "cutesdr_last_error": (C.c_char_p, []),
     "cutesdr_version": (C.c_char_p, []),
     "cutesdr_device_count": (C.c_int, [_ip]),
+    "cutesdr_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
     "cutesdr_bank_create": (C.c_int, [_pp, C.c_int, C.c_double, C.c_int]),
     "cutesdr_bank_destroy": (None, [_vp]),
     "cutesdr_bank_set_demod": (C.c_int, [_vp, C.c_int, C.c_int, _info]),
@@ -50,7 +51,14 @@ PROTOTYPES = {
     "cutesdr_bank_process_raw": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_async_raw": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_async_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _ip]),
+    "cutesdr_mgpu_unique_id": (C.c_int, [_vp]),
+    "cutesdr_mgpu_init": (C.c_int, [_pp, _vp, C.c_int, C.c_int, C.c_int]),
+    "cutesdr_mgpu_destroy": (None, [_vp]),
+    "cutesdr_mgpu_info": (C.c_int, [_vp, _ip, _ip, _ip, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "cutesdr_mgpu_channel_slice": (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _ip]),
+    "cutesdr_bank_process_async_bcast": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_device": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _ip]),
+    "cutesdr_bank_process_device_raw": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_synchronize": (C.c_int, [_vp]),
     "cutesdr_bank_join": (C.c_int, [_vp]),
     "cutesdr_bank_last_block": (C.c_int, [_vp, _pp, _ip]),
@@ -83,6 +91,7 @@ PROTOTYPES = {
     "cutesdr_fft_put": (C.c_int, [_vp, C.c_int, _dp, _ip]),
     "cutesdr_fft_put_f32": (C.c_int, [_vp, C.c_int, _fp, _ip]),
     "cutesdr_fft_put_device": (C.c_int, [_vp, C.c_int, _vp, _ip]),
+    "cutesdr_fft_put_device_async": (C.c_int, [_vp, C.c_int, _vp, _vp, _ip]),
     "cutesdr_fft_launch_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "cutesdr_fft_get_screen": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _i32, _ip]),
     "cutesdr_fft_get_plot": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _i32, _i32, _ip]),

@@ -14,13 +14,16 @@ def carrier_grid(nch, spacing):
     return (np.arange(nch) - nch / 2 + 0.5) * spacing
 
 
-def channel_tones(c):
-    return 400.0 + 7.0 * (c % 97), 1500.0 + 11.0 * (c % 89)
+def channel_tones(c, snap=None):
+    f1, f2 = 400.0 + 7.0 * (c % 97), 1500.0 + 11.0 * (c % 89)
+    if snap:
+        f1, f2 = np.rint(f1 / snap) * snap, np.rint(f2 / snap) * snap
+    return f1, f2
 
 
-def baseband(mode, c, t):
-    """Complex baseband modulation s_c(t) for channel index c."""
-    f1, f2 = channel_tones(c)
+def baseband(mode, c, t, snap=None):
+    """Complex baseband modulation s_c(t) for channel index c (snap: tone frequencies rounded to multiples of it)."""
+    f1, f2 = channel_tones(c, snap)
     if mode in (DEMOD_AM, DEMOD_SAM):
         return (1.0 + 0.5 * np.cos(2 * np.pi * f1 * t) + 0.3 * np.cos(2 * np.pi * f2 * t)).astype(np.complex128)
     if mode == DEMOD_FM:
@@ -31,6 +34,8 @@ def baseband(mode, c, t):
     if mode in (DEMOD_CWU, DEMOD_CWL):
         # carrier plus a weak +-(60 + c mod 50) Hz sideband: both inside a +-250 Hz CW filter
         fo = 60.0 + (c % 50)
+        if snap:
+            fo = np.rint(fo / snap) * snap
         return 1.0 + 0.2 * np.exp(2j * np.pi * fo * t)
     sign = 1.0 if mode == DEMOD_USB else -1.0
     return 0.5 * np.exp(sign * 2j * np.pi * f1 * t) + 0.5 * np.exp(sign * 2j * np.pi * f2 * t)
@@ -58,6 +63,49 @@ def syn_iq(fs, n, modes, carriers, seed, n0=0, noise_db=-40.0, total_amp=16000.0
         acc += sigma * (rng.standard_normal(m) + 1j * rng.standard_normal(m))
         out[s:s + m] = acc.astype(np.complex64)
     return out
+
+
+def syn_iq_fft(fs, n, modes, carriers, seed, decim, noise_db=-40.0, total_amp=16000.0, active=None, impulses=0):
+    """SYN-IQ for the full-size banks (1024-4096 carriers x 20-40 M samples), built in the frequency domain:
+    every channel's modulation s_c is evaluated at the low rate fs/decim (n/decim samples), transformed, and its
+    spectrum placed at the carrier's bin of ONE n-point inverse FFT -- the same x[n] = sum_c A s_c e^{j(2 pi f_c n/fs + p_c)}
+    + noise as syn_iq, with s_c band-limited-interpolated instead of evaluated per wideband sample (minutes -> seconds).
+    The stream is exactly periodic in n samples: carriers and modulation tones are snapped to multiples of fs/n, and the
+    snapped carriers are returned (tune the receivers to those). Every carrier gets a seeded random phase p_c, so a
+    thousand carriers do not add up coherently at n = 0 and the sum stays inside the int16 range.
+    `active` limits the carriers that are actually present (default: all); `impulses` single-sample spikes of
+    amplitude 30000 are added at seeded positions (noise-blanker stimulus). decim must divide n, and fs/decim must
+    cover the widest modulation (FM: ~ +-5 kHz). Returns (complex64[n], carriers)."""
+    from scipy import fft as sfft
+    nch = len(modes)
+    assert n % decim == 0
+    m = n // decim
+    A = total_amp / np.sqrt(nch)
+    sigma = A * 10.0 ** (noise_db / 20.0)
+    df = fs / n
+    kbin = np.rint(np.asarray(carriers, dtype=np.float64) / df).astype(np.int64)
+    snapped = kbin * df
+    rng = np.random.Generator(np.random.PCG64([seed, n]))
+    phase = rng.uniform(0.0, 2.0 * np.pi, nch)
+    X = np.zeros(n, dtype=np.complex128)
+    t = np.arange(m, dtype=np.float64) * (decim / fs)
+    q = np.fft.fftfreq(m, 1.0 / m).astype(np.int64)          # baseband bin numbers 0..m/2-1, -m/2..-1
+    for c in (range(nch) if active is None else active):
+        b = baseband(modes[c], c, t, snap=df) * np.exp(1j * phase[c])
+        X[(kbin[c] + q) % n] += sfft.fft(b) * (A * n / m)
+    x = sfft.ifft(X, workers=-1, overwrite_x=True)
+    del X
+    out = np.empty(n, dtype=np.complex64)
+    step = 1 << 22
+    for s0 in range(0, n, step):
+        k = min(step, n - s0)
+        g = rng.standard_normal((k, 2), dtype=np.float32)
+        out[s0:s0 + k] = x[s0:s0 + k].astype(np.complex64)
+        out[s0:s0 + k] += np.float32(sigma) * g.view(np.complex64)[:, 0]
+    if impulses:
+        pos = np.sort(rng.choice(n, size=impulses, replace=False))
+        out[pos] += np.complex64(30000.0)
+    return out, snapped
 
 
 def snr_db(ref, test):

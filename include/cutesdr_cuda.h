@@ -58,6 +58,11 @@ const char* cutesdr_last_error(void);
 const char* cutesdr_version(void);
 int cutesdr_device_count(int* n);
 
+/* Device microbenchmarks behind bench.py's roofline denominators (no reference counterpart; SURVEY.md 8d asks for
+ * them): which = 0 FP32 FMA issue peak [TFLOP/s], 1 tcgen05 kind::tf32 dense peak [TFLOP/s], 2 tcgen05 kind::f16
+ * dense peak [TFLOP/s], 3 HBM copy bandwidth [GB/s, read + write]. Each takes a few milliseconds. */
+int cutesdr_microbench(int device, int which, double* value);
+
 /* ======================================================================================
  * Receiver bank: N virtual receivers ( = N independent CDemodulator objects,
  * dsp/demodulator.h:56-100) fed from ONE wideband complex stream.
@@ -76,7 +81,8 @@ int cutesdr_bank_set_demod_freq(cutesdr_bank* b, int ch, double freq);
 int cutesdr_bank_get_output_rate(cutesdr_bank* b, int ch, double* rate);
 /* m_InBufLimit: input samples per DSP block                   dsp/demodulator.cpp:145-146 */
 int cutesdr_bank_block_length(cutesdr_bank* b, int* n);
-/* GetSMeterPeak()/GetSMeterAve() (peak is reset on read)      dsp/demodulator.h:64-65 */
+/* GetSMeterPeak()/GetSMeterAve(): either pointer may be NULL. Reading the peak resets the held
+ * peak (CSMeter::GetPeak, dsp/smeter.cpp:99-104); a NULL `peak` leaves it alone (GetAve).   dsp/demodulator.h:64-65 */
 int cutesdr_bank_get_smeter(cutesdr_bank* b, int ch, double* peak, double* ave);
 
 /* CSdrInterface::SetupNoiseProc -> CNoiseProc::SetupBlanker on the shared wideband stream
@@ -120,6 +126,27 @@ int cutesdr_bank_process_async_raw(cutesdr_bank* b, int n_in, const void* data, 
 int cutesdr_bank_process_async_device(cutesdr_bank* b, int n_in, const void* d_iq, void* src_stream, float* audio,
                                       int audio_stride, int* n_out);
 
+/* ---- multi-GPU (one process per GPU). Channels shard across ranks -- every rank owns a bank with its
+ * slice of the channel list -- and the only exchange is the wideband block: rank 0 receives it from the host and it is
+ * broadcast with NCCL over NVLink / NVSwitch. No reference counterpart (the reference is single-threaded CPU code); the
+ * per-rank calls are the same CDemodulator-shaped calls as above. NCCL is loaded at run time (libnccl.so.2).
+ *   rank 0:     cutesdr_mgpu_unique_id(id)  -> hand the 128 bytes to the other processes (MPI, a socket, torch.distributed ...)
+ *   every rank: cutesdr_mgpu_init(&m, id, rank, world, device); cutesdr_mgpu_channel_slice(n, rank, world, &first, &count);
+ *               bank of `count` channels; then per DSP block cutesdr_bank_process_async_bcast(...). */
+typedef struct cutesdr_mgpu cutesdr_mgpu;
+int cutesdr_mgpu_unique_id(void* id128);
+int cutesdr_mgpu_init(cutesdr_mgpu** out, const void* id128, int rank, int world, int device);
+void cutesdr_mgpu_destroy(cutesdr_mgpu* m);
+int cutesdr_mgpu_info(cutesdr_mgpu* m, int* rank, int* world, int* nccl_version, long long* blocks, long long* bytes_bcast);
+int cutesdr_mgpu_channel_slice(int n_channels, int rank, int world, int* first, int* count);
+/* cutesdr_bank_process_async_raw for one DSP block whose samples only rank 0 has: iq_rank0 (PINNED host memory, format
+ * fmt, n_in == block_length; ignored on the other ranks) is copied to rank 0's GPU in 1 MiB chunks and every chunk is
+ * broadcast as soon as it has landed (the copy of chunk k+1 overlaps the broadcast of chunk k), directly into the
+ * bank's input slot on every rank; the block's kernels, the audio D2H and the host-buffer contract are those of
+ * cutesdr_bank_process_async. Every rank must make the same sequence of calls. world == 1 degenerates to process_async. */
+int cutesdr_bank_process_async_bcast(cutesdr_bank* b, cutesdr_mgpu* m, int n_in, const void* iq_rank0, int fmt, float* audio,
+                                     int audio_stride, int* n_out);
+
 /* Pipelined form of cutesdr_bank_process for exactly one DSP block per call (n_in == block_length,
  * iq and audio in PINNED host memory): the call only queues work -- the H2D copy of this block runs on
  * a copy stream under the previous block's kernels, the D2H of finished audio on another. n_out[] is
@@ -134,6 +161,9 @@ int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float
  * stream; *n_out_max is known on return (burst timing is deterministic). */
 int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, void* d_audio, int audio_stride,
                                 int* n_out_max);
+/* same with the device block still in a wire format (fmt as in cutesdr_bank_process_raw) */
+int cutesdr_bank_process_device_raw(cutesdr_bank* b, const void* d_data, int fmt, int n_in, void* d_audio, int audio_stride,
+                                    int* n_out_max);
 /* process_device queues work on the bank's main stream (decimation) and on internal side streams
  * (FIR / AGC / demodulator bursts, which overlap the next blocks' decimation). synchronize waits
  * for all of it; join only orders the main stream after all queued burst work, so that an event
@@ -154,7 +184,8 @@ int cutesdr_bank_launch_count(cutesdr_bank* b, long long* n);
  * kernel_time returns the accumulated milliseconds and launch count since the last read. */
 int cutesdr_bank_kernel_timing(cutesdr_bank* b, int enable);
 int cutesdr_bank_kernel_time(cutesdr_bank* b, int which, double* ms_total, long long* launches);
-/* What bounds kernel `which` (0): on_tensor_cores = 1 when every chain group runs kernel 1T (the NCO mix + first
+/* What bounds kernel 1 (which = 0; which = 1 asks instead whether every group runs the fp16-operand form of
+ * kernel 1T, kind::f16): on_tensor_cores = 1 when every chain group runs kernel 1T (the NCO mix + first
  * four CIC3 stages of dsp/downconvert.cpp:186-263,425-460 as a tcgen05 GEMM); flops_per_block = the GEMM's
  * multiply-adds x 2 per DSP block, each real product counted once (the 3 tf32 partial products that emulate one
  * fp32 product are one). bench.py's roofline line is built from this and cutesdr_bank_kernel_time. */
@@ -214,6 +245,11 @@ int cutesdr_fft_put(cutesdr_fft* h, int n, const double* in, int* total_count);
 int cutesdr_fft_put_f32(cutesdr_fft* h, int n, const float* in, int* total_count);
 /* same, frame already in device memory (complex64[n]) -- e.g. a slice of the bank's wideband block */
 int cutesdr_fft_put_device(cutesdr_fft* h, int n, const void* d_in, int* total_count);
+/* same, stream-ordered and without host synchronisation (the concurrent spectrum of a running bank): the frame is
+ * taken over in order with respect to src_stream (a cudaStream_t, e.g. cutesdr_bank_stream) -- it may be overwritten
+ * as soon as the call returns --, the transform runs on the object's own stream, and the overload flag / averages are
+ * picked up by the next GetScreenIntegerFFTData / get_plot, which waits for this object's work only */
+int cutesdr_fft_put_device_async(cutesdr_fft* h, int n, const void* d_in, void* src_stream, int* total_count);
 int cutesdr_fft_launch_count(cutesdr_fft* h, long long* n);
 /* GetScreenIntegerFFTData(...) -> out[max_width], *overload   dsp/fft.cpp:308-410 */
 int cutesdr_fft_get_screen(cutesdr_fft* h, int max_height, int max_width, double max_db, double min_db,

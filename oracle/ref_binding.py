@@ -131,6 +131,17 @@ def load(big=False):
     sig("ref_demod_run", C.c_long, vp, C.c_long, C.c_void_p, C.c_int, C.c_int, _dp, C.c_long, C.c_int)
     sig("ref_bench_chains", C.c_double, C.c_int, _ip, _dp, _ip, C.c_double, C.c_long, C.POINTER(C.c_float),
         C.c_int, C.c_int, _dp)
+    fp = C.POINTER(C.c_float)
+    sig("ref_chains_new", vp, C.c_int, _ip, _dp, _ip, C.c_double, C.c_double, C.c_int)
+    sig("ref_chains_delete", None, vp)
+    sig("ref_chains_set_freq", None, vp, C.c_int, C.c_double)
+    sig("ref_chains_set_demod", None, vp, C.c_int, C.c_int, _ip)
+    sig("ref_chains_smeter_ave", C.c_double, vp, C.c_int)
+    sig("ref_chains_run", C.c_double, vp, C.c_long, fp, C.c_int)
+    sig("ref_chains_out_size", C.c_long, vp, C.c_int)
+    sig("ref_chains_out_read", None, vp, C.c_int, _dp, C.c_int)
+    sig("ref_chains_checksum", C.c_double, vp)
+    sig("ref_noiseproc_process_f32", C.c_double, vp, C.c_long, fp)
     _libs[big] = L
     return L
 
@@ -508,3 +519,55 @@ def bench_chains(modes, freqs, infos_by_mode, in_rate, iq_c64, nthreads, resampl
                            float(in_rate), len(iq), iq.ctypes.data_as(C.POINTER(C.c_float)), int(nthreads),
                            int(resample48k), C.byref(cs))
     return t, cs.value
+
+
+class RefChainSet:
+    """N persistent CDemodulator (+ CFractResampler) chains on one wideband stream, run over std::threads. Objects are
+    built here (outside any timed region) and keep their state across run() calls, like a receiver that is running."""
+
+    def __init__(self, modes, freqs, infos, in_rate, audio_rate=0.0, keep_output=True, big=False):
+        self.L = load(big)
+        self.n = len(modes)
+        m = np.ascontiguousarray(modes, dtype=np.int32)
+        f = np.ascontiguousarray(freqs, dtype=np.float64)
+        inf = np.concatenate([info_array(i) for i in infos]).astype(np.int32)
+        self.h = self.L.ref_chains_new(self.n, m.ctypes.data_as(_ip), _d(f), inf.ctypes.data_as(_ip), float(in_rate),
+                                       float(audio_rate), int(bool(keep_output)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ref_chains_delete(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def run(self, iq_c64, nthreads):
+        """Feeds the complex64 samples to every chain; returns the seconds the threaded section took."""
+        iq = np.ascontiguousarray(iq_c64, dtype=np.complex64)
+        return self.L.ref_chains_run(self.h, len(iq), iq.ctypes.data_as(C.POINTER(C.c_float)), int(nthreads))
+
+    def output(self, c, clear=True):
+        n = self.L.ref_chains_out_size(self.h, int(c))
+        out = np.empty(n, dtype=np.float64)
+        self.L.ref_chains_out_read(self.h, int(c), _d(out), int(clear))
+        return out
+
+    def SetDemodFreq(self, c, f):
+        self.L.ref_chains_set_freq(self.h, int(c), float(f))
+
+    def SetDemod(self, c, mode, info):
+        a = info_array(info)
+        self.L.ref_chains_set_demod(self.h, int(c), int(mode), a.ctypes.data_as(_ip))
+
+    def GetSMeterAve(self, c):
+        return self.L.ref_chains_smeter_ave(self.h, int(c))
+
+    def checksum(self):
+        return self.L.ref_chains_checksum(self.h)
+
+
+def blank_stream_f32(nb, iq_c64):
+    """CNoiseProc::ProcessBlanker over a complex64 stream, in place (<= 4096 samples per call). Returns seconds."""
+    assert iq_c64.dtype == np.complex64 and iq_c64.flags.c_contiguous
+    return nb.L.ref_noiseproc_process_f32(nb.h, len(iq_c64), iq_c64.ctypes.data_as(C.POINTER(C.c_float)))

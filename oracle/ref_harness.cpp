@@ -276,4 +276,103 @@ double ref_bench_chains(int nch, const int* modes, const double* freqs, const in
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+
+// ---------------- persistent multi-channel chain set ----------------
+// N independent CDemodulator chains (+ optional CFractResampler to `audio_rate`) that live across calls, so a
+// benchmark can build them once (object construction, the 1025-tap design and CFractResampler::Init's 280 001
+// sin/cos are NOT in the timed region) and a parity test can stream 0.2 s of signal through a subset of a big
+// bank on all host cores and read every channel's audio back.
+struct ChainSet {
+    int nch;
+    double in_rate, audio_rate;
+    int keep;
+    std::vector<CDemodulator*> d;
+    std::vector<CFractResampler*> rs;
+    std::vector<double> orate;
+    std::vector<std::vector<double> > out;
+    std::vector<double> sums;
+};
+
+void* ref_chains_new(int nch, const int* modes, const double* freqs, const int* infos14, double in_rate, double audio_rate, int keep_output) {
+    ChainSet* s = new ChainSet();
+    s->nch = nch; s->in_rate = in_rate; s->audio_rate = audio_rate; s->keep = keep_output;
+    s->d.resize(nch); s->rs.assign(nch, (CFractResampler*)NULL); s->orate.resize(nch); s->out.resize(nch); s->sums.assign(nch, 0.0);
+    for (int c = 0; c < nch; c++) {
+        CDemodulator* d = znew<CDemodulator>();
+        d->SetInputSampleRate(in_rate);
+        d->SetDemod(modes[c], make_info(infos14 + 14 * c));
+        d->SetDemodFreq(freqs[c]);
+        s->d[c] = d;
+        s->orate[c] = d->GetOutputRate();
+        if (audio_rate > 0) { s->rs[c] = znew<CFractResampler>(); s->rs[c]->Init(8192); }
+    }
+    return s;
+}
+void ref_chains_delete(void* h) {
+    ChainSet* s = (ChainSet*)h;
+    if (!s) return;
+    for (int c = 0; c < s->nch; c++) { zdelete(s->d[c]); if (s->rs[c]) zdelete(s->rs[c]); }
+    delete s;
+}
+void ref_chains_set_freq(void* h, int c, double f) { ((ChainSet*)h)->d[c]->SetDemodFreq(f); }
+void ref_chains_set_demod(void* h, int c, int mode, const int* info14) { ((ChainSet*)h)->d[c]->SetDemod(mode, make_info(info14)); }
+double ref_chains_smeter_ave(void* h, int c) { return ((ChainSet*)h)->d[c]->GetSMeterAve(); }
+// Feed n complex64 samples to every chain in 256-sample packets (interface/netiobase.cpp:593), channels
+// partitioned over nthreads std::threads. Returns the wall-clock seconds of the threaded section.
+double ref_chains_run(void* h, long n, const float* iq, int nthreads) {
+    ChainSet* s = (ChainSet*)h;
+    if (nthreads < 1) nthreads = 1;
+    auto work = [&](int t) {
+        ensure_bench();
+        g_pTestBench->m_CaptureMask = 0;
+        std::vector<TYPECPX> pkt(256);
+        std::vector<double> obuf(16384), rbuf(32768);
+        for (int c = t; c < s->nch; c += nthreads) {
+            CDemodulator* d = s->d[c];
+            CFractResampler* rs = s->rs[c];
+            double acc = 0.0;
+            for (long i = 0; i < n; i += 256) {
+                int m = (int)((n - i) < 256 ? (n - i) : 256);
+                const float* f = iq + 2 * i;
+                for (int k = 0; k < m; k++) { pkt[k].re = f[2 * k]; pkt[k].im = f[2 * k + 1]; }
+                int r = d->ProcessData(m, pkt.data(), (TYPEREAL*)obuf.data());
+                const double* o = obuf.data();
+                if (r > 0 && rs) { r = rs->Resample(r, s->orate[c] / s->audio_rate, obuf.data(), rbuf.data()); o = rbuf.data(); }
+                for (int k = 0; k < r; k++) acc += o[k];
+                if (s->keep && r > 0) s->out[c].insert(s->out[c].end(), o, o + r);
+            }
+            s->sums[c] += acc;
+        }
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+long ref_chains_out_size(void* h, int c) { return (long)((ChainSet*)h)->out[c].size(); }
+void ref_chains_out_read(void* h, int c, double* out, int clear) {
+    std::vector<double>& v = ((ChainSet*)h)->out[c];
+    if (!v.empty()) memcpy(out, v.data(), v.size() * sizeof(double));
+    if (clear) std::vector<double>().swap(v);
+}
+double ref_chains_checksum(void* h) { ChainSet* s = (ChainSet*)h; double a = 0; for (int c = 0; c < s->nch; c++) a += s->sums[c]; return a; }
+
+// noise blanker over a complex64 stream (shared wideband pre-processing, interface/sdrinterface.cpp:884): in place,
+// <= 4096 samples per call. Returns seconds.
+double ref_noiseproc_process_f32(void* h, long n, float* io) {
+    CNoiseProc* p = (CNoiseProc*)h;
+    std::vector<TYPECPX> buf(4096);
+    auto t0 = std::chrono::steady_clock::now();
+    for (long i = 0; i < n; i += 4096) {
+        int m = (int)((n - i) < 4096 ? (n - i) : 4096);
+        float* f = io + 2 * i;
+        for (int k = 0; k < m; k++) { buf[k].re = f[2 * k]; buf[k].im = f[2 * k + 1]; }
+        p->ProcessBlanker(m, buf.data(), buf.data());
+        for (int k = 0; k < m; k++) { f[2 * k] = (float)buf[k].re; f[2 * k + 1] = (float)buf[k].im; }
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 } // extern "C"

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cutesdr_b200.sharding import broadcast_block, shard_bounds, shard_channels
+from cutesdr_b200.sharding import exchange_unique_id, shard_bounds, shard_channels
 
 
 def test_shard_bounds_partition():
@@ -30,11 +30,11 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        L = 19968
-        rng = np.random.default_rng(5)
-        block = torch.from_numpy(rng.standard_normal(2 * L).astype(np.float32)) if rank == 0 else torch.zeros(2 * L)
-        broadcast_block(block, src=0)
-        ref = torch.from_numpy(np.random.default_rng(5).standard_normal(2 * L).astype(np.float32))
+        # the one thing the host application does itself: hand rank 0's 128-byte communicator id to every rank
+        # (the id is made by NCCL on a GPU box; any 128 bytes exercise the exchange here)
+        uid = exchange_unique_id(lambda: bytes(range(128)), rank, world)
+        block = torch.frombuffer(bytearray(uid), dtype=torch.uint8)
+        ref = torch.arange(128, dtype=torch.uint8)
         chans = shard_channels(list(range(1000)), rank, world)
         # every rank reports its slice; rank 0 checks they tile the channel list
         gathered = [None] * world
@@ -60,6 +60,6 @@ def test_two_rank_broadcast_and_sharding():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, same, gathered, tmax in res:
-        assert same, "rank %d did not receive the broadcast block" % rank
+        assert same, "rank %d did not receive the communicator id" % rank
         assert gathered == [(0, 499, 500), (500, 999, 500)]
         assert tmax == 2.0
