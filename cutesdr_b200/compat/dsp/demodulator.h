@@ -4,6 +4,7 @@
 #define CUTESDR_B200_COMPAT_DEMODULATOR_H
 #include "dsp/datatypes.h"
 #include "dsp/cutesdr_shim.h"
+#include "dsp/iir.h"      // the reference pulls CIir in here (demodulator.h -> fmdemod.h -> iir.h); interface/sdrinterface.h:178 relies on it
 #define DEMOD_AM 0
 #define DEMOD_SAM 1
 #define DEMOD_FM 2

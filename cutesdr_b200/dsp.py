@@ -498,3 +498,35 @@ class CNoiseProc(_Handle):
         out = np.empty_like(buf)
         check(self.L.cutesdr_noiseproc_process(self.h, len(x), _dptr(buf), _dptr(out)))
         return _f64_to_cpx(out, len(x))
+
+
+class CIir(_Handle):
+    """dsp/iir.h:16-40 -- one direct-form-2 biquad (InitLP/HP/BP/BR, ProcessFilter real or complex)."""
+    _create, _destroy = "cutesdr_iir_create", "cutesdr_iir_destroy"
+
+    def _init(self, kind, f0, q, rate):
+        check(self.L.cutesdr_iir_init(self.h, kind, float(f0), float(q), float(rate)))
+
+    def InitLP(self, f0, q, rate):
+        self._init(0, f0, q, rate)
+
+    def InitHP(self, f0, q, rate):
+        self._init(1, f0, q, rate)
+
+    def InitBP(self, f0, q, rate):
+        self._init(2, f0, q, rate)
+
+    def InitBR(self, f0, q, rate):
+        self._init(3, f0, q, rate)
+
+    def ProcessFilter(self, x):
+        x = np.asarray(x)
+        if np.iscomplexobj(x):
+            buf = _cpx_to_f64(x)
+            out = np.empty_like(buf)
+            check(self.L.cutesdr_iir_process_cpx(self.h, len(x), _dptr(buf), _dptr(out)))
+            return _f64_to_cpx(out, len(x))
+        buf = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(buf)
+        check(self.L.cutesdr_iir_process_real(self.h, len(buf), _dptr(buf), _dptr(out)))
+        return out

@@ -110,6 +110,11 @@ PROTOTYPES = {
     "cutesdr_resampler_cpx": (C.c_int, [_vp, C.c_int, C.c_double, _dp, _dp]),
     "cutesdr_resampler_mono16": (C.c_int, [_vp, C.c_int, C.c_double, _dp, _i16, C.c_double]),
     "cutesdr_resampler_stereo16": (C.c_int, [_vp, C.c_int, C.c_double, _dp, _i16, C.c_double]),
+    "cutesdr_iir_create": (C.c_int, [_pp, C.c_int]),
+    "cutesdr_iir_destroy": (None, [_vp]),
+    "cutesdr_iir_init": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double]),
+    "cutesdr_iir_process_real": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "cutesdr_iir_process_cpx": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "cutesdr_noiseproc_create": (C.c_int, [_pp, C.c_int]),
     "cutesdr_noiseproc_destroy": (None, [_vp]),
     "cutesdr_noiseproc_setup": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double]),

@@ -292,6 +292,21 @@ int cutesdr_resampler_cpx(cutesdr_resampler* h, int n, double rate, const double
 int cutesdr_resampler_mono16(cutesdr_resampler* h, int n, double rate, const double* in, int16_t* out, double gain);
 int cutesdr_resampler_stereo16(cutesdr_resampler* h, int n, double rate, const double* in, int16_t* out, double gain);
 
+/* ---- CIir, dsp/iir.h:16-40 (one direct-form-2 biquad; embedded in CSdrInterface, interface/sdrinterface.h:178) ---- */
+#define CUTESDR_IIR_LP 0
+#define CUTESDR_IIR_HP 1
+#define CUTESDR_IIR_BP 2
+#define CUTESDR_IIR_BR 3
+typedef struct cutesdr_iir cutesdr_iir;
+/* CIir(): InitBR(25000, 1000, 100000)                          dsp/iir.cpp:77-80 */
+int cutesdr_iir_create(cutesdr_iir** out, int device);
+void cutesdr_iir_destroy(cutesdr_iir* h);
+/* InitLP / InitHP / InitBP / InitBR(F0Freq, FilterQ, SampleRate); clears the delay storage   dsp/iir.cpp:86-163 */
+int cutesdr_iir_init(cutesdr_iir* h, int kind, double f0, double q, double sample_rate);
+/* ProcessFilter(InLength, in, out) real / complex (interleaved doubles); returns n           dsp/iir.cpp:169-201 */
+int cutesdr_iir_process_real(cutesdr_iir* h, int n, const double* in, double* out);
+int cutesdr_iir_process_cpx(cutesdr_iir* h, int n, const double* in, double* out);
+
 /* ---- CNoiseProc, dsp/noiseproc.h:23-53 ---- */
 typedef struct cutesdr_noiseproc cutesdr_noiseproc;
 int cutesdr_noiseproc_create(cutesdr_noiseproc** out, int device);
