@@ -90,18 +90,22 @@ int cutesdr_bank::rebuild()
         if (!ch[c].configured) { set_error("channel %d has no demodulator (call set_demod first)", c); return CUTESDR_E_STATE; }
         by_bw[ch[c].max_bw].push_back(c);
     }
-    if (stereo && audio_rate > 0.0) {
-        set_error("stereo output together with the bank resampler is not supported (resample the stereo stream with cutesdr_resampler_stereo16)");
-        return CUTESDR_E_ARG;
-    }
-    int newL = -1;
+    // DSP block length. The reference takes m_InBufLimit = 10 ms of input rounded down to a multiple of 256
+    // (dsp/demodulator.cpp:145-146) although its decimator asks for a multiple of 2^stages
+    // (dsp/downconvert.cpp:182-183): at e.g. exactly 100e6 sps (999 936 samples, 11 stages) its deeper stages then get
+    // odd lengths and drop / re-read a sample at every block edge. The bank rounds the same 10 ms down to a multiple
+    // of 2^stages of its deepest ladder instead, so ANY input rate is accepted and the decimated stream is the clean
+    // one; whenever the reference's own length already is such a multiple the two are identical.
+    int newL = -1, max_stages = 0;
     for (auto& kv : by_bw) {
         std::vector<int> lens;
         double orate = plan_stages(in_rate, kv.first, lens);
         int lim = block_limit(in_rate, orate);
+        max_stages = std::max(max_stages, (int)lens.size());
         if (newL < 0) newL = lim;
         else if (lim != newL) { set_error("channel groups disagree on the DSP block length (%d vs %d)", lim, newL); return CUTESDR_E_ARG; }
     }
+    if (newL > 0 && max_stages > 8) newL &= ~((1 << max_stages) - 1);
     if (newL <= 0) { set_error("input rate %g too low: DSP block length is %d", in_rate, newL); return CUTESDR_E_ARG; }
     if (newL != L) {
         L = newL;
@@ -147,7 +151,8 @@ int cutesdr_bank::rebuild()
         CSDR_CK(cudaMemcpy(g->d_local_map, ident.data(), stride * sizeof(int), cudaMemcpyHostToDevice));
         if (audio_rate > 0.0) {
             g->rs.reset(new ResamplerBank());
-            CSDR_TRY(g->rs->init(n, kMaxBurstSamples, g->st_post, &lc));
+            // stereo: rows of (left,right) pairs through the TYPECPX form of the resampler (dsp/fractresampler.cpp:194-249)
+            CSDR_TRY(g->rs->init(n, kMaxBurstSamples, g->st_post, &lc, stereo ? 2 : 1));
         }
         const int gi = (int)groups.size();
         for (int i = 0; i < n; i++) { ch[g->chans[i]].group = gi; ch[g->chans[i]].local = i; }
@@ -200,7 +205,7 @@ int cutesdr_bank::run_block(const void* d_block, int fmt, float* d_audio_out, in
             // demod audio goes into the resampler's input rows, the resampler writes the user rows
             CSDR_TRY(g.post.run(n, g.rs->in_ptr(), g.rs->in_stride(), 0, g.d_local_map));
             const double rate = g.dec.out_rate() / audio_rate;     // interface/soundout.cpp:204
-            if (d_audio_out && off + g.rs->max_out(n, rate) > audio_stride) {
+            if (d_audio_out && (stereo ? 2 : 1) * (off + g.rs->max_out(n, rate)) > audio_stride) {
                 set_error("audio_stride %d too small for %d resampled samples at offset %d", audio_stride, g.rs->max_out(n, rate), off);
                 return CUTESDR_E_ARG;
             }
@@ -498,6 +503,53 @@ int cutesdr_bank_process_raw(cutesdr_bank* b, int n_in, const void* data, int fm
 int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audio, int audio_stride, int* n_out)
 {
     return bank_process_host(b, n_in, iq, 0, audio, audio_stride, n_out);
+}
+
+// CUdpThread::OnreadyRead (interface/netiobase.cpp:464-534) + CIQDataThread::run (:571-600): datagrams of 1028 bytes
+// (256 int16 I/Q pairs) or 1444 bytes (240 packed int24 pairs) after a 4-byte header whose bytes 2-3 are a little-endian
+// sequence number. The sequence bookkeeping is the reference's, statement for statement (16-bit wrap skips 0, a 0 from
+// the radio restarts the count, the gap is added as a signed 16-bit difference); payloads go on in their wire format,
+// so the unpack still happens inside kernel 1's tile load.
+int cutesdr_bank_process_packets(cutesdr_bank* b, int n_packets, const void* packets, int packet_bytes, float* audio,
+                                 int audio_stride, int* n_out)
+{
+    if (!b || n_packets < 0 || (n_packets > 0 && !packets)) { set_error("bank_process_packets: bad arguments"); return CUTESDR_E_ARG; }
+    int fmt, payload;
+    if (packet_bytes == CUTESDR_PKT_LENGTH_16) { fmt = CUTESDR_FMT_CS16; payload = CUTESDR_PKT_LENGTH_16 - 4; }
+    else if (packet_bytes == CUTESDR_PKT_LENGTH_24) { fmt = CUTESDR_FMT_CS24; payload = CUTESDR_PKT_LENGTH_24 - 4; }
+    else {
+        // the reference silently ignores datagrams of any other size (:480,:507); a whole call of them is a caller error
+        set_error("bank_process_packets: packet length %d is neither %d (16-bit) nor %d (24-bit)", packet_bytes,
+                  CUTESDR_PKT_LENGTH_16, CUTESDR_PKT_LENGTH_24);
+        return CUTESDR_E_ARG;
+    }
+    {
+        std::lock_guard<std::mutex> lk(b->mu);
+        b->pkt_payload.resize((size_t)n_packets * payload);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(packets);
+        for (int k = 0; k < n_packets; k++, src += packet_bytes) {
+            const unsigned short seq = (unsigned short)(src[2] | (src[3] << 8));
+            if (0 == seq) b->pkt_last_seq = 0;                         // first packet after the radio started
+            if (seq != b->pkt_last_seq) {
+                b->missed_packets += (short)seq - (short)b->pkt_last_seq;
+                b->pkt_last_seq = seq;
+            }
+            b->pkt_last_seq++;
+            if (0 == b->pkt_last_seq) b->pkt_last_seq = 1;
+            memcpy(b->pkt_payload.data() + (size_t)k * payload, src + 4, payload);
+        }
+    }
+    const int samples = n_packets * (fmt == CUTESDR_FMT_CS16 ? payload / 4 : payload / 6);
+    return bank_process_host(b, samples, b->pkt_payload.data(), fmt, audio, audio_stride, n_out);
+}
+
+int cutesdr_bank_missed_packets(cutesdr_bank* b, long long* missed, int reset)
+{
+    if (!b) { set_error("missed_packets: bad handle"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    if (missed) *missed = b->missed_packets;
+    if (reset) { b->missed_packets = 0; b->pkt_last_seq = 0; }
+    return CUTESDR_OK;
 }
 
 static int bank_process_host(cutesdr_bank* b, int n_in, const void* iq, int fmt, float* audio, int audio_stride, int* n_out)

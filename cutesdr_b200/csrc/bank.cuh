@@ -88,6 +88,10 @@ struct cutesdr_bank {
     bool nb_on = false;
     double nb_thresh = 50.0, nb_width = 2.0;
     std::vector<int> blk_nout;           // per channel, samples produced by the last block
+    // UDP packet front end (CUdpThread::OnreadyRead, interface/netiobase.cpp:464-534)
+    unsigned short pkt_last_seq = 0;     // m_LastSeqNum
+    long long missed_packets = 0;        // m_MissedPackets
+    std::vector<unsigned char> pkt_payload;
 
     int rebuild();
     int run_block(const void* d_block, int fmt, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);

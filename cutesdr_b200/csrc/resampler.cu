@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(128) k_resample_weights(const double* __restri
     }
 }
 
-// Pass 2: w: [nrows][row_len], row = 28 carried samples then the new inputs. Thread per (output, row);
-// consecutive lanes take consecutive outputs of one row (inputs and weights stream, no table access).
+// Pass 2: w: [nrows][row_len], row = 28 carried samples then the new inputs (W floats per sample). Thread per
+// (output, row); consecutive lanes take consecutive outputs of one row (inputs and weights stream, no table access).
+template <int W>
 __global__ void __launch_bounds__(128) k_resample(const float* __restrict__ w, int row_len, int nrows,
                                                   const float* __restrict__ wts, const int* __restrict__ pos, int n_out,
                                                   float* __restrict__ out, int out_stride,
@@ -52,25 +53,34 @@ __global__ void __launch_bounds__(128) k_resample(const float* __restrict__ w, i
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (k >= n_out) return;
-    const float* x = w + (size_t)r * row_len + pos[k];
+    const float* x = w + (size_t)r * row_len + (size_t)W * pos[k];
     const float4* c4 = reinterpret_cast<const float4*>(wts + (size_t)k * kRsPeriods);
-    float acc = 0.f;
+    float acc[W];
+#pragma unroll
+    for (int e = 0; e < W; e++) acc[e] = 0.f;
 #pragma unroll
     for (int q = 0; q < kRsPeriods / 4; q++) {
         const float4 c = __ldg(c4 + q);
         // same accumulation order as the reference loop i = 1..28
-        acc = fmaf(x[4 * q + 1], c.x, acc);
-        acc = fmaf(x[4 * q + 2], c.y, acc);
-        acc = fmaf(x[4 * q + 3], c.z, acc);
-        acc = fmaf(x[4 * q + 4], c.w, acc);
+#pragma unroll
+        for (int e = 0; e < W; e++) {
+            acc[e] = fmaf(x[W * (4 * q + 1) + e], c.x, acc[e]);
+            acc[e] = fmaf(x[W * (4 * q + 2) + e], c.y, acc[e]);
+            acc[e] = fmaf(x[W * (4 * q + 3) + e], c.z, acc[e]);
+            acc[e] = fmaf(x[W * (4 * q + 4) + e], c.w, acc[e]);
+        }
     }
     if (out16) {
-        float v = acc * gain;                                       // :228-239 gain, clip, truncate
-        v = fminf(fmaxf(v, -32767.0f), 32767.0f);
-        out16[(size_t)k * interleave16 + r] = (int16_t)v;
+#pragma unroll
+        for (int e = 0; e < W; e++) {
+            float v = acc[e] * gain;                                // :228-239 gain, clip, truncate
+            v = fminf(fmaxf(v, -32767.0f), 32767.0f);
+            out16[(size_t)k * interleave16 + W * r + e] = (int16_t)v;
+        }
     } else {
         const int row = row_map ? row_map[r] : r;
-        out[(size_t)row * out_stride + out_off + k] = acc;
+#pragma unroll
+        for (int e = 0; e < W; e++) out[(size_t)row * out_stride + (size_t)W * (out_off + k) + e] = acc[e];
     }
 }
 
@@ -84,14 +94,14 @@ __global__ void k_resample_times(double t0, double rate, int m, double* __restri
 }
 
 // carry the last 28 inputs of every row to the row's front (dsp/fractresampler.cpp:180-182)
-__global__ void k_resample_carry(float* w, int row_len, int nrows, int n_in)
+__global__ void k_resample_carry(float* w, int row_len, int nrows, int n_in, int width)
 {
     const int r = blockIdx.x;
     const int i = threadIdx.x;
     float v = 0.f;
-    if (i < kRsPeriods) v = w[(size_t)r * row_len + n_in + i];
+    if (i < width * kRsPeriods) v = w[(size_t)r * row_len + (size_t)width * n_in + i];
     __syncthreads();
-    if (i < kRsPeriods) w[(size_t)r * row_len + i] = v;
+    if (i < width * kRsPeriods) w[(size_t)r * row_len + i] = v;
 }
 
 ResamplerBank::~ResamplerBank()
@@ -103,10 +113,11 @@ ResamplerBank::~ResamplerBank()
     cudaFree(d_pos_);
 }
 
-int ResamplerBank::init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc)
+int ResamplerBank::init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc, int width)
 {
-    nrows_ = nrows; max_in_ = max_in; st_ = st; lc_ = lc;
-    row_len_ = round_up(kRsPeriods + max_in, 4);
+    if (width != 1 && width != 2) { set_error("resampler: width %d", width); return CUTESDR_E_ARG; }
+    nrows_ = nrows; max_in_ = max_in; st_ = st; lc_ = lc; width_ = width;
+    row_len_ = round_up(width * (kRsPeriods + max_in), 4);
     CSDR_CK(cudaMalloc(&d_w_, (size_t)nrows * row_len_ * sizeof(float)));
     CSDR_CK(cudaMemsetAsync(d_w_, 0, (size_t)nrows * row_len_ * sizeof(float), st_));
     // window-sinc table, dsp/fractresampler.cpp:104-115 (computed in double, stored float32)
@@ -149,13 +160,17 @@ int ResamplerBank::run(int n_in, double rate, float* d_out, int out_stride, int 
         if (d_out || d_out16) {
             dim3 grid((m + 127) / 128, nrows_);
             k_resample_weights<<<(m + 3) / 4, 128, 0, st_>>>(d_times_, m, d_sinc_, d_wts_, d_pos_);
-            k_resample<<<grid, 128, 0, st_>>>(d_w_, row_len_, nrows_, d_wts_, d_pos_, m, d_out, out_stride, out_off,
-                                              d_row_map, d_out16, (float)gain, interleave16);
+            if (width_ == 2)
+                k_resample<2><<<grid, 128, 0, st_>>>(d_w_, row_len_, nrows_, d_wts_, d_pos_, m, d_out, out_stride, out_off,
+                                                     d_row_map, d_out16, (float)gain, interleave16);
+            else
+                k_resample<1><<<grid, 128, 0, st_>>>(d_w_, row_len_, nrows_, d_wts_, d_pos_, m, d_out, out_stride, out_off,
+                                                     d_row_map, d_out16, (float)gain, interleave16);
             lc_->n += 2;
             CSDR_CK(cudaGetLastError());
         }
     }
-    k_resample_carry<<<nrows_, 32, 0, st_>>>(d_w_, row_len_, nrows_, n_in);
+    k_resample_carry<<<nrows_, 64, 0, st_>>>(d_w_, row_len_, nrows_, n_in, width_);
     lc_->n++;
     CSDR_CK(cudaGetLastError());
     return CUTESDR_OK;

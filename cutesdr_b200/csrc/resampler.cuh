@@ -30,21 +30,24 @@ public:
     ResamplerBank(const ResamplerBank&) = delete;
     ResamplerBank& operator=(const ResamplerBank&) = delete;
 
-    // nrows independent real streams (a complex stream is two rows), at most max_in inputs per call
-    int init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc);
+    // nrows independent streams, at most max_in inputs per call. width 1: real rows (a complex stream may be two
+    // rows); width 2: rows of interleaved (re,im) / (left,right) float pairs -- the stereo form
+    // Resample(.., TYPECPX*, TYPESTEREO16*/TYPECPX*), dsp/fractresampler.cpp:194-249,309-352: same clock, same
+    // weights, two accumulators.
+    int init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc, int width = 1);
     // device buffer the producer writes new inputs into: row r starts at in_ptr() + r*in_stride()
-    float* in_ptr() { return d_w_ + kRsPeriods; }
+    float* in_ptr() { return d_w_ + width_ * kRsPeriods; }
     int in_stride() const { return row_len_; }
     int max_out(int n_in, double rate) const { return (int)(n_in / rate) + 8; }
     // Resample n_in new inputs per row. Output k of row r goes to
-    //   d_out[row_map ? row_map[r] : r][out_stride] + out_off + k   (float32), or, when d_out16 is
+    //   d_out[row_map ? row_map[r] : r][out_stride] + width * (out_off + k)   (float32, `width` floats), or, when d_out16 is
     // given, to int16 after gain + clip + truncation (dsp/fractresampler.cpp:228-239).
     // Returns the number of outputs per row through *n_out.
     int run(int n_in, double rate, float* d_out, int out_stride, int out_off, const int* d_row_map, int* n_out,
             int16_t* d_out16 = nullptr, double gain = 1.0, int interleave16 = 1);
 
 private:
-    int nrows_ = 0, max_in_ = 0, row_len_ = 0;
+    int nrows_ = 0, max_in_ = 0, row_len_ = 0, width_ = 1;
     cudaStream_t st_ = 0;
     LaunchCounter* lc_ = nullptr;
     ResampleClock clk_;

@@ -181,6 +181,26 @@ class ReceiverBank:
                                               n_out.ctypes.data_as(C.POINTER(C.c_int))))
         return audio, n_out
 
+    def ProcessPackets(self, packets, packet_bytes, audio_stride=None):
+        """The radio's UDP datagrams as received (uint8 array, n * packet_bytes): 1028-byte 16-bit or 1444-byte 24-bit
+        packets with their 4-byte headers (CUdpThread::OnreadyRead, interface/netiobase.cpp:464-534)."""
+        packets = np.ascontiguousarray(packets, dtype=np.uint8)
+        npk = packets.size // packet_bytes
+        n = npk * (256 if packet_bytes == 1028 else 240)
+        L = self.block_length()
+        audio_stride = audio_stride or (n // L + 2) * 2048 * 2
+        audio = np.zeros((self.n_channels, audio_stride), dtype=np.float32)
+        n_out = np.zeros(self.n_channels, dtype=np.int32)
+        check(self.L.cutesdr_bank_process_packets(self.h, int(npk), packets.ctypes.data, int(packet_bytes), audio.ctypes.data,
+                                                  int(audio_stride), n_out.ctypes.data_as(C.POINTER(C.c_int))))
+        return audio, n_out
+
+    def MissedPackets(self, reset=False):
+        """m_MissedPackets of the UDP front end (interface/netiobase.cpp:487-496)"""
+        v = C.c_longlong()
+        check(self.L.cutesdr_bank_missed_packets(self.h, C.byref(v), int(bool(reset))))
+        return v.value
+
     def process_ptr(self, n_in, iq_ptr, audio_ptr, audio_stride, n_out_arr=None):
         """Raw-pointer form (pinned host memory) used by bench.py's end-to-end leg."""
         p = n_out_arr.ctypes.data_as(C.POINTER(C.c_int)) if n_out_arr is not None else None

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "cutesdr_bank_process_async": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_raw": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip]),
     "cutesdr_bank_process_async_raw": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip]),
+    "cutesdr_bank_process_packets": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip]),
+    "cutesdr_bank_missed_packets": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.c_int]),
     "cutesdr_bank_process_async_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _ip]),
     "cutesdr_mgpu_unique_id": (C.c_int, [_vp]),
     "cutesdr_mgpu_init": (C.c_int, [_pp, _vp, C.c_int, C.c_int, C.c_int]),

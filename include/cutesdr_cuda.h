@@ -98,7 +98,8 @@ int cutesdr_bank_set_audio_rate(cutesdr_bank* b, double audio_rate);
  * rows then hold interleaved (left,right) float32 pairs, n_out counts frames and audio_stride (in floats)
  * must hold 2 floats per frame. AM and FM put the mono signal on both channels, SSB/CW pass the complex
  * filter output through, SAM splits lower/upper sideband with its Hilbert pair (dsp/samdemod.cpp:115-158).
- * Switching rebuilds the bank (all channel state restarts). Not combinable with set_audio_rate. */
+ * Switching rebuilds the bank (all channel state restarts). With set_audio_rate the (left,right) frames go through the
+ * stereo form of CFractResampler (dsp/fractresampler.cpp:194-249, call site interface/soundout.cpp:204). */
 int cutesdr_bank_set_stereo(cutesdr_bank* b, int stereo);
 
 /* N x CDemodulator::ProcessData(n_in, iq, audio) -- mono    dsp/demodulator.cpp:163-215
@@ -112,13 +113,25 @@ int cutesdr_bank_process(cutesdr_bank* b, int n_in, const float* iq, float* audi
  * the samples still in the radio's integer format -- fmt 1 = interleaved little-endian int16 I,Q (4 bytes
  * per sample, value = the integer), fmt 2 = packed little-endian int24 I,Q (6 bytes per sample, value =
  * integer/256), fmt 0 = complex64. The unpack happens inside kernel 1's tile load, so H2D traffic is half
- * (int16) or three quarters (int24) of the float path and no conversion pass exists. Packet headers
- * (4 bytes per UDP packet) are the caller's to strip. */
+ * (int16) or three quarters (int24) of the float path and no conversion pass exists. These two take bare
+ * samples; cutesdr_bank_process_packets below takes the radio's datagrams as they arrive. */
 #define CUTESDR_FMT_CF32 0
 #define CUTESDR_FMT_CS16 1
 #define CUTESDR_FMT_CS24 2
 int cutesdr_bank_process_raw(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out);
 int cutesdr_bank_process_async_raw(cutesdr_bank* b, int n_in, const void* data, int fmt, float* audio, int audio_stride, int* n_out);
+/* The radio's UDP datagrams as received (CUdpThread::OnreadyRead, interface/netiobase.cpp:464-534): n_packets
+ * datagrams of packet_bytes each, back to back in HOST memory; packet_bytes = 1028 (4-byte header + 256 int16 I/Q
+ * pairs) or 1444 (header + 240 packed int24 pairs). Bytes 2-3 of the header are the little-endian sequence number;
+ * gaps are counted exactly as the reference counts m_MissedPackets (:487-496) and read with
+ * cutesdr_bank_missed_packets (reset != 0 clears the count and restarts the sequence, as a new CUdpThread does).
+ * The payloads then take the cutesdr_bank_process_raw path (any packet count; DSP blocks are cut every block_length
+ * samples like m_pDemodInBuf, CIQDataThread::run :571-600 -> ProcessIQData). */
+#define CUTESDR_PKT_LENGTH_16 1028
+#define CUTESDR_PKT_LENGTH_24 1444
+int cutesdr_bank_process_packets(cutesdr_bank* b, int n_packets, const void* packets, int packet_bytes, float* audio,
+                                 int audio_stride, int* n_out);
+int cutesdr_bank_missed_packets(cutesdr_bank* b, long long* missed, int reset);
 /* Pipelined form for a block that is already in DEVICE memory (multi-GPU: the NCCL broadcast of rank 0's block lands
  * there). d_iq (complex64[n_in]) is read in stream order with respect to src_stream (a cudaStream_t): the library
  * waits for the work queued on it so far and makes it wait until the block has been taken over, so the caller can

@@ -1212,6 +1212,10 @@ void orc_demod_set_demod(orc_demod* d, int mode, const orc_demod_info* info)
 
 double orc_demod_output_rate(const orc_demod* d) { return d->out_rate; }
 int orc_demod_inbuf_limit(const orc_demod* d) { return d->limit; }
+/* Test aid (not in the reference): replace m_InBufLimit until the next SetDemod. The parity tests for input rates
+ * whose 10 ms block is not a multiple of 2^stages run the reference algorithm on the block length the CUDA bank
+ * picks (the same 10 ms rounded down to such a multiple). */
+void orc_demod_set_inbuf_limit(orc_demod* d, int limit) { d->limit = limit; }
 double orc_demod_smeter_peak(orc_demod* d) { return orc_smeter_peak(d->sm); }
 double orc_demod_smeter_ave(const orc_demod* d) { return orc_smeter_ave(d->sm); }
 

@@ -143,6 +143,8 @@ void orc_demod_set_demod(orc_demod*, int mode, const orc_demod_info* info);
 void orc_demod_set_freq(orc_demod*, double f);
 double orc_demod_output_rate(const orc_demod*);
 int orc_demod_inbuf_limit(const orc_demod*);
+/* test aid, not in the reference: override m_InBufLimit until the next set_demod */
+void orc_demod_set_inbuf_limit(orc_demod*, int limit);
 double orc_demod_smeter_peak(orc_demod*);
 double orc_demod_smeter_ave(const orc_demod*);
 /* tap capture: profile 1..4 as in gui/testbench.cpp:71-81 (1=post-downconvert cpx,

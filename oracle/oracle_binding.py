@@ -128,6 +128,7 @@ def load():
     sig("orc_demod_set_freq", None, vp, C.c_double)
     sig("orc_demod_output_rate", C.c_double, vp)
     sig("orc_demod_inbuf_limit", C.c_int, vp)
+    sig("orc_demod_set_inbuf_limit", None, vp, C.c_int)
     sig("orc_demod_smeter_peak", C.c_double, vp)
     sig("orc_demod_smeter_ave", C.c_double, vp)
     sig("orc_demod_set_tap", None, vp, C.c_int, _dp, C.c_long)
@@ -438,6 +439,10 @@ class Demodulator(_Obj):
 
     def inbuf_limit(self):
         return self.L.orc_demod_inbuf_limit(self.h)
+
+    def set_inbuf_limit(self, limit):
+        """test aid: override m_InBufLimit until the next SetDemod"""
+        self.L.orc_demod_set_inbuf_limit(self.h, int(limit))
 
     def run(self, iq, packet=256, taps=()):
         iq = np.ascontiguousarray(iq, dtype=np.complex64)

@@ -128,6 +128,8 @@ def load(big=False):
     sig("ref_demod_smeter_peak", C.c_double, vp)
     sig("ref_demod_smeter_ave", C.c_double, vp)
     sig("ref_demod_inbuf_limit", C.c_int, vp)
+    sig("ref_demod_set_inbuf_limit", None, vp, C.c_int)
+    sig("ref_chains_set_inbuf_limit", None, vp, C.c_int)
     sig("ref_demod_run", C.c_long, vp, C.c_long, C.c_void_p, C.c_int, C.c_int, _dp, C.c_long, C.c_int)
     sig("ref_bench_chains", C.c_double, C.c_int, _ip, _dp, _ip, C.c_double, C.c_long, C.POINTER(C.c_float),
         C.c_int, C.c_int, _dp)
@@ -475,6 +477,10 @@ class RefDemodulator(_Obj):
     def inbuf_limit(self):
         return self.L.ref_demod_inbuf_limit(self.h)
 
+    def set_inbuf_limit(self, limit):
+        """test aid: override m_InBufLimit until the next SetDemod"""
+        self.L.ref_demod_set_inbuf_limit(self.h, int(limit))
+
     def run(self, iq, packet=256, stereo=False, taps=()):
         """Feed complex64 (or complex128) samples in `packet`-sized calls; returns audio and
         optionally the PROFILE_n tap streams (dict profile -> array)."""
@@ -562,6 +568,10 @@ class RefChainSet:
 
     def GetSMeterAve(self, c):
         return self.L.ref_chains_smeter_ave(self.h, int(c))
+
+    def set_inbuf_limit(self, limit):
+        """test aid: every chain's m_InBufLimit (until a SetDemod recomputes it)"""
+        self.L.ref_chains_set_inbuf_limit(self.h, int(limit))
 
     def checksum(self):
         return self.L.ref_chains_checksum(self.h)

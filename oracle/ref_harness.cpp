@@ -208,6 +208,8 @@ double ref_demod_output_rate(void* h) { return ((CDemodulator*)h)->GetOutputRate
 double ref_demod_smeter_peak(void* h) { return ((CDemodulator*)h)->GetSMeterPeak(); }
 double ref_demod_smeter_ave(void* h) { return ((CDemodulator*)h)->GetSMeterAve(); }
 int ref_demod_inbuf_limit(void* h) { return ((CDemodulator*)h)->m_InBufLimit; }
+// test aid: run the unmodified chain on another DSP block length (valid until the next SetDemod recomputes it)
+void ref_demod_set_inbuf_limit(void* h, int limit) { ((CDemodulator*)h)->m_InBufLimit = limit; }
 
 // Feed n complex samples in `packet`-sample calls (the app uses 256,
 // interface/netiobase.cpp:593); mono audio appended to out. Returns count.
@@ -316,6 +318,7 @@ void ref_chains_delete(void* h) {
 }
 void ref_chains_set_freq(void* h, int c, double f) { ((ChainSet*)h)->d[c]->SetDemodFreq(f); }
 void ref_chains_set_demod(void* h, int c, int mode, const int* info14) { ((ChainSet*)h)->d[c]->SetDemod(mode, make_info(info14)); }
+void ref_chains_set_inbuf_limit(void* h, int limit) { ChainSet* s = (ChainSet*)h; for (int c = 0; c < s->nch; c++) s->d[c]->m_InBufLimit = limit; }
 double ref_chains_smeter_ave(void* h, int c) { return ((ChainSet*)h)->d[c]->GetSMeterAve(); }
 // Feed n complex64 samples to every chain in 256-sample packets (interface/netiobase.cpp:593), channels
 // partitioned over nthreads std::threads. Returns the wall-clock seconds of the threaded section.

@@ -93,9 +93,11 @@ def _gpu_bank(fs, modes, carriers, infos, iq, check, audio_rate=0.0, blanker=Fal
     return {c: np.concatenate(outs[c]) for c in check}, screens, tc, sm
 
 
-def _ref_chains(rb, fs, modes, carriers, infos, iq, check, audio_rate=0.0):
+def _ref_chains(rb, fs, modes, carriers, infos, iq, check, audio_rate=0.0, inbuf_limit=None):
     cset = rb.RefChainSet([modes[c] for c in check], [-carriers[c] for c in check], [infos[c] for c in check], fs,
                           audio_rate=audio_rate, keep_output=True, big=True)
+    if inbuf_limit:
+        cset.set_inbuf_limit(inbuf_limit)
     cset.run(iq, os.cpu_count() or 1)
     out = {c: cset.output(i) for i, c in enumerate(check)}
     sm = {c: cset.GetSMeterAve(i) for i, c in enumerate(check[:8])}
@@ -261,3 +263,29 @@ def test_cfg5_4096_channels_seeded_64_per_mode_blanker_spectrum_vs_reference(ref
     assert worst_bin <= 1
     _compare(ref, got, modes, "cfg5 4096-ch mixed + blanker + 65536-pt spectrum @ 200.2944 Msps (%s), spectrum bins within %d" % (
         "kernel 1T" if tc else "CUDA-core kernel 1", worst_bin), pert)
+
+
+@pytest.mark.parametrize("fs, nch, mode, stages", [(100e6, 64, M.DEMOD_FM, 11), (200e6, 32, M.DEMOD_FM, 12), (20e6, 32, M.DEMOD_AM, 9)],
+                         ids=["100e6-FM", "200e6-FM", "20e6-AM"])
+def test_rates_whose_10ms_block_is_not_a_multiple_of_2_pow_stages(refbig, fs, nch, mode, stages):
+    """Exactly 100e6 / 200e6 sps and 20e6 AM: the reference's m_InBufLimit (multiple of 256 only, dsp/demodulator.cpp:145-146)
+    is not a multiple of 2^stages there, and its deeper half-band stages then mis-handle an odd length at every block edge
+    (dsp/downconvert.cpp:298-313). The bank accepts these rates with the same 10 ms rounded down to a multiple of
+    2^stages; it is compared with the UNMODIFIED reference classes run on that block length (m_InBufLimit overridden)."""
+    modes = [mode] * nch
+    infos = [_info(mode, c) for c in range(nch)]
+    bank = cs.ReceiverBank(nch, fs)
+    for c in range(nch):
+        bank.SetDemod(c, mode, infos[c])
+    L = bank.block_length()
+    del bank
+    ref_l = int(fs / 100.0) & ~255
+    assert L % (1 << stages) == 0 and ref_l - (1 << stages) < L <= ref_l and ref_l % (1 << stages) != 0
+    iq, carriers = syn_iq_fft(fs, NBLK * L, modes, carrier_grid(nch, 62500.0), seed=20266, decim=1 << stages)
+    check = list(range(0, nch, 4))
+    got, _, _, _ = _gpu_bank(fs, modes, carriers, infos, iq, check)
+    ref, _ = _ref_chains(refbig, fs, modes, carriers, infos, iq, check, inbuf_limit=L)
+    pert = None
+    if mode in PLL_MODES:
+        pert, _ = _ref_chains(refbig, fs, modes, carriers, infos, _perturb_1ulp(iq, 3), check, inbuf_limit=L)
+    _compare(ref, got, modes, "%g sps, %d-stage ladder, block %d (reference: %d)" % (fs, stages, L, ref_l), pert)

@@ -806,3 +806,33 @@ def test_plot_producer_and_display_dc_offset(lib, ref):
         assert np.abs(wf - ra).max() <= 1 and np.abs(tr - rb).max() <= 1
         _, wf2, tr2 = g2.GetPlot(h, w, 0.0, -140.0, lo, hi)
         assert np.abs(wf - wf2).max() <= 1 and np.abs(tr - tr2).max() <= 1
+
+
+@pytest.mark.parametrize("mode,lo,hi", [(M.DEMOD_USB, 100, 2800), (M.DEMOD_AM, -5000, 5000), (M.DEMOD_SAM, -5000, 5000)])
+def test_stereo_output_through_the_bank_resampler(lib, ref, mode, lo, hi):
+    """m_StereoOut + CSoundOut::PutOutQueue (interface/sdrinterface.cpp:912-916, interface/soundout.cpp:204): the stereo
+    demodulator output goes through the TYPECPX form of CFractResampler (dsp/fractresampler.cpp:194-249) burst by burst."""
+    fs, fc, arate = 2e6, 250000.0, 48000.0
+    n = 800000
+    iq = syn_iq(fs, n, [mode], [fc], seed=20267, total_amp=8000.0)
+    info = M.demod_info(mode, HiCut=hi, LowCut=lo)
+    a = ref.RefDemodulator()
+    a.SetInputSampleRate(fs)
+    a.SetDemod(mode, info)
+    a.SetDemodFreq(-fc)
+    ya = a.run(iq, stereo=True)
+    rs = ref.RefFractResampler()
+    rate = a.GetOutputRate() / arate
+    want = np.concatenate([rs.Resample(ya[k:k + 1024], rate) for k in range(0, len(ya), 1024)])
+    bank = cs.ReceiverBank(3, fs)
+    bank.SetStereo(True)
+    bank.SetAudioRate(arate)
+    for c in range(3):
+        bank.SetDemod(c, mode, info)
+        bank.SetDemodFreq(c, -fc)
+    audio, n_out = bank.ProcessData(iq)
+    got = audio[2, 0:2 * n_out[2]:2].astype(np.float64) + 1j * audio[2, 1:2 * n_out[2]:2].astype(np.float64)
+    assert len(want) == len(got) >= 8 * 1000
+    skip = 6 * 1024 if mode == M.DEMOD_SAM else 0
+    assert snr_db(want[skip:], got[skip:]) > SNR_MIN, "%.1f dB" % snr_db(want[skip:], got[skip:])
+    assert np.array_equal(audio[0], audio[2])
