@@ -31,6 +31,20 @@ Group::~Group()
     if (st_post) cudaStreamDestroy(st_post);
 }
 
+TapSpectrum::~TapSpectrum()
+{
+    cudaFree(d_frame);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+}
+
+// kind 0: complex rows (float2); 1: real samples -> (x, 0) (TYPEREAL DisplayData, gui/testbench.cpp:657-658)
+__global__ void k_tap_append(float2* __restrict__ dst, const void* __restrict__ src, int n, int kind)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[i] = kind ? make_float2(reinterpret_cast<const float*>(src)[i], 0.f) : reinterpret_cast<const float2*>(src)[i];
+}
+
 static int block_limit(double in_rate, double out_rate)
 {
     // m_InBufLimit, dsp/demodulator.cpp:145-146 (same expression, same evaluation order)
@@ -191,7 +205,10 @@ int cutesdr_bank::run_block(const void* d_block, int fmt, float* d_audio_out, in
         const long long total = g.dec.total_out();
         const int nbursts = (int)(total / kBurst - g.bursts_done);
         g.last_fir_n = 0;
-        if (nbursts <= 0) continue;
+        if (nbursts <= 0) {
+            if (!tap_spectra.empty()) CSDR_TRY(feed_tap_spectra(g, (int)gi, 0, nullptr, 0, 0));
+            continue;
+        }
         const int n = nbursts * kBurst;
         if (n > kMaxBurstSamples) { set_error("more than %d FIR bursts in one DSP block", kMaxBurstSamples / kBurst); return CUTESDR_E_STATE; }
         CSDR_CK(cudaStreamWaitEvent(g.st_post, g.dec.done_event(), 0));
@@ -217,6 +234,7 @@ int cutesdr_bank::run_block(const void* d_block, int fmt, float* d_audio_out, in
             }
             CSDR_TRY(g.post.run(n, d_audio_out, audio_stride, off, g.d_chan_map));
         }
+        if (!tap_spectra.empty()) CSDR_TRY(feed_tap_spectra(g, (int)gi, n, d_audio_out, audio_stride, off));
         cudaEvent_t done = g.ev_post[g.post_launches++ & 7];
         CSDR_CK(cudaEventRecord(done, g.st_post));
         g.pending.push_back({done, block_index});
@@ -249,6 +267,77 @@ int cutesdr_bank::sync_all()
     if (st_h2d) CSDR_CK(cudaStreamSynchronize(st_h2d));
     if (st_d2h) CSDR_CK(cudaStreamSynchronize(st_d2h));
     d2h_pending = false;
+    return CUTESDR_OK;
+}
+
+// CTestBench::DisplayData, frequency-domain branch (gui/testbench.cpp:594-611), for n samples at src on stream st:
+// fill m_FftInBuf; every full frame bumps the skip counter and, when it reaches m_DisplaySkipValue, goes through
+// PutInDisplayFFT of the attached CFft. All of it is queued in stream order; nothing synchronises.
+static int tap_spectrum_append(cutesdr_bank* b, TapSpectrum& t, const void* src, int n, int kind, cudaStream_t st)
+{
+    const size_t esz = kind ? sizeof(float) : sizeof(float2);
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(src);
+    while (n > 0) {
+        const int take = std::min(n, kTestFftSize - t.pos);
+        k_tap_append<<<(take + 255) / 256, 256, 0, st>>>(t.d_frame + t.pos, p, take, kind);
+        b->lc.n++;
+        CSDR_CK(cudaGetLastError());
+        t.pos += take;
+        p += (size_t)take * esz;
+        n -= take;
+        if (t.pos >= kTestFftSize) {
+            t.pos = 0;
+            if (++t.skip_counter >= t.skip_value) {
+                t.skip_counter = 0;
+                int total = 0;
+                CSDR_TRY(cutesdr_fft_put_device_async(t.fft, kTestFftSize, t.d_frame, (void*)st, &total));
+                t.frames++;
+            }
+        }
+    }
+    return CUTESDR_OK;
+}
+
+// Feed the attached test-bench spectra of group g for the block just queued: PROFILE_1 = this block's decimated
+// samples (dsp/demodulator.cpp:175), PROFILE_2/3/4 = the burst's FIR output, AGC output and audio (:180,187,208).
+// Runs on the group's burst stream, after the burst chain.
+int cutesdr_bank::feed_tap_spectra(Group& g, int gi, int n_burst, float* d_audio_out, int audio_stride, int audio_off)
+{
+    for (auto& tp : tap_spectra) {
+        TapSpectrum& t = *tp;
+        const ChanCfg& cc = ch[t.ch];
+        if (cc.group != gi) continue;
+        const int i = cc.local;
+        if (t.profile == 1) {
+            const int n_dec = g.dec.out_per_block();
+            CSDR_CK(cudaStreamWaitEvent(g.st_post, g.dec.done_event(), 0));
+            const long long first = g.dec.total_out() - n_dec;
+            for (int k = 0; k < n_dec;) {
+                const int pos = (int)((first + k) & (kDecRing - 1));
+                const int run = std::min(n_dec - k, kDecRing - pos);
+                CSDR_TRY(tap_spectrum_append(this, t, g.dec.ring() + (size_t)i * kDecRing + pos, run, 0, g.st_post));
+                k += run;
+            }
+            // the ring must not be overwritten before these reads: same ordering as a pending burst chain
+            cudaEvent_t& e = t.ev[t.n_ev++ & 7];
+            if (!e) CSDR_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CSDR_CK(cudaEventRecord(e, g.st_post));
+            g.pending.push_back({e, block_index});
+            continue;
+        }
+        if (n_burst <= 0) continue;
+        if (t.profile == 2)
+            CSDR_TRY(tap_spectrum_append(this, t, g.post.y_in() + (size_t)i * g.post.y_stride() - n_burst, n_burst, 0, g.st_post));
+        else if (t.profile == 3)
+            CSDR_TRY(tap_spectrum_append(this, t, g.post.tap3() + (size_t)i * g.post.tap3_stride(), n_burst, 0, g.st_post));
+        else if (t.profile == 4) {
+            // the demodulator output at m_OutputRate, i.e. in front of the bank resampler; stereo frames are complex
+            const float* src = nullptr;
+            if (g.rs) src = g.rs->in_ptr() + (size_t)i * g.rs->in_stride();
+            else if (d_audio_out) src = d_audio_out + (size_t)t.ch * audio_stride + (size_t)(stereo ? 2 : 1) * audio_off;
+            if (src) CSDR_TRY(tap_spectrum_append(this, t, src, n_burst, stereo ? 0 : 1, g.st_post));
+        }
+    }
     return CUTESDR_OK;
 }
 
@@ -839,6 +928,49 @@ int cutesdr_bank_tap_enable(cutesdr_bank* b, int c, unsigned profile_mask)
         for (int u : g->chans) if (b->ch[u].tap_mask & 0xEu) g->any_tap = true;
     }
     return CUTESDR_OK;
+}
+
+int cutesdr_bank_tap_spectrum(cutesdr_bank* b, int c, int profile, cutesdr_fft* fft, int display_rate)
+{
+    if (!b || c < 0 || c >= b->nch || profile < 1 || profile > 4 || (fft && display_rate <= 0)) { set_error("tap_spectrum: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    CSDR_CK(cudaSetDevice(b->device));
+    if (b->layout_dirty) CSDR_TRY(b->rebuild());
+    // one spectrum per (channel, profile); a NULL fft detaches
+    for (size_t k = 0; k < b->tap_spectra.size();) {
+        if (b->tap_spectra[k]->ch == c && b->tap_spectra[k]->profile == profile) {
+            CSDR_TRY(b->sync_all());
+            b->tap_spectra.erase(b->tap_spectra.begin() + k);
+        } else k++;
+    }
+    if (!fft) return CUTESDR_OK;
+    std::unique_ptr<TapSpectrum> t(new TapSpectrum());
+    t->ch = c;
+    t->profile = profile;
+    t->fft = fft;
+    t->display_rate = display_rate;
+    std::vector<int> lens;
+    t->rate = plan_stages(b->in_rate, b->ch[c].dc_max_bw, lens);             // m_OutputRate of the channel's CDemodulator
+    // CTestBench::Reset, gui/testbench.cpp:535-575 (m_DisplaySkipValue is a qint32: the quotient is truncated)
+    CSDR_TRY(cutesdr_fft_set_params(fft, kTestFftSize, 0, 0.0, t->rate));
+    t->skip_value = (int)(t->rate / (kTestFftSize * (double)display_rate));
+    t->skip_counter = -2;
+    CSDR_TRY(cutesdr_fft_reset(fft));
+    CSDR_CK(cudaMalloc(&t->d_frame, kTestFftSize * sizeof(float2)));
+    CSDR_CK(cudaMemsetAsync(t->d_frame, 0, kTestFftSize * sizeof(float2), b->st));
+    CSDR_CK(cudaStreamSynchronize(b->st));
+    b->tap_spectra.push_back(std::move(t));
+    return CUTESDR_OK;
+}
+
+int cutesdr_bank_tap_spectrum_frames(cutesdr_bank* b, int c, int profile, long long* frames)
+{
+    if (!b || !frames) { set_error("tap_spectrum_frames: bad arguments"); return CUTESDR_E_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    for (auto& t : b->tap_spectra)
+        if (t->ch == c && t->profile == profile) { *frames = t->frames; return CUTESDR_OK; }
+    set_error("tap_spectrum_frames: no spectrum attached to channel %d profile %d", c, profile);
+    return CUTESDR_E_STATE;
 }
 
 int cutesdr_bank_tap_size(cutesdr_bank* b, int c, int profile, long* n_floats)

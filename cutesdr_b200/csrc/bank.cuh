@@ -51,6 +51,24 @@ struct Group {
 
 constexpr int kMaxBurstSamples = 2 * kBurst;   // a DSP block completes at most two FIR bursts
 
+// Test-bench spectrum of one PROFILE tap of one channel: CTestBench's frequency-domain DisplayData branch
+// (gui/testbench.cpp:583-611) kept on the device -- the tap's samples are appended to a 2048-sample frame in stream
+// order and every m_DisplaySkipValue-th full frame goes through the attached CFft object's PutInDisplayFFT.
+constexpr int kTestFftSize = 2048;             // TEST_FFTSIZE, gui/testbench.h:44
+struct TapSpectrum {
+    int ch = -1, profile = 0;
+    cutesdr_fft* fft = nullptr;
+    int display_rate = 10;                     // m_DisplayRate
+    double rate = 0;                           // m_DisplaySampleRate
+    int skip_value = 0, skip_counter = -2;     // m_DisplaySkipValue / m_DisplaySkipCounter (:570,574)
+    int pos = 0;                               // m_FftBufPos
+    long long frames = 0;                      // PutInDisplayFFT calls so far
+    float2* d_frame = nullptr;                 // m_FftInBuf
+    cudaEvent_t ev[8] = {};
+    long long n_ev = 0;
+    ~TapSpectrum();
+};
+
 }  // namespace csdr
 
 struct cutesdr_bank {
@@ -92,10 +110,12 @@ struct cutesdr_bank {
     unsigned short pkt_last_seq = 0;     // m_LastSeqNum
     long long missed_packets = 0;        // m_MissedPackets
     std::vector<unsigned char> pkt_payload;
+    std::vector<std::unique_ptr<csdr::TapSpectrum>> tap_spectra;
 
     int rebuild();
     int run_block(const void* d_block, int fmt, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);
     int collect_taps();
+    int feed_tap_spectra(csdr::Group& g, int gi, int n_burst, float* d_audio_out, int audio_stride, int audio_off);
     int join();                          // order the main stream after every outstanding burst chain
     int sync_all();
     ~cutesdr_bank();

@@ -250,6 +250,18 @@ class ReceiverBank:
         return out
 
 
+    def tap_spectrum(self, ch, profile, fft, display_rate=10):
+        """CTestBench's spectrum of a PROFILE tap (gui/testbench.cpp:583-611) on the device; fft=None detaches."""
+        check(self.L.cutesdr_bank_tap_spectrum(self.h, int(ch), int(profile), fft.h if fft is not None else None, int(display_rate)))
+        if fft is not None:
+            fft._size = 2048
+
+    def tap_spectrum_frames(self, ch, profile):
+        n = C.c_longlong()
+        check(self.L.cutesdr_bank_tap_spectrum_frames(self.h, int(ch), int(profile), C.byref(n)))
+        return n.value
+
+
 class MultiGpu:
     """cutesdr_mgpu: this process's rank in the multi-GPU receiver (one process per GPU). The 128-byte NCCL id is
     created by rank 0 (`MultiGpu.unique_id()`) and handed to the other processes by the host application."""

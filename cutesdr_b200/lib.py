@@ -70,6 +70,8 @@ PROTOTYPES = {
     "cutesdr_bank_kernel_time": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_longlong)]),
     "cutesdr_bank_kernel_model": (C.c_int, [_vp, C.c_int, _ip, _dp]),
     "cutesdr_bank_tap_enable": (C.c_int, [_vp, C.c_int, C.c_uint]),
+    "cutesdr_bank_tap_spectrum": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int]),
+    "cutesdr_bank_tap_spectrum_frames": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "cutesdr_bank_tap_size": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_long)]),
     "cutesdr_bank_tap_read": (C.c_int, [_vp, C.c_int, C.c_int, _fp, C.c_long]),
     "cutesdr_downconvert_create": (C.c_int, [_pp, C.c_int]),

@@ -212,6 +212,19 @@ int cutesdr_bank_tap_enable(cutesdr_bank* b, int ch, unsigned profile_mask);
 int cutesdr_bank_tap_size(cutesdr_bank* b, int ch, int profile, long* n_floats);
 int cutesdr_bank_tap_read(cutesdr_bank* b, int ch, int profile, float* out, long cap_floats);
 
+/* The test bench's spectrum display of one tap, kept on the device (CTestBench::DisplayData frequency-domain branch,
+ * gui/testbench.cpp:583-611; set-up CTestBench::Reset :535-575 and the constructor :128-132): the tap's samples are
+ * appended to a TEST_FFTSIZE = 2048 sample frame in stream order and every m_DisplaySkipValue-th full frame
+ * (m_DisplaySkipValue = (int)(rate / (2048 * display_rate)), counter starting at -2) goes through PutInDisplayFFT of
+ * `fft`, which this call sets to SetFFTParams(2048, FALSE, 0.0, rate) + ResetFFT like the test bench does. Nothing
+ * synchronises: read the result with cutesdr_fft_get_screen / get_plot whenever the GUI timer fires. Real taps
+ * (PROFILE_4 mono) enter as (x, 0) like the TYPEREAL overload (:657-658); PROFILE_4 is the demodulator output at the
+ * channel's output rate (in front of the bank resampler) and needs an audio destination in the process call.
+ * fft == NULL detaches; detach before destroying the fft object. frames = PutInDisplayFFT calls made so far. */
+struct cutesdr_fft;
+int cutesdr_bank_tap_spectrum(cutesdr_bank* b, int ch, int profile, struct cutesdr_fft* fft, int display_rate);
+int cutesdr_bank_tap_spectrum_frames(cutesdr_bank* b, int ch, int profile, long long* frames);
+
 /* ======================================================================================
  * Single-object entry points (one reference object each; TYPECPX = double pairs)
  * ====================================================================================== */

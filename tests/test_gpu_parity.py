@@ -836,3 +836,70 @@ def test_stereo_output_through_the_bank_resampler(lib, ref, mode, lo, hi):
     skip = 6 * 1024 if mode == M.DEMOD_SAM else 0
     assert snr_db(want[skip:], got[skip:]) > SNR_MIN, "%.1f dB" % snr_db(want[skip:], got[skip:])
     assert np.array_equal(audio[0], audio[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# Test-bench spectrum of the PROFILE taps: CTestBench::DisplayData's frequency-domain
+# branch, gui/testbench.cpp:583-611, restated here around the oracle's CFft
+# ------------------------------------------------------------------------------------------------
+def _testbench_spectra(orc, x, rate, display_rate, screen):
+    """m_FftInBuf / m_FftBufPos / m_DisplaySkipCounter bookkeeping of CTestBench (Reset :535-575, DisplayData :594-611);
+    returns the screen after every PutInDisplayFFT."""
+    f = orc.Fft()
+    f.SetFFTParams(2048, False, 0.0, rate)
+    f.SetFFTAve(0)
+    f.ResetFFT()
+    skip_value = int(rate / (2048 * display_rate))          # qint32 m_DisplaySkipValue
+    skip_counter = -2
+    out = []
+    for k in range(0, len(x) - 2047, 2048):                  # the frame buffer fills in order: frames are consecutive slices
+        skip_counter += 1
+        if skip_counter >= skip_value:
+            skip_counter = 0
+            f.PutInDisplayFFT(np.asarray(x[k:k + 2048], dtype=np.complex128))
+            out.append(f.GetScreenIntegerFFTData(*screen))
+    return out
+
+
+@pytest.mark.parametrize("mode,lo,hi", [(M.DEMOD_AM, -5000, 5000), (M.DEMOD_USB, 100, 2800)])
+def test_testbench_tap_spectra_on_device(lib, orc, mode, lo, hi):
+    fs, fc, n = 2e6, 250000.0, 900000
+    iq = syn_iq(fs, n, [mode], [fc], seed=20266, total_amp=8000.0)
+    info = M.demod_info(mode, HiCut=hi, LowCut=lo)
+    a = orc.Demodulator()
+    a.SetInputSampleRate(fs)
+    a.SetDemod(mode, info)
+    a.SetDemodFreq(-fc)
+    ya, ta = a.run(iq, taps=(1, 2, 3, 4))
+    rate = a.GetOutputRate()
+    screen = (300, 600, 0.0, -140.0, int(-rate / 2), int(rate / 2))
+    streams = {p: ta[p][0::2] + 1j * ta[p][1::2] for p in (1, 2, 3)}
+    streams[4] = np.asarray(ta[4], dtype=np.float64) + 0j     # TYPEREAL DisplayData: (x, 0), :657-658
+    want = {p: _testbench_spectra(orc, streams[p], rate, 10, screen) for p in (1, 2, 3, 4)}
+    assert all(len(want[p]) >= 2 for p in want)
+
+    bank = cs.ReceiverBank(1, fs)
+    bank.SetDemod(0, mode, info)
+    bank.SetDemodFreq(0, -fc)
+    ffts = {p: cs.CFft() for p in (1, 2, 3, 4)}
+    for p, f in ffts.items():
+        f.SetFFTAve(0)
+        bank.tap_spectrum(0, p, f, 10)
+    pos, checked = 0, 0
+    for chunk in (300000, 19968, 200000, 5000, n):
+        m = min(chunk, n - pos)
+        bank.ProcessData(iq[pos:pos + m])
+        pos += m
+        for p, f in ffts.items():
+            k = bank.tap_spectrum_frames(0, p)
+            assert k <= len(want[p])
+            if k:
+                ova, sa = want[p][k - 1]
+                ovb, sb = f.GetScreenIntegerFFTData(*screen)
+                assert ova == ovb and np.max(np.abs(sa - sb)) <= 1, (p, k)
+                checked += 1
+    for p in ffts:
+        assert bank.tap_spectrum_frames(0, p) == len(want[p])
+    assert checked >= 8
+    for p in ffts:
+        bank.tap_spectrum(0, p, None)
