@@ -9,9 +9,9 @@ compiled CUDA library and a CUDA device, and fails loudly otherwise.
 from .modes import (DEMOD_AM, DEMOD_SAM, DEMOD_FM, DEMOD_USB, DEMOD_LSB, DEMOD_CWU, DEMOD_CWL, NUM_DEMODS,
                     MODE_NAMES, demod_info, max_bandwidth)
 from .lib import load_library, library_path, CuteSdrError
-from .dsp import (ReceiverBank, MultiGpu, channel_slice, microbench, CDemodulator, CDownConvert, CFastFIR, CFft, CAgc, CFractResampler, CNoiseProc, CIir)
+from .dsp import (ReceiverBank, MultiGpu, channel_slice, microbench, device_memory, CDemodulator, CDownConvert, CFastFIR, CFft, CAgc, CFractResampler, CNoiseProc, CIir)
 
 __all__ = ["DEMOD_AM", "DEMOD_SAM", "DEMOD_FM", "DEMOD_USB", "DEMOD_LSB", "DEMOD_CWU", "DEMOD_CWL", "NUM_DEMODS",
            "MODE_NAMES", "demod_info", "max_bandwidth", "load_library", "library_path", "CuteSdrError",
-           "ReceiverBank", "MultiGpu", "channel_slice", "microbench", "CDemodulator", "CDownConvert", "CFastFIR", "CFft", "CAgc", "CFractResampler",
+           "ReceiverBank", "MultiGpu", "channel_slice", "microbench", "device_memory", "CDemodulator", "CDownConvert", "CFastFIR", "CFft", "CAgc", "CFractResampler",
            "CNoiseProc", "CIir"]

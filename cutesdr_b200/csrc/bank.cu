@@ -94,6 +94,116 @@ static int apply_channel(cutesdr_bank* b, int c, bool new_demod)
     return CUTESDR_OK;
 }
 
+// A group of channels that share the decimation chain for max_bw: its stage objects, burst stream and maps.
+// min_cap > number of channels leaves parked slots for channels that join later (move_channel).
+int cutesdr_bank::create_group(double max_bw, const std::vector<int>& chans, int min_cap, int* index)
+{
+    std::unique_ptr<Group> g(new Group());
+    g->max_bw = max_bw;
+    g->chans = chans;
+    const int n = (int)g->chans.size();
+    {   // burst kernels get scheduled ahead of kernel 1's queued CTAs whenever an SM slot frees up
+        int lo = 0, hi = 0;
+        CSDR_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CSDR_CK(cudaStreamCreateWithPriority(&g->st_post, cudaStreamNonBlocking, hi));
+    }
+    CSDR_CK(cudaEventCreateWithFlags(&g->ev_dec, cudaEventDisableTiming));
+    for (auto& e : g->ev_post) CSDR_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CSDR_TRY(g->dec.init(std::max(n, min_cap), in_rate, g->max_bw, L, st, &lc));
+    CSDR_TRY(g->dec.set_overlap(getenv("CUTESDR_OVERLAP_K2") != nullptr));   // measured: no gain
+    const int stride = g->dec.stride();
+    g->cap = stride;
+    CSDR_TRY(g->fir.init(n, stride, g->st_post, &lc));
+    CSDR_TRY(g->post.init(n, stride, g->dec.out_rate(), kMaxBurstSamples, g->st_post, &lc));
+    g->post.set_stereo(stereo);
+    CSDR_CK(cudaMalloc(&g->d_chan_map, stride * sizeof(int)));
+    CSDR_CK(cudaMalloc(&g->d_local_map, stride * sizeof(int)));
+    std::vector<int> ident(stride, 0);
+    g->h_chan_map.assign(stride, 0);
+    for (int i = 0; i < stride; i++) ident[i] = i;
+    for (int i = 0; i < n; i++) g->h_chan_map[i] = g->chans[i];
+    CSDR_CK(cudaMemcpy(g->d_chan_map, g->h_chan_map.data(), stride * sizeof(int), cudaMemcpyHostToDevice));
+    CSDR_CK(cudaMemcpy(g->d_local_map, ident.data(), stride * sizeof(int), cudaMemcpyHostToDevice));
+    if (audio_rate > 0.0) {
+        g->rs.reset(new ResamplerBank());
+        // stereo: rows of (left,right) pairs through the TYPECPX form of the resampler (dsp/fractresampler.cpp:194-249)
+        CSDR_TRY(g->rs->init(stride, kMaxBurstSamples, g->st_post, &lc, stereo ? 2 : 1));
+        g->rs->set_rows(n);
+    }
+    const int gi = (int)groups.size();
+    for (int i = 0; i < n; i++) { ch[g->chans[i]].group = gi; ch[g->chans[i]].local = i; }
+    groups.push_back(std::move(g));
+    if (index) *index = gi;
+    return CUTESDR_OK;
+}
+
+// CDemodulator::SetDemod with a new m_DesiredMaxOutputBandwidth on a RUNNING bank (dsp/demodulator.cpp:111-142): the
+// reference rebuilds that one object's decimation chain and demodulator and leaves every other CDemodulator alone. Here
+// the channel leaves its group's slot and takes a parked slot of a group with the new chain (or a new group); only its
+// own rows are re-initialised, in stream order. The other channels' state, the wideband halo and the stream position
+// are untouched -- their output is bit-identical to a run without the change.
+int cutesdr_bank::move_channel(int c)
+{
+    ChanCfg& cc = ch[c];
+    std::vector<int> lens;
+    const double orate = plan_stages(in_rate, cc.max_bw, lens);
+    if (block_limit(in_rate, orate) != block_limit(in_rate, groups[cc.group]->dec.out_rate()) || L % (1 << lens.size()) != 0) {
+        layout_dirty = true;          // the new chain needs another DSP block length: only a full rebuild can do that
+        return CUTESDR_OK;
+    }
+    {   // leave the old slot
+        const int ga = cc.group;
+        Group& a = *groups[ga];
+        a.chans[cc.local] = -1;
+        a.fir.release(cc.local);
+        a.post.free_channel(cc.local);
+        while (!a.chans.empty() && a.chans.back() < 0) a.chans.pop_back();
+        const int used = (int)a.chans.size();
+        a.fir.set_nch(used);
+        a.post.set_nch(used);
+        if (a.rs) a.rs->set_rows(used);
+        if (used == 0) {
+            // last channel gone: drop the group (its destructor waits for its own burst stream only)
+            CSDR_TRY(join());
+            CSDR_CK(cudaStreamSynchronize(st));
+            groups.erase(groups.begin() + ga);
+            for (auto& o : ch) if (o.group > ga) o.group--;
+        }
+        cc.group = -1;
+        cc.local = -1;
+    }
+    int gb = -1, slot = -1, biggest = 0;
+    for (size_t gi = 0; gi < groups.size() && gb < 0; gi++) {
+        Group& g = *groups[gi];
+        if (g.max_bw != cc.max_bw) continue;
+        biggest = std::max(biggest, g.cap);
+        for (int i = 0; i < g.cap; i++)
+            if (i >= (int)g.chans.size() || g.chans[i] < 0) { gb = (int)gi; slot = i; break; }
+    }
+    if (gb < 0) {
+        // no parked slot with this chain: a new group, with room for the next movers (capacity doubles per overflow group)
+        const int room = std::min(next_pow2(nch), std::max(32, 2 * biggest));
+        CSDR_TRY(create_group(cc.max_bw, std::vector<int>(), room, &gb));
+        slot = 0;
+    }
+    Group& g = *groups[gb];
+    if (slot >= (int)g.chans.size()) g.chans.resize(slot + 1, -1);
+    g.chans[slot] = c;
+    const int used = (int)g.chans.size();
+    g.fir.set_nch(used);
+    g.post.set_nch(used);
+    if (g.rs) { g.rs->set_rows(used); CSDR_TRY(g.rs->reset_row(slot)); }
+    CSDR_TRY(g.dec.reset_channel(slot));
+    g.fir.release(slot);
+    g.post.free_channel(slot);
+    g.h_chan_map[slot] = c;
+    CSDR_TRY(g.stage.upload(g.d_chan_map, g.h_chan_map.data(), g.cap * sizeof(int), g.st_post));
+    cc.group = gb;
+    cc.local = slot;
+    CSDR_TRY(apply_channel(this, c, true));
+    return CUTESDR_OK;
+}
+
 int cutesdr_bank::rebuild()
 {
     CSDR_CK(cudaSetDevice(device));
@@ -139,38 +249,10 @@ int cutesdr_bank::rebuild()
     stream_pos = 0;
     block_index = 0;
     for (auto& kv : by_bw) {
-        std::unique_ptr<Group> g(new Group());
-        g->max_bw = kv.first;
-        g->chans = kv.second;
-        std::stable_sort(g->chans.begin(), g->chans.end(), [&](int a, int c2) { return ch[a].mode < ch[c2].mode; });
-        const int n = (int)g->chans.size();
-        {   // burst kernels get scheduled ahead of kernel 1's queued CTAs whenever an SM slot frees up
-            int lo = 0, hi = 0;
-            CSDR_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CSDR_CK(cudaStreamCreateWithPriority(&g->st_post, cudaStreamNonBlocking, hi));
-        }
-        CSDR_CK(cudaEventCreateWithFlags(&g->ev_dec, cudaEventDisableTiming));
-        for (auto& e : g->ev_post) CSDR_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CSDR_TRY(g->dec.init(n, in_rate, g->max_bw, L, st, &lc));
-        CSDR_TRY(g->dec.set_overlap(getenv("CUTESDR_OVERLAP_K2") != nullptr));   // measured: no gain
-        const int stride = g->dec.stride();
-        CSDR_TRY(g->fir.init(n, stride, g->st_post, &lc));
-        CSDR_TRY(g->post.init(n, stride, g->dec.out_rate(), kMaxBurstSamples, g->st_post, &lc));
-        g->post.set_stereo(stereo);
-        CSDR_CK(cudaMalloc(&g->d_chan_map, stride * sizeof(int)));
-        CSDR_CK(cudaMalloc(&g->d_local_map, stride * sizeof(int)));
-        std::vector<int> map(stride, 0), ident(stride, 0);
-        for (int i = 0; i < n; i++) { map[i] = g->chans[i]; ident[i] = i; }
-        CSDR_CK(cudaMemcpy(g->d_chan_map, map.data(), stride * sizeof(int), cudaMemcpyHostToDevice));
-        CSDR_CK(cudaMemcpy(g->d_local_map, ident.data(), stride * sizeof(int), cudaMemcpyHostToDevice));
-        if (audio_rate > 0.0) {
-            g->rs.reset(new ResamplerBank());
-            // stereo: rows of (left,right) pairs through the TYPECPX form of the resampler (dsp/fractresampler.cpp:194-249)
-            CSDR_TRY(g->rs->init(n, kMaxBurstSamples, g->st_post, &lc, stereo ? 2 : 1));
-        }
-        const int gi = (int)groups.size();
-        for (int i = 0; i < n; i++) { ch[g->chans[i]].group = gi; ch[g->chans[i]].local = i; }
-        groups.push_back(std::move(g));
+        std::vector<int> sorted = kv.second;
+        // inside a group channels are sorted by mode so warps of the lane-per-channel kernels do not diverge
+        std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int c2) { return ch[a].mode < ch[c2].mode; });
+        CSDR_TRY(create_group(kv.first, sorted, 0, nullptr));
     }
     for (int c = 0; c < nch; c++) CSDR_TRY(apply_channel(this, c, true));
     if (nb_on || nb) {
@@ -238,7 +320,7 @@ int cutesdr_bank::run_block(const void* d_block, int fmt, float* d_audio_out, in
         cudaEvent_t done = g.ev_post[g.post_launches++ & 7];
         CSDR_CK(cudaEventRecord(done, g.st_post));
         g.pending.push_back({done, block_index});
-        for (int c : g.chans) blk_nout[c] = produced;
+        for (int c : g.chans) if (c >= 0) blk_nout[c] = produced;
         nmax = std::max(nmax, produced);
     }
     halo_cur ^= 1;      // kernel 1 saved this block's tail into the other halo buffer
@@ -353,6 +435,7 @@ int cutesdr_bank::collect_taps()
         if (!g.any_tap) continue;
         const int n_dec = g.dec.out_per_block();
         for (int i = 0; i < (int)g.chans.size(); i++) {
+            if (g.chans[i] < 0) continue;
             ChanCfg& cc = ch[g.chans[i]];
             if (!cc.tap_mask) continue;
             if (cc.tap_mask & 2u) {   // PROFILE_1: decimated samples of this block
@@ -400,6 +483,16 @@ int cutesdr_device_count(int* n)
     return CUTESDR_OK;
 }
 
+int cutesdr_device_memory(int device, long long* free_bytes, long long* total_bytes)
+{
+    CSDR_CK(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    CSDR_CK(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (long long)f;
+    if (total_bytes) *total_bytes = (long long)t;
+    return CUTESDR_OK;
+}
+
 int cutesdr_bank_create(cutesdr_bank** out, int n_channels, double in_rate, int device)
 {
     if (!out || n_channels <= 0 || !(in_rate > 0)) { set_error("bank_create: bad arguments"); return CUTESDR_E_ARG; }
@@ -429,7 +522,7 @@ int cutesdr_bank_set_demod(cutesdr_bank* b, int c, int mode, const cutesdr_demod
     CSDR_CK(cudaSetDevice(b->device));
     ChanCfg& cc = b->ch[c];
     cc.info = *info;                                   // dsp/demodulator.cpp:110
-    bool new_demod = false;
+    bool new_demod = false, chain_changed = false;
     if (cc.mode != mode) {                             // :111-142
         cc.mode = mode;
         new_demod = true;
@@ -440,7 +533,7 @@ int cutesdr_bank_set_demod(cutesdr_bank* b, int c, int mode, const cutesdr_demod
             // which adds the current CW offset once more (dsp/downconvert.cpp:98-107,168)
             cc.dc_max_bw = cc.max_bw;
             cc.dc_nco_freq = cc.dc_nco_freq + cc.dc_cw;
-            b->layout_dirty = true;
+            chain_changed = true;
         }
     }
     cc.demod_cw = cc.info.Offset;                      // :143-144
@@ -448,6 +541,12 @@ int cutesdr_bank_set_demod(cutesdr_bank* b, int c, int mode, const cutesdr_demod
     const bool first = !cc.configured;
     cc.configured = true;
     if (first) b->layout_dirty = true;
+    if (chain_changed && !b->layout_dirty && cc.group >= 0) {
+        cc.demod_cw = cc.info.Offset;
+        CSDR_TRY(b->move_channel(c));                  // restarts this channel only
+        return CUTESDR_OK;
+    }
+    if (chain_changed) b->layout_dirty = true;
     if (!b->layout_dirty) CSDR_TRY(apply_channel(b, c, new_demod));
     return CUTESDR_OK;
 }
@@ -676,11 +775,13 @@ static int bank_process_host(cutesdr_bank* b, int n_in, const void* iq, int fmt,
         CSDR_TRY(b->run_block(dblk, dfmt, audio ? b->d_audio : nullptr, b->audio_cap, goff.data(), &m));
         for (size_t gi = 0; gi < b->groups.size(); gi++) {
             Group& g = *b->groups[gi];
-            if (g.chans.empty()) continue;
-            int produced = b->blk_nout[g.chans[0]];
+            int first = -1;
+            for (int c : g.chans) if (c >= 0) { first = c; break; }
+            if (first < 0) continue;
+            int produced = b->blk_nout[first];
             if (produced > 0 && audio) {
                 // PROFILE_4 tap = the audio rows themselves
-                for (int c : g.chans) if (b->ch[c].tap_mask & 16u) {
+                for (int c : g.chans) if (c >= 0 && (b->ch[c].tap_mask & 16u)) {
                     CSDR_TRY(b->sync_all());
                     const int w = b->stereo ? 2 : 1;
                     std::vector<float> tmp((size_t)w * produced);
@@ -690,7 +791,7 @@ static int bank_process_host(cutesdr_bank* b, int n_in, const void* iq, int fmt,
                 }
             }
             goff[gi] += produced;
-            for (int c : g.chans) nout[c] += produced;
+            for (int c : g.chans) if (c >= 0) nout[c] += produced;
             nmax = std::max(nmax, goff[gi]);
         }
         CSDR_TRY(b->collect_taps());
@@ -925,7 +1026,7 @@ int cutesdr_bank_tap_enable(cutesdr_bank* b, int c, unsigned profile_mask)
     for (int p = 1; p <= 4; p++) b->ch[c].tap[p].clear();
     for (auto& g : b->groups) {
         g->any_tap = false;
-        for (int u : g->chans) if (b->ch[u].tap_mask & 0xEu) g->any_tap = true;
+        for (int u : g->chans) if (u >= 0 && (b->ch[u].tap_mask & 0xEu)) g->any_tap = true;
     }
     return CUTESDR_OK;
 }

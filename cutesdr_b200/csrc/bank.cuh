@@ -27,7 +27,10 @@ struct ChanCfg {
 
 struct Group {
     double max_bw = 0;
-    std::vector<int> chans;              // user channel index of each local channel
+    std::vector<int> chans;              // user channel index of each local slot in use (-1 = parked slot)
+    int cap = 0;                         // slots allocated (the stage objects' stride)
+    std::vector<int> h_chan_map;         // host copy of d_chan_map
+    csdr::PinnedStage stage;
     Decimator dec;
     FirBank fir;
     PostBank post;
@@ -113,6 +116,8 @@ struct cutesdr_bank {
     std::vector<std::unique_ptr<csdr::TapSpectrum>> tap_spectra;
 
     int rebuild();
+    int create_group(double max_bw, const std::vector<int>& chans, int min_cap, int* index);
+    int move_channel(int c);             // channel c's decimation chain changed on a running bank
     int run_block(const void* d_block, int fmt, float* d_audio_out, int audio_stride, const int* audio_off, int* n_out_max);
     int collect_taps();
     int feed_tap_spectra(csdr::Group& g, int gi, int n_burst, float* d_audio_out, int audio_stride, int audio_off);

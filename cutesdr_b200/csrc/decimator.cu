@@ -1552,6 +1552,20 @@ void Decimator::set_frequency(int i, double nco_freq)
     tc_dirty_ = true;
 }
 
+int Decimator::reset_channel(int i)
+{
+    if (i < 0 || i >= stride_) { set_error("Decimator::reset_channel: slot %d of %d", i, stride_); return CUTESDR_E_ARG; }
+    if (overlap_) CSDR_TRY(join_main());
+    for (size_t s = 0; s < d_stage_.size(); s++)      // time-major rings: one float2 column
+        CSDR_CK(cudaMemset2DAsync(d_stage_[s] + i, (size_t)stride_ * sizeof(float2), 0, sizeof(float2), stage_rows_[s], st_));
+    CSDR_CK(cudaMemsetAsync(d_ring_ + (size_t)i * kDecRing, 0, (size_t)kDecRing * sizeof(float2), st_));
+    for (int k = 0; k < 2; k++) CSDR_CK(cudaMemsetAsync(d_phase_[k] + i, 0, sizeof(unsigned long long), st_));
+    h_nco_[i] = NcoDev{0ull, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f};
+    dirty_ = true;
+    tc_dirty_ = true;
+    return CUTESDR_OK;
+}
+
 int Decimator::upload_dirty()
 {
     if (!dirty_) return CUTESDR_OK;

@@ -47,6 +47,10 @@ public:
 
     // CDownConvert::SetFrequency for local channel i (freq already includes the CW offset)
     void set_frequency(int i, double nco_freq);
+    // A new CDownConvert chain for local channel i only (CDownConvert::SetDataRate rebuilds the stage objects,
+    // dsp/downconvert.cpp:114-173): its stage histories, decimated ring and oscillator phase restart from zero, queued in
+    // stream order; every other channel's state is untouched.
+    int reset_channel(int i);
 
     // Run one block of L <= block_len samples (L a multiple of 2^stages; L < 0 = the full block).
     // d_x: the block (device, complex64, 16-byte aligned). halo_cur: kHaloMax samples that preceded

@@ -231,11 +231,11 @@ int FirBank::init(int nch, int stride, cudaStream_t st, LaunchCounter* lc)
 {
     static_assert(sizeof(FirJob) == sizeof(Job), "job layout");
     nch_ = nch; stride_ = stride; st_ = st; lc_ = lc;
-    cur_.assign(nch, Params{-1.0, 1.0, 1.0, 1.0});        // CFastFIR ctor, dsp/fastfir.cpp:126-129
+    cur_.assign(stride, Params{-1.0, 1.0, 1.0, 1.0});     // CFastFIR ctor, dsp/fastfir.cpp:126-129
     h_id_.assign(stride, 0);
     // row 0 = all zeros (a channel that never had a valid SetupParameters); every other row is referenced by at
-    // least one channel, so nch + 1 rows always suffice
-    cap_ = nch + 1;
+    // least one channel, so (slots + 1) rows always suffice
+    cap_ = stride + 1;
     refs_.assign(cap_, 0);
     row_key_.assign(cap_, Key{0, 0, 0});
     free_.clear();

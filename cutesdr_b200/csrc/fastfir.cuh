@@ -13,7 +13,9 @@ public:
     FirBank(const FirBank&) = delete;
     FirBank& operator=(const FirBank&) = delete;
 
+    // nch channels in use out of `stride` slots; set_nch changes the number in use later (slots are all allocated)
     int init(int nch, int stride, cudaStream_t st, LaunchCounter* lc);
+    void set_nch(int n) { nch_ = n; }
     // CFastFIR::SetupParameters for local channel i. Host bookkeeping only: the design itself (windowed sinc +
     // 2048-point FFT, dsp/fastfir.cpp:207-254) runs ON THE DEVICE, queued in stream order by the next run() --
     // a retune never synchronises the stream and never stalls the other channels.

@@ -621,13 +621,13 @@ int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream
         uni_.lp_a1 = A * (-2.0 * cos(w0));
         uni_.lp_a2 = A * (1.0 - alpha);
     }
-    agc_.assign(nch, AgcHost());
-    fm_bw_.assign(nch, 3000.0);
+    agc_.assign(stride, AgcHost());
+    fm_bw_.assign(stride, 3000.0);
     h_par_.assign((size_t)P_COUNT * stride, 0.0);
     h_taps_.assign((size_t)kFirMax * stride, 0.0);
     h_mode_.assign(stride, POST_NONE);
     h_reset_.assign(stride, 0);
-    for (int i = 0; i < nch; i++) {
+    for (int i = 0; i < stride; i++) {
         h_reset_[i] = R_AGC | R_DEMOD | R_FIR | R_SMETER;
         h_par_[(size_t)P_AGC_ON * stride + i] = 1.0;
         h_par_[(size_t)P_NTAPS * stride + i] = 1.0;
@@ -699,6 +699,18 @@ void PostBank::set_mode(int i, int mode)
     if (m == POST_FM) {   // CFmDemod ctor designs its squelch high-pass for 3 kHz (dsp/fmdemod.cpp:79,88)
         fm_bw_[i] = -1.0;
     }
+    dirty_ = true;
+}
+
+void PostBank::free_channel(int i)
+{
+    // the slot's next user is a new CDemodulator: new CAgc, CSMeter and demodulator objects
+    h_mode_[i] = POST_NONE;
+    h_reset_[i] = R_AGC | R_DEMOD | R_FIR | R_SMETER;
+    agc_[i] = AgcHost();
+    fm_bw_[i] = 3000.0;
+    h_par_[(size_t)P_AGC_ON * stride_ + i] = 1.0;
+    h_par_[(size_t)P_NTAPS * stride_ + i] = 1.0;
     dirty_ = true;
 }
 
@@ -784,7 +796,7 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
     b.row = max_n_; b.v = d_v_; b.v2 = d_v2_; b.sam_taps = d_sam_taps_; b.v_row = v_row_; b.par = d_par_; b.taps = d_taps_; b.mode = d_mode_; b.reset = d_reset_;
     b.state = d_state_; b.istate = d_istate_; b.nch = nch_; b.stride = stride_; b.qpow = d_qpow_;
     if (need_reset_kernel_) {
-        k_post_reset<<<nch_, 128, 0, st_>>>(b);
+        k_post_reset<<<stride_, 128, 0, st_>>>(b);      // every slot: parked slots keep their flags until used
         lc_->n++;
         need_reset_kernel_ = false;
     }

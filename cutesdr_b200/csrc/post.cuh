@@ -37,6 +37,9 @@ public:
     // new demodulator object for local channel i (zeroes its demod state); mode is a
     // CUTESDR_DEMOD_* value or POST_AGC_ONLY
     void set_mode(int i, int mode);
+    // slots in use (<= stride); free_channel parks a slot (no demodulator, all state re-initialised at its next use)
+    void set_nch(int n) { nch_ = n; }
+    void free_channel(int i);
     // CAgc::SetParameters (rate is the group's)
     void set_agc(int i, int on, int hang, int thresh, int manual_gain, int slope, int decay);
     // CAmDemod::SetBandwidth -- re-designs AND zeroes the post filter (dsp/amdemod.cpp:56-60)

@@ -136,6 +136,12 @@ int ResamplerBank::init(int nrows, int max_in, cudaStream_t st, LaunchCounter* l
     return CUTESDR_OK;
 }
 
+int ResamplerBank::reset_row(int r)
+{
+    CSDR_CK(cudaMemsetAsync(d_w_ + (size_t)r * row_len_, 0, (size_t)width_ * kRsPeriods * sizeof(float), st_));
+    return CUTESDR_OK;
+}
+
 int ResamplerBank::run(int n_in, double rate, float* d_out, int out_stride, int out_off, const int* d_row_map,
                        int* n_out, int16_t* d_out16, double gain, int interleave16)
 {

@@ -35,6 +35,9 @@ public:
     // Resample(.., TYPECPX*, TYPESTEREO16*/TYPECPX*), dsp/fractresampler.cpp:194-249,309-352: same clock, same
     // weights, two accumulators.
     int init(int nrows, int max_in, cudaStream_t st, LaunchCounter* lc, int width = 1);
+    // rows in use (<= the nrows given to init); reset_row zeroes one row's 28 carried inputs in stream order
+    void set_rows(int n) { nrows_ = n; }
+    int reset_row(int r);
     // device buffer the producer writes new inputs into: row r starts at in_ptr() + r*in_stride()
     float* in_ptr() { return d_w_ + width_ * kRsPeriods; }
     int in_stride() const { return row_len_; }

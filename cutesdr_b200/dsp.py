@@ -306,6 +306,13 @@ def channel_slice(n_channels, rank, world):
     return f.value, n.value
 
 
+def device_memory(device=0):
+    """(free, total) bytes of the device, cudaMemGetInfo."""
+    f, t = C.c_longlong(), C.c_longlong()
+    check(load_library().cutesdr_device_memory(int(device), C.byref(f), C.byref(t)))
+    return f.value, t.value
+
+
 def microbench(which, device=0):
     """0 FP32 FMA TFLOP/s, 1 tcgen05 tf32 TFLOP/s, 2 tcgen05 f16 TFLOP/s, 3 HBM copy GB/s (cutesdr_microbench)."""
     v = C.c_double()

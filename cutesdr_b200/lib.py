@@ -36,6 +36,7 @@ PROTOTYPES = {
     "cutesdr_version": (C.c_char_p, []),
     "cutesdr_device_count": (C.c_int, [_ip]),
     "cutesdr_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
+    "cutesdr_device_memory": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "cutesdr_bank_create": (C.c_int, [_pp, C.c_int, C.c_double, C.c_int]),
     "cutesdr_bank_destroy": (None, [_vp]),
     "cutesdr_bank_set_demod": (C.c_int, [_vp, C.c_int, C.c_int, _info]),

@@ -62,6 +62,8 @@ int cutesdr_device_count(int* n);
  * them): which = 0 FP32 FMA issue peak [TFLOP/s], 1 tcgen05 kind::tf32 dense peak [TFLOP/s], 2 tcgen05 kind::f16
  * dense peak [TFLOP/s], 3 HBM copy bandwidth [GB/s, read + write]. Each takes a few milliseconds. */
 int cutesdr_microbench(int device, int which, double* value);
+/* cudaMemGetInfo of `device` (tests use it to show that a long-running, constantly retuned bank does not grow) */
+int cutesdr_device_memory(int device, long long* free_bytes, long long* total_bytes);
 
 /* ======================================================================================
  * Receiver bank: N virtual receivers ( = N independent CDemodulator objects,
@@ -73,7 +75,12 @@ typedef struct cutesdr_bank cutesdr_bank;
 int cutesdr_bank_create(cutesdr_bank** out, int n_channels, double in_rate, int device);
 void cutesdr_bank_destroy(cutesdr_bank* b);
 
-/* CDemodulator::SetDemod(Mode, info) for channel ch          dsp/demodulator.cpp:107-157 */
+/* CDemodulator::SetDemod(Mode, info) for channel ch          dsp/demodulator.cpp:107-157
+ * On a running bank every change is live and touches this channel only: filter / AGC / squelch parameters are swapped
+ * for the next burst; a mode change that alters the decimation chain (another m_DesiredMaxOutputBandwidth, :116-121)
+ * restarts THIS channel's chain and demodulator from zero state -- it moves to a slot of the channel group with the new
+ * chain -- while all other channels run on bit-identically. (Only a chain whose DSP block length differs from the
+ * bank's forces a rebuild of the whole bank.) */
 int cutesdr_bank_set_demod(cutesdr_bank* b, int ch, int mode, const cutesdr_demod_info* info);
 /* CDemodulator::SetDemodFreq(Freq) for channel ch             dsp/demodulator.h:68-69 */
 int cutesdr_bank_set_demod_freq(cutesdr_bank* b, int ch, double freq);

@@ -903,3 +903,103 @@ def test_testbench_tap_spectra_on_device(lib, orc, mode, lo, hi):
     assert checked >= 8
     for p in ffts:
         bank.tap_spectrum(0, p, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# Live control storm: retunes, filter changes and chain changes on a running bank touch the
+# changed channel only
+# ------------------------------------------------------------------------------------------------
+def test_retune_storm_leaves_other_channels_bit_identical(lib, orc):
+    """64 control changes per DSP block for 100 blocks (SetDemodFreq, SetDemod with a new filter -- designed on the
+    device --, and mode changes that alter the decimation chain: AM <-> USB <-> CWU). The channels nobody touched must
+    be BIT-IDENTICAL to an undisturbed bank's, device memory must stay flat once the groups exist, and a channel
+    that changed chain must settle onto what a CDemodulator started at that moment produces
+    (dsp/demodulator.cpp:107-157: only that object's chain and demodulator restart)."""
+    fs, nch, nblk = 2e6, 160, 100
+    quiet = list(range(96, nch))
+    base_modes = [[M.DEMOD_AM, M.DEMOD_USB, M.DEMOD_FM, M.DEMOD_CWU][c % 4] for c in range(nch)]
+    carriers = carrier_grid(nch, 11000.0)
+
+    def info(m, lo=None, hi=None, agc=True):
+        d = {M.DEMOD_AM: (-5000, 5000), M.DEMOD_USB: (100, 2800), M.DEMOD_FM: (-5000, 5000), M.DEMOD_CWU: (-250, 250)}[m]
+        return M.demod_info(m, LowCut=d[0] if lo is None else lo, HiCut=d[1] if hi is None else hi,
+                            Offset=700 if m == M.DEMOD_CWU else 0, AgcOn=agc, AgcManualGain=60)
+
+    def make():
+        b = cs.ReceiverBank(nch, fs)
+        for c in range(nch):
+            b.SetDemod(c, base_modes[c], info(base_modes[c]))
+            b.SetDemodFreq(c, -carriers[c])
+        return b
+
+    calm, storm = make(), make()
+    L = calm.block_length()
+    iq = _cheap_wideband(L, nblk, seed=77)
+    rng = np.random.default_rng(4242)
+    cur_mode = list(base_modes)
+    moved_at = {}                 # channel -> (block, mode, info, freq) of its LAST chain change (AGC off)
+    mem = {}
+    got = {c: [] for c in range(nch)}
+    ref_quiet = {c: [] for c in quiet}
+    for k in range(nblk):
+        if k >= 2:
+            # channels 32..95: retunes and filter changes (all 64 of them per block once the moves have stopped);
+            # channels 0..31: chain changes, 4 per block until block 60 (so the last ones can be checked afterwards)
+            n_move = 4 if k < 60 else 0
+            for c in rng.choice(np.arange(32, 96), size=64 - n_move, replace=False):
+                c = int(c)
+                m = cur_mode[c]
+                if rng.integers(0, 3) or m in (M.DEMOD_FM, M.DEMOD_CWU):
+                    storm.SetDemodFreq(c, -carriers[c] + float(rng.integers(-800, 800)))
+                elif m == M.DEMOD_AM:
+                    w = int(rng.integers(2000, 5000))
+                    storm.SetDemod(c, m, info(m, -w, w))
+                else:
+                    storm.SetDemod(c, m, info(m, 100 + int(rng.integers(0, 300)), 2400 + int(rng.integers(0, 600))))
+            for c in rng.choice(32, size=n_move, replace=False):
+                c = int(c)
+                # chain change: AM (31.25 kHz) -> USB (62.5 kHz) -> CWU (15.625 kHz) -> AM ...
+                nxt = {M.DEMOD_AM: M.DEMOD_USB, M.DEMOD_USB: M.DEMOD_CWU, M.DEMOD_CWU: M.DEMOD_AM, M.DEMOD_FM: M.DEMOD_AM}[cur_mode[c]]
+                i2 = info(nxt, agc=False)
+                storm.SetDemod(c, nxt, i2)
+                storm.SetDemodFreq(c, -carriers[c])
+                cur_mode[c] = nxt
+                moved_at[c] = (k, nxt, i2, -carriers[c])
+                got[c] = []
+        blk = iq[k * L:(k + 1) * L]
+        a1, n1 = calm.ProcessData(blk)
+        a2, n2 = storm.ProcessData(blk)
+        for c in quiet:
+            ref_quiet[c].append(a1[c, :n1[c]].copy())
+        for c in range(nch):
+            got[c].append(a2[c, :n2[c]].copy())
+        if k in (62, nblk - 1):
+            mem[k] = cs.device_memory()[0]
+    for c in quiet:
+        a, b = np.concatenate(ref_quiet[c]), np.concatenate(got[c])
+        assert len(a) == len(b) > 0 and np.array_equal(a, b), "untouched channel %d changed" % c
+    assert mem[nblk - 1] >= mem[62] - (1 << 20), "device memory grew by %d bytes during the retune storm" % (mem[62] - mem[nblk - 1])
+    assert len(moved_at) >= 20
+    # moved channels: compare with a CDemodulator started at the move (AGC off -> the chain is linear and time
+    # invariant once the filters have filled; the bank's burst grid is the group's, so the streams differ by a lag)
+    checked = 0
+    for c, (k0, mode, i2, f) in sorted(moved_at.items()):
+        if checked >= 8:
+            break
+        d = orc.Demodulator()
+        d.SetInputSampleRate(fs)
+        d.SetDemod(mode, i2)
+        d.SetDemodFreq(f)
+        exp = d.run(iq[k0 * L:])
+        y = np.concatenate(got[c])
+        if min(len(exp), len(y)) < 3072 + 2048 + 1024:
+            continue              # narrow chains (CWU: 78 samples per block) moved late have too little output
+        best = -1e9
+        for lag in range(-1024, 1025):
+            a = exp[3072:3072 + 2048]
+            b = y[3072 + lag:3072 + lag + 2048]
+            if len(b) == len(a):
+                best = max(best, snr_db(a, b))
+        assert best > SNR_MIN, "moved channel %d (%s at block %d): best alignment %.1f dB" % (c, M.MODE_NAMES[mode], k0, best)
+        checked += 1
+    assert checked >= 3
