@@ -17,6 +17,7 @@
 // Reference: CDownConvert::ProcessData and the three DecBy2 classes, dsp/downconvert.cpp:186-460.
 #include "decimator.cuh"
 #include "halfband_tables.h"
+#include <cuda.h>            // CUtensorMap + cuTensorMapEncodeTiled prototype (resolved at run time through the runtime)
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -37,6 +38,11 @@ Tuning Tuning::from_env()
     if (const char* e = getenv("CUTESDR_FUSE_HB")) t.fuse_hb = atoi(e);
     if (const char* e = getenv("CUTESDR_TILE")) t.tile = atoi(e);
     if (const char* e = getenv("CUTESDR_TC_SEG")) t.tc_seg = atoi(e);
+    t.no_hbstream = getenv("CUTESDR_NO_HBSTREAM") != nullptr;
+    t.no_hbtail = getenv("CUTESDR_NO_HBTAIL") != nullptr;
+    if (const char* e = getenv("CUTESDR_HS_HALO")) t.hs_halo = atoi(e);
+    if (const char* e = getenv("CUTESDR_TC_SPARE")) t.tc_spare = std::max(0, atoi(e));
+    if (const char* e = getenv("CUTESDR_HS_CTAS")) t.hs_ctas = std::max(1, atoi(e));
     return t;
 }
 
@@ -1215,6 +1221,140 @@ __global__ void __launch_bounds__(256) k_hb_tail(const float2* __restrict__ in, 
 }
 
 // ------------------------------------------------------------------------------------------
+// K2s: the first THREE half-band stages after kernel 1 (11, 11 and 11 or 15 taps: 7/8 of kernel 2's input bytes) in one
+// streaming pass, state in REGISTERS. Lane = channel (32 channels = one 256-byte row of the time-major stage ring),
+// warp = time slice: every warp walks its slice row by row through all three stages with register delay lines, like
+// kernel 1's epilogue does for its fused stages, so a row costs ONE shared-memory load and ~7 packed FP32x2
+// instructions per channel instead of a gather of 7-8 loads per output and stage -- the pass is bound by HBM, not by
+// instruction issue. Rows arrive through a per-warp ring of TMA boxes (cp.async.bulk.tensor.2d, 32 rows x 256 B,
+// completion on an mbarrier, three boxes in flight ahead of the arithmetic); warps never synchronise with each other.
+// A slice re-primes its (feed-forward) delay lines from 86-117 rows in front of it: the stage ring in HBM keeps the
+// previous block. Per output the operation sequence is k_halfband's (centre tap, then the outermost pair inwards;
+// FADD2/FFMA2 on the (re, im) pair round exactly like the scalar pair), so every path gives the same bits.
+// ------------------------------------------------------------------------------------------
+constexpr int kH3Ch = 32;          // channels per warp (float2 each: 256-byte rows)
+constexpr int kH3Box = 32;         // rows per TMA box
+constexpr int kH3Boxes = 4;        // boxes in a warp's shared-memory ring
+constexpr int kH3Warps = 2;        // time slices per CTA
+constexpr int kH3Smem = kH3Warps * kH3Boxes * kH3Box * kH3Ch * 8;
+
+template <int N> struct HbR {      // streaming half-band decimator, N = 11 or 15
+    static constexpr int H = (N - 1) / 2, NP = (H + 1) / 2;      // even-sample history, tap pairs ( = odd-sample history)
+    float2 e[H];                   // e[0] = most recent even-indexed input
+    float2 o[NP];                  // o[0] = most recent odd-indexed input
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int i = 0; i < H; i++) e[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NP; i++) o[i] = make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ void odd(float2 v)
+    {
+#pragma unroll
+        for (int i = NP - 1; i > 0; i--) o[i] = o[i - 1];
+        o[0] = v;
+    }
+    // even-indexed input x[2m] completes output m
+    __device__ __forceinline__ float2 even(float2 v, const float* h)
+    {
+        float2 acc = __fmul2_rn(make_float2(0.5f, 0.5f), o[NP - 1]);
+        acc = __ffma2_rn(make_float2(h[0], h[0]), __fadd2_rn(e[H - 1], v), acc);
+#pragma unroll
+        for (int k = 1; k < NP; k++) acc = __ffma2_rn(make_float2(h[k], h[k]), __fadd2_rn(e[H - 1 - k], e[k - 1]), acc);
+#pragma unroll
+        for (int i = H - 1; i > 0; i--) e[i] = e[i - 1];
+        e[0] = v;
+        return acc;
+    }
+};
+
+template <int L2>
+__global__ void __launch_bounds__(32 * kH3Warps) k_hb3r(const __grid_constant__ CUtensorMap tmap, unsigned in_mask, long long in_base, int n_out,
+                                                         int per_slice, int toff2, OutDesc od)
+{
+    extern __shared__ __align__(128) unsigned char h3_smem[];
+    __shared__ __align__(8) uint64_t full[kH3Warps][kH3Boxes];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slice = blockIdx.x * kH3Warps + warp;
+    const int o0 = slice * per_slice;
+    const int o1 = min(o0 + per_slice, n_out);
+    if (o0 >= o1) return;                                     // whole warp; warps are independent
+    const float2* ring = reinterpret_cast<const float2*>(h3_smem) + (size_t)warp * kH3Boxes * kH3Box * kH3Ch;
+    constexpr int HALO = 2 * (2 * (L2 - 1) + 10) + 10;        // stage-0 rows in front of output o0's first stage-2 input
+    // the slice's stream starts on a 32-row boundary of the ring (in_base is a multiple of 32: no box straddles the ring
+    // end, and a row's parity at every stage is its position in the box)
+    const long long abs0 = (in_base + 8LL * o0 - HALO) & ~(long long)(kH3Box - 1);
+    const int first0 = (int)(abs0 - in_base);
+    const int n_boxes = (8 * (o1 - 1) - first0) / kH3Box + 1;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kH3Boxes; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[warp][i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int b) {
+        const uint32_t bar = smem_u32(&full[warp][b & (kH3Boxes - 1)]);
+        const int y = (int)((abs0 + (long long)b * kH3Box) & (long long)in_mask);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kH3Box * kH3Ch * 8) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                         smem_u32(ring + (size_t)(b & (kH3Boxes - 1)) * kH3Box * kH3Ch)),
+                     "l"(&tmap), "r"((int)(blockIdx.y * kH3Ch * 2)), "r"(y), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0)
+        for (int b = 0; b < kH3Boxes - 1 && b < n_boxes; b++) issue(b);
+    float h0[3], h2[HbR<L2>::NP];
+#pragma unroll
+    for (int i = 0; i < 3; i++) h0[i] = c_hb_taps[i];         // 11-tap stage: table offset 0
+#pragma unroll
+    for (int i = 0; i < HbR<L2>::NP; i++) h2[i] = c_hb_taps[toff2 + i];
+    HbR<11> s0, s1;
+    HbR<L2> s2;
+    s0.clear(); s1.clear(); s2.clear();
+    const int c = blockIdx.y * kH3Ch + lane;
+    for (int b = 0; b < n_boxes; b++) {
+        // boxes 0 .. kH3Boxes-2 were issued up front; box b + kH3Boxes - 1 goes into the slot of box b - 1, which the whole
+        // warp finished with one iteration ago (for b = 0 that slot has never been used): three boxes stay in flight
+        if (lane == 0 && b + kH3Boxes - 1 < n_boxes) issue(b + kH3Boxes - 1);
+        {
+            const uint32_t bar = smem_u32(&full[warp][b & (kH3Boxes - 1)]);
+            const uint32_t parity = (uint32_t)((b / kH3Boxes) & 1);
+            asm volatile(
+                "{\n\t.reg .pred p;\n"
+                "W_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra D_%=;\n\t"
+                "bra W_%=;\n"
+                "D_%=:\n\t}\n" ::"r"(bar),
+                "r"(parity)
+                : "memory");
+        }
+        const float2* x = ring + (size_t)(b & (kH3Boxes - 1)) * kH3Box * kH3Ch + lane;
+        const int m_box = (first0 + b * kH3Box) >> 3;         // stage-2 output index completed by row 0 of this box
+#pragma unroll
+        for (int r = 0; r < kH3Box; r++) {
+            const float2 v = x[r * kH3Ch];
+            if (r & 1) s0.odd(v);
+            else {
+                const float2 y0 = s0.even(v, h0);
+                if (r & 2) s1.odd(y0);
+                else {
+                    const float2 y1 = s1.even(y0, h0);
+                    if (r & 4) s2.odd(y1);
+                    else {
+                        const float2 y2 = s2.even(y1, h2);
+                        const int m = m_box + (r >> 3);
+                        if (m >= o0 && m < o1) store_out(od, m, c, y2);
+                    }
+                }
+            }
+        }
+        __syncwarp();          // every lane is done with this box before lane 0 lets the next iteration refill its neighbour
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K2: one decimate-by-2 stage, thread per (output row m, channel c)
 //   half-band : y[m] = sum_j h[j] x[2m-(N-1)+j]            (dsp/downconvert.cpp:286-320, 348-423)
 //   N == 3    : CIC3, y[m] = .125 (x[2m+1] + 3x[2m] + 3x[2m-1] + x[2m-2])          (:444-460)
@@ -1423,7 +1563,7 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
         long long hist = 0;
         for (int j = nhb - 1; j >= s; j--) hist = std::min<long long>(2 * hist + (lens_[k1_stages() + j] - 1), 8192);
         // ring 0 keeps two blocks so kernel 1 of block k+1 can fill it while kernel 2 still reads block k
-        int rows = next_pow2((long long)n_rows * (s == 0 ? 2 : 1) + 64 + (nhb - s <= 4 ? hist : 0));
+        int rows = next_pow2((long long)n_rows * (s == 0 ? 2 : 1) + 64 + ((nhb - s <= 4 || s == 0) ? hist + kH3Box : 0));
         float2* p = nullptr;
         size_t bytes = (size_t)rows * stride_ * sizeof(float2);
         CSDR_CK(cudaMalloc(&p, bytes));
@@ -1431,6 +1571,33 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
         d_stage_.push_back(p);
         stage_rows_.push_back(rows);
         stage_base_.push_back(0);
+    }
+    // kernel 2s (register-streaming pass over the first three stages) applies when they are 11, 11 and 11 or 15 taps long,
+    // which is every ladder of SURVEY's configs once kernel 1 has taken its share
+    hs_stages_ = 0;
+    if (nhb >= 3 && stride_ % kH3Ch == 0 && !tun_.no_hbstream && (block_len >> k1_stages()) % kH3Box == 0 &&
+        lens_[k1_stages()] == 11 && lens_[k1_stages() + 1] == 11 && (lens_[k1_stages() + 2] == 11 || lens_[k1_stages() + 2] == 15))
+        hs_stages_ = 3;
+    if (hs_stages_ > 0) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CSDR_CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return CUTESDR_E_CUDA; }
+        // stage ring 0 as a 2-D tensor of floats: x = 2 floats per channel (row = 2 stride floats), y = ring rows
+        const cuuint64_t dims[2] = {(cuuint64_t)2 * stride_, (cuuint64_t)stage_rows_[0]};
+        const cuuint64_t strides[1] = {(cuuint64_t)stride_ * sizeof(float2)};
+        const cuuint32_t box[2] = {2 * kH3Ch, kH3Box};
+        const cuuint32_t estr[2] = {1, 1};
+        static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+        const CUresult r = reinterpret_cast<EncodeFn>(fn)(reinterpret_cast<CUtensorMap*>(tmap0_), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_stage_[0], dims,
+                                                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CUTESDR_E_CUDA; }
+        CSDR_CK(cudaFuncSetAttribute(k_hb3r<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, kH3Smem));
+        CSDR_CK(cudaFuncSetAttribute(k_hb3r<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, kH3Smem));
     }
     size_t rbytes = (size_t)stride_ * kDecRing * sizeof(float2);
     CSDR_CK(cudaMalloc(&d_ring_, rbytes));
@@ -1510,7 +1677,8 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
         // outputs and rounds up to whole MMA tiles
         const int pre = tc_pre(ncic_ - 4, nhbf_);
         {
-            const int ctas_x = std::max(1, sms / tc_groups_);
+            // tc_spare SMs are left to the burst chain's packed sequential kernels (see post.cu)
+            const int ctas_x = std::max(1, (sms - tun_.tc_spare) / tc_groups_);
             int sl = (block_len + kTcSegs * ctas_x - 1) / (kTcSegs * ctas_x);
             tc_seg_len_ = std::max(256, (sl + 255) / 256 * 256);
         }
@@ -1659,7 +1827,42 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
     }
 
     int s_first = 0;
-    {
+    if (hs_stages_ == 3 && (L >> k1_stages()) % kH3Box == 0 && stage_base_[0] % kH3Box == 0) {
+        // kernel 2s: stages 0-2 in one register-streaming pass
+        const int L2 = lens_[k1_stages() + 2];
+        const int n2 = L >> (k1_stages() + 3);
+        int dev = 0, sms = 148;
+        CSDR_CK(cudaGetDevice(&dev));
+        CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int groups = stride_ / kH3Ch;
+        // ~hs_ctas x 2 warps per SM in total; a slice is at least 16 outputs (128 rows) so the ~100 priming rows stay a fraction
+        int slices = std::max(1, std::min(n2 / 16, (sms * tun_.hs_ctas * kH3Warps + groups / 2) / groups));
+        slices = (slices + kH3Warps - 1) / kH3Warps * kH3Warps;
+        const int per_slice = (n2 + slices - 1) / slices;
+        OutDesc o2;
+        if (3 < nhb) {
+            o2.p = d_stage_[3];
+            o2.mask = (unsigned)(stage_rows_[3] - 1);
+            o2.stride = stride_;
+            o2.transposed = 0;
+            o2.base = stage_base_[3];
+        } else {
+            o2.p = d_ring_;
+            o2.mask = 0;
+            o2.stride = stride_;
+            o2.transposed = 1;
+            o2.base = total_out_;
+        }
+        dim3 grid(((n2 + per_slice - 1) / per_slice + kH3Warps - 1) / kH3Warps, groups);
+        const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(tmap0_);
+        if (L2 == 11) k_hb3r<11><<<grid, 32 * kH3Warps, kH3Smem, s2>>>(tm, (unsigned)(stage_rows_[0] - 1), stage_base_[0], n2, per_slice, tap_offset_for(11), o2);
+        else k_hb3r<15><<<grid, 32 * kH3Warps, kH3Smem, s2>>>(tm, (unsigned)(stage_rows_[0] - 1), stage_base_[0], n2, per_slice, tap_offset_for(15), o2);
+        lc_->n++;
+        CSDR_CK(cudaGetLastError());
+        for (int s = 0; s < 3; s++) stage_base_[s] += (L >> (k1_stages() + s));
+        s_first = 3;
+    }
+    if (s_first == 0) {
         // leading run of 11-tap stages -> one fused pass
         int nchain = 0;
         while (nchain < 3 && nchain < nhb && lens_[k1_stages() + nchain] == 11) nchain++;
@@ -1705,7 +1908,7 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
         const int ns = nhb - s_first;
         // opt-in (CUTESDR_HBTAIL=1): measured neutral inside the step (0.322 vs 0.320 ms, cfg4) -- the three small launches it
         // replaces already overlap with the burst chain, and its deep halo recomputes ~1.8x of the first two stages
-        bool ok = ns >= 2 && ns <= 4 && stride_ % 16 == 0 && tun_.hbtail;
+        bool ok = ns >= 2 && ns <= 4 && stride_ % 16 == 0 && (tun_.hbtail || (s_first == 3 && hs_stages_ == 3 && !tun_.no_hbtail));
         for (int s = s_first; ok && s < nhb; s++) ok = lens_[k1_stages() + s] != 3;
         if (ok) {
             constexpr int CH = kHbcCh;

@@ -23,7 +23,8 @@ inline int sample_bytes(int fmt) { return fmt == 0 ? 8 : (fmt == 1 ? 4 : 6); }
 // None is needed for correctness; DESIGN.md section 7 lists them.
 struct Tuning {
     bool no_tc = false, tc_f16 = false, no_hbchain = false, hbtail = false, no_overlap = false, debug_timing = false;
-    int fuse_hb = -1, tile = 0, tc_seg = 0;
+    bool no_hbstream = false, no_hbtail = false;
+    int fuse_hb = -1, tile = 0, tc_seg = 0, hs_halo = 300, hs_ctas = 3, tc_spare = 0;
     static Tuning from_env();
 };
 
@@ -111,6 +112,9 @@ private:
     // stage rings: ring s holds the INPUT rows of half-band stage s (time-major [row][stride])
     std::vector<float2*> d_stage_;
     std::vector<int> stage_rows_;      // power of two
+    // kernel 2s (streaming fused half-bands): TMA descriptor of stage ring 0 and the number of stages it fuses
+    alignas(64) unsigned char tmap0_[128];
+    int hs_stages_ = 0;
     float2* d_ring_ = nullptr;
     bool overlap_ = false;
     Tuning tun_;

@@ -198,13 +198,19 @@ __device__ __forceinline__ void store16(double* __restrict__ p, const double* v)
     for (int i = 0; i < 8; i++) q[i] = make_double2(v[2 * i], v[2 * i + 1]);
 }
 
-// ---- sequential poles; one warp per CTA: even CTAs run the AGC averagers of 32 channels, odd CTAs
-// the S-meter of the same channels. 32 threads x <= 128 registers = 4096 registers, which is what is
-// left beside kernel 1's three resident CTAs, so these latency-bound loops run UNDER kernel 1.
-__global__ void __maxnreg__(128) k_post_seq1(PostBufs b, int n, PostUniform u)
+// ---- sequential poles; even warps run the AGC averagers of 32 channels, odd warps the S-meter of the same channels.
+// The loops are latency-bound (one dependent FP64 chain per lane), so the warps are PACKED: kSeqThreads per CTA puts the
+// whole bank on a handful of SMs instead of one 32-thread CTA on each of 64 SMs -- kernel 1T needs a whole SM (every
+// register) per CTA and cannot start on an SM that hosts even one of these warps for the ~100 us they live.
+// How far they can be packed is set by the FP64 pipe: one of these warps alone keeps it ~20 % (PLL loop) / ~8 % (averagers)
+// busy (ncu), so the PLL kernel gets 2 warps per CTA and the averagers 4 -- measured: 8 PLL warps per CTA run 3x slower.
+constexpr int kSeqThreads = 128;
+constexpr int kSeq2Threads = 64;
+__global__ void __launch_bounds__(kSeqThreads, 4) k_post_seq1(PostBufs b, int n, PostUniform u)
 {
-    const int c = (blockIdx.x >> 1) * 32 + threadIdx.x;
-    const bool smeter_warp = (blockIdx.x & 1) != 0;
+    const int gw = blockIdx.x * (kSeqThreads / 32) + (threadIdx.x >> 5);
+    const int c = (gw >> 1) * 32 + (threadIdx.x & 31);
+    const bool smeter_warp = (gw & 1) != 0;
     if (c >= b.nch) return;
     const int mode = b.mode[c];
     const int n16 = n & ~15;
@@ -322,7 +328,7 @@ __device__ __forceinline__ double wrap_pi(double d)
 }
 
 // ---- DC blockers and PLLs; thread per channel
-__global__ void __maxnreg__(128) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
+__global__ void __launch_bounds__(kSeq2Threads, 4) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
                                                   int audio_stride, int audio_off, const int* __restrict__ chan_map)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -800,13 +806,12 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
         lc_->n++;
         need_reset_kernel_ = false;
     }
-    const size_t smem_pre = 2 * (size_t)(kAgcBuf + max_n_) * sizeof(double);
     const size_t smem_fir = (size_t)((uni_.stereo ? 2 : 1) * (kHist + max_n_) + kFirMax + 16) * sizeof(double);
     const int seq_blocks = (nch_ + 31) / 32;
     k_post_pre<<<nch_, 256, 2 * (size_t)(uni_.agc_window - 1 + n) * sizeof(double), st_>>>(b, n, uni_.agc_window);
-    k_post_seq1<<<2 * seq_blocks, 32, 0, st_>>>(b, n, uni_);
+    k_post_seq1<<<(2 * seq_blocks * 32 + kSeqThreads - 1) / kSeqThreads, kSeqThreads, 0, st_>>>(b, n, uni_);
     k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, uni_.stereo, d_audio, audio_stride, audio_off, d_chan_map);
-    k_post_seq2<<<seq_blocks, 32, 0, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
+    k_post_seq2<<<(seq_blocks * 32 + kSeq2Threads - 1) / kSeq2Threads, kSeq2Threads, 0, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_fir<<<nch_, 256, smem_fir, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     lc_->n += 5;
     CSDR_CK(cudaGetLastError());

@@ -160,16 +160,17 @@ def test_kernel1t_many_channel_groups_and_ragged_group():
         assert np.abs(a1[0, :n1[0]]).max() > 0
 
 
-def test_fused_tail_halfbands_are_bit_identical():
-    """CUTESDR_HBTAIL=1 runs the last half-band stages (15..51 taps) in one pass (k_hb_tail) instead of one launch per
-    stage; same operation order, so the audio must not change by a bit."""
+def test_kernel2_paths_are_bit_identical():
+    """Kernel 2 has three forms of the same arithmetic: one launch per half-band stage (k_halfband / k_hb11_chain), the
+    register-streaming TMA pass over the first three stages (k_hb3r, default) and the fused last stages (k_hb_tail).
+    Every form keeps k_halfband's operation order per output, so the audio must not change by a bit."""
     fs = 100147200.0
-    nch = 64                                  # two chain groups of 32 channels (whole 128-byte channel rows)
+    nch = 64                                  # two chain groups of 32 channels (whole 256-byte channel rows)
     modes = [[M.DEMOD_FM, M.DEMOD_AM][c // 32] for c in range(nch)]
     carriers = carrier_grid(nch, 1.0e6)
     outs = []
-    for tail in (None, "1"):
-        with _env(CUTESDR_HBTAIL=tail):
+    for env in (dict(CUTESDR_NO_HBSTREAM="1"), dict(), dict(CUTESDR_NO_HBTAIL="1"), dict(CUTESDR_NO_HBSTREAM="1", CUTESDR_HBTAIL="1")):
+        with _env(**env):
             b = cs.ReceiverBank(nch, fs)
             for c in range(nch):
                 b.SetDemod(c, modes[c], M.demod_info(modes[c]))
@@ -180,8 +181,10 @@ def test_fused_tail_halfbands_are_bit_identical():
             a, n = b.ProcessData(x)
             outs.append((a, n, b.launch_count() - launches0))
     assert outs[0][1].max() > 0
-    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
-    assert outs[1][2] < outs[0][2]            # fewer launches: the fused pass really ran
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][0], o[0])
+    assert outs[1][2] < outs[2][2] < outs[0][2]            # fewer launches: the fused passes really ran
+    assert outs[3][2] < outs[0][2]
 
 
 def test_kernel1t_fp16_operand_form(orc):
