@@ -181,98 +181,174 @@ __global__ void __launch_bounds__(256) k_post_pre(PostBufs b, int n, int window)
     }
 }
 
-// Row access for the sequential kernels: every lane walks its own channel row, so a plain
-// `row[t]` load per step would expose the full memory latency 1024 times. Rows are read in
-// 16-sample chunks (one 128-byte line per lane) with the next chunk in flight while the current
-// one is consumed from registers.
-__device__ __forceinline__ void load16(const double* __restrict__ p, double* v)
+// ------------------------------------------------------------------------------------------
+// Row streaming for the sequential kernels (lane = channel, every lane walks its own row).
+// A plain per-lane load touches 32 different lines per warp instruction; at 8 LDG.128 + 8 STG.128 per 16 samples the
+// warps sat in the LSU queue (ncu: stall_lg 70 % of all samples) instead of in their 8-clock DFMA chains. (One bulk copy
+// per lane and chunk was measured too: 96 small cp.async.bulk per warp and chunk serialise in the copy engine, 3x slower.)
+// Rows now move as TILES of 32 channels x 16 samples: the warp copies a tile cooperatively with cp.async -- 8 lanes
+// cover one 128-byte row segment, so an instruction touches 4 full lines -- into a ring of stages in shared memory,
+// several tiles ahead of the arithmetic; results go back the same way (lane rows -> tile -> coalesced 16-byte stores).
+// Inside a tile the 16-byte chunk j of row r sits at chunk j ^ (r & 7), which makes both the cooperative accesses and the
+// per-lane LDS.128 / STS.128 of a quarter warp conflict-free.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileT = 16;                        // samples per tile row (128 bytes)
+constexpr int kTileD = 32 * kTileT;               // doubles per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// queue the copy of tile k (samples [16k, 16k+16) of rows c0..c0+31 that have their bit set in rowmask); base points at
+// sample 0 of row 0 of the array, rows are `stride` doubles apart
+__device__ __forceinline__ void tile_fetch(double* tile, const double* base, size_t stride, int c0, int k, uint32_t rowmask, int lane)
 {
-    const double2* q = reinterpret_cast<const double2*>(p);
+    const int j = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { const double2 d = q[i]; v[2 * i] = d.x; v[2 * i + 1] = d.y; }
+    for (int i = 0; i < 8; i++) {
+        const int r = 4 * i + (lane >> 3);
+        if ((rowmask >> r) & 1u)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(tile + r * kTileT + ((j ^ (r & 7)) << 1))),
+                         "l"(base + (size_t)(c0 + r) * stride + (size_t)k * kTileT + 2 * j)
+                         : "memory");
+    }
 }
-__device__ __forceinline__ void store16(double* __restrict__ p, const double* v)
+__device__ __forceinline__ void tile_store(const double* tile, double* base, size_t stride, int c0, int k, uint32_t rowmask, int lane)
 {
-    double2* q = reinterpret_cast<double2*>(p);
+    const int j = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 8; i++) q[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 8; i++) {
+        const int r = 4 * i + (lane >> 3);
+        if ((rowmask >> r) & 1u) {
+            const double2 v = *reinterpret_cast<const double2*>(tile + r * kTileT + ((j ^ (r & 7)) << 1));
+            *reinterpret_cast<double2*>(base + (size_t)(c0 + r) * stride + (size_t)k * kTileT + 2 * j) = v;
+        }
+    }
 }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// the lane's own row of a tile: samples 2j, 2j+1 as one 16-byte access
+__device__ __forceinline__ double2 row_ld(const double* tile, int lane, int j)
+{
+    return *reinterpret_cast<const double2*>(tile + lane * kTileT + ((j ^ (lane & 7)) << 1));
+}
+__device__ __forceinline__ void row_st(double* tile, int lane, int j, double a, double b)
+{
+    *reinterpret_cast<double2*>(tile + lane * kTileT + ((j ^ (lane & 7)) << 1)) = make_double2(a, b);
+}
+// keeps a loop-invariant operand in a register (the compiler otherwise re-reads kernel parameters from the constant bank
+// under a predicate inside a select, which turns a two-instruction clamp into a branch)
+__device__ __forceinline__ double in_reg(double v) { asm volatile("" : "+d"(v)); return v; }
 
 // ---- sequential poles; even warps run the AGC averagers of 32 channels, odd warps the S-meter of the same channels.
-// The loops are latency-bound (one dependent FP64 chain per lane), so the warps are PACKED: kSeqThreads per CTA puts the
-// whole bank on a handful of SMs instead of one 32-thread CTA on each of 64 SMs -- kernel 1T needs a whole SM (every
-// register) per CTA and cannot start on an SM that hosts even one of these warps for the ~100 us they live.
-// How far they can be packed is set by the FP64 pipe: one of these warps alone keeps it ~20 % (PLL loop) / ~8 % (averagers)
-// busy (ncu), so the PLL kernel gets 2 warps per CTA and the averagers 4 -- measured: 8 PLL warps per CTA run 3x slower.
-constexpr int kSeqThreads = 128;
-constexpr int kSeq2Threads = 64;
-__global__ void __launch_bounds__(kSeqThreads, 4) k_post_seq1(PostBufs b, int n, PostUniform u)
+// The loops are bound by one dependent FP64 chain per lane, so the warps are PACKED: kSeqThreads per CTA puts the whole
+// bank on a handful of SMs instead of one 32-thread CTA on each of 64 SMs -- kernel 1T needs a whole SM (every register)
+// per CTA and cannot start on an SM that hosts even one of these warps for as long as they live.
+constexpr int kSeqThreads = 256;
+constexpr int kSeq2Threads = 128;
+constexpr int kSeq1Stages = 4;
+constexpr int kSeq2Stages = 4;
+constexpr int kSeq1WarpD = (kSeq1Stages + 1) * kTileD;          // doubles of shared memory per warp: input ring + one output tile
+constexpr int kSeq2WarpD = (2 * kSeq2Stages + 2) * kTileD;      // (th, u) ring + (v, lp) output tiles
+constexpr int kSeq1Smem = (kSeqThreads / 32) * kSeq1WarpD * 8;
+constexpr int kSeq2Smem = (kSeq2Threads / 32) * kSeq2WarpD * 8;
+__global__ void __launch_bounds__(kSeqThreads, 1) k_post_seq1(PostBufs b, int n, PostUniform u)
 {
-    const int gw = blockIdx.x * (kSeqThreads / 32) + (threadIdx.x >> 5);
-    const int c = (gw >> 1) * 32 + (threadIdx.x & 31);
+    extern __shared__ __align__(128) double sm_tiles[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (kSeqThreads / 32) + warp;
+    const int c0 = (gw >> 1) * 32, c = c0 + lane;
     const bool smeter_warp = (gw & 1) != 0;
-    if (c >= b.nch) return;
-    const int mode = b.mode[c];
-    const int n16 = n & ~15;
+    if (c0 >= b.nch) return;
+    const bool in_bank = c < b.nch;
+    const int mode = in_bank ? b.mode[c] : POST_NONE;
+    const int nchunks = n / kTileT, n16 = nchunks * kTileT;
+    double* ring = sm_tiles + warp * kSeq1WarpD;
+    double* otile = ring + kSeq1Stages * kTileD;
     if (smeter_warp) {
-        if (mode == POST_AGC_ONLY) return;
+        const bool act = in_bank && mode != POST_AGC_ONLY;
+        const uint32_t mask = __ballot_sync(0xffffffffu, act);
+        if (!mask) return;
         // CSMeter::ProcessData, dsp/smeter.cpp:77-91
-        double sm_att = ST(S_SM_ATT), sm_dec = ST(S_SM_DEC), sm_ave = ST(S_SM_AVE), sm_peak = ST(S_SM_PEAK);
-        const double* row = b.smag + (size_t)c * b.row;
-        const double qa = 1.0 - u.sm_attack, qd = 1.0 - u.sm_decay;
+        double sm_att = 0, sm_dec = 0, sm_ave = 0, sm_peak = 0;
+        if (act) { sm_att = ST(S_SM_ATT); sm_dec = ST(S_SM_DEC); sm_ave = ST(S_SM_AVE); sm_peak = ST(S_SM_PEAK); }
+        const double qa = 1.0 - u.sm_attack, qd = 1.0 - u.sm_decay, ka = u.sm_attack, kd = u.sm_decay;
+        // Both poles advance with one dependent DFMA each; the reference's "if (att > dec) { ave = att; dec = att; } else
+        // ave = dec;" leaves ave == dec == max(att, dec) in either branch, so the step is two FMAs, a compare and a select
+        // (no branch: a divergent branch costs several times the 8-clock DFMA latency that bounds this loop).
         auto step = [&](double mag) {
-            sm_att = qa * sm_att + u.sm_attack * mag;
-            sm_dec = qd * sm_dec + u.sm_decay * mag;
-            if (sm_att > sm_dec) { sm_ave = sm_att; sm_dec = sm_att; }
-            else sm_ave = sm_dec;
-            if (mag > sm_peak) sm_peak = mag;
+            const double sa = fma(qa, sm_att, ka * mag);
+            const double sd = fma(qd, sm_dec, kd * mag);
+            sm_att = sa;
+            sm_dec = sa > sd ? sa : sd;
+            sm_peak = mag > sm_peak ? mag : sm_peak;
         };
-        double cur[16], nxt[16];
-        if (n16 > 0) load16(row, cur);
-        for (int t0 = 0; t0 < n16; t0 += 16) {
-            if (t0 + 16 < n16) load16(row + t0 + 16, nxt);
+        for (int k = 0; k < kSeq1Stages - 1; k++) { if (k < nchunks) tile_fetch(ring + k * kTileD, b.smag, b.row, c0, k, mask, lane); cp_commit(); }
+        for (int k = 0; k < nchunks; k++) {
+            cp_wait<kSeq1Stages - 2>();
+            __syncwarp();
+            const int kn = k + kSeq1Stages - 1;
+            if (kn < nchunks) tile_fetch(ring + (kn % kSeq1Stages) * kTileD, b.smag, b.row, c0, kn, mask, lane);
+            cp_commit();
+            const double* x = ring + (k % kSeq1Stages) * kTileD;
+            if (act) {
 #pragma unroll
-            for (int k = 0; k < 16; k++) step(cur[k]);
-#pragma unroll
-            for (int k = 0; k < 16; k++) cur[k] = nxt[k];
+                for (int j = 0; j < kTileT / 2; j++) { const double2 v = row_ld(x, lane, j); step(v.x); step(v.y); }
+            }
         }
-        for (int t = n16; t < n; t++) step(row[t]);
-        ST(S_SM_ATT) = sm_att; ST(S_SM_DEC) = sm_dec; ST(S_SM_AVE) = sm_ave; ST(S_SM_PEAK) = sm_peak;
+        if (act) {
+            const double* row = b.smag + (size_t)c * b.row;
+            for (int t = n16; t < n; t++) step(row[t]);
+            if (n > 0) sm_ave = sm_dec;
+            ST(S_SM_ATT) = sm_att; ST(S_SM_DEC) = sm_dec; ST(S_SM_AVE) = sm_ave; ST(S_SM_PEAK) = sm_peak;
+        }
         return;
     }
-    if (PAR(P_AGC_ON) == 0.0) return;
+    const bool act = in_bank && PAR(P_AGC_ON) != 0.0;
+    const uint32_t mask = __ballot_sync(0xffffffffu, act);
+    if (!mask) return;
     // attack/decay averagers of CAgc::ProcessData, dsp/agc.cpp:235-276; row <- max(attack, decay)
-    const bool use_hang = PAR(P_AGC_HANG) != 0.0;
-    const double a_rise = PAR(P_A_RISE), a_fall = PAR(P_A_FALL), d_rise = PAR(P_D_RISE), d_fall = PAR(P_D_FALL);
-    const int hang_time = (int)PAR(P_HANG_TIME);
-    double att = ST(S_AGC_ATT), dec = ST(S_AGC_DEC);
-    int hang_timer = IST(I_AGC_HANGT);
-    double* row = b.peak + (size_t)c * b.row;
+    const int cs = act ? c : c0 + __ffs(mask) - 1;          // idle lanes read a valid channel's parameters
+    const bool use_hang = b.par[(size_t)P_AGC_HANG * b.stride + cs] != 0.0;
+    const double a_rise = b.par[(size_t)P_A_RISE * b.stride + cs], a_fall = b.par[(size_t)P_A_FALL * b.stride + cs];
+    const double d_rise = b.par[(size_t)P_D_RISE * b.stride + cs], d_fall = b.par[(size_t)P_D_FALL * b.stride + cs];
+    const int hang_time = (int)b.par[(size_t)P_HANG_TIME * b.stride + cs];
+    double att = b.state[(size_t)S_AGC_ATT * b.stride + cs], dec = b.state[(size_t)S_AGC_DEC * b.stride + cs];
+    int hang_timer = b.istate[(size_t)I_AGC_HANGT * b.stride + cs];
+    // Branch-free step: both candidates of each averager are one DFMA from the state, the comparisons run beside them,
+    // the selects pick. Dependent chain per step = DFMA + select instead of compare -> branch -> DMUL -> DFMA.
+    const double qar = 1.0 - a_rise, qaf = 1.0 - a_fall, qdr = 1.0 - d_rise, qdf = 1.0 - d_fall;
     auto step = [&](double peak) -> double {
-        if (peak > att) att = (1.0 - a_rise) * att + a_rise * peak;
-        else att = (1.0 - a_fall) * att + a_fall * peak;
-        if (use_hang) {
-            if (peak > dec) { dec = (1.0 - d_rise) * dec + d_rise * peak; hang_timer = 0; }
-            else if (hang_timer < hang_time) hang_timer++;
-            else dec = (1.0 - d_fall) * dec + d_fall * peak;
-        } else {
-            if (peak > dec) dec = (1.0 - d_rise) * dec + d_rise * peak;
-            else dec = (1.0 - d_fall) * dec + d_fall * peak;
-        }
+        const double ar = fma(qar, att, a_rise * peak), af = fma(qaf, att, a_fall * peak);
+        const double dr = fma(qdr, dec, d_rise * peak), df = fma(qdf, dec, d_fall * peak);
+        const bool ga = peak > att, gd = peak > dec;
+        const bool hold = use_hang && !gd && hang_timer < hang_time;        // hang: decay frozen while the timer runs
+        att = ga ? ar : af;
+        dec = gd ? dr : (hold ? dec : df);
+        hang_timer = use_hang ? (gd ? 0 : hang_timer + (hold ? 1 : 0)) : hang_timer;
         return att > dec ? att : dec;
     };
-    double cur[16], nxt[16];
-    if (n16 > 0) load16(row, cur);
-    for (int t0 = 0; t0 < n16; t0 += 16) {
-        if (t0 + 16 < n16) load16(row + t0 + 16, nxt);
+    for (int k = 0; k < kSeq1Stages - 1; k++) { if (k < nchunks) tile_fetch(ring + k * kTileD, b.peak, b.row, c0, k, mask, lane); cp_commit(); }
+    for (int k = 0; k < nchunks; k++) {
+        cp_wait<kSeq1Stages - 2>();
+        __syncwarp();                       // tile k has landed for every lane; the previous tile_store has read otile
+        const int kn = k + kSeq1Stages - 1;
+        if (kn < nchunks) tile_fetch(ring + (kn % kSeq1Stages) * kTileD, b.peak, b.row, c0, kn, mask, lane);
+        cp_commit();
+        const double* x = ring + (k % kSeq1Stages) * kTileD;
 #pragma unroll
-        for (int k = 0; k < 16; k++) cur[k] = step(cur[k]);
-        store16(row + t0, cur);
-#pragma unroll
-        for (int k = 0; k < 16; k++) cur[k] = nxt[k];
+        for (int j = 0; j < kTileT / 2; j++) {          // idle lanes run along on harmless values: no divergence
+            const double2 v = row_ld(x, lane, j);
+            const double o0 = step(v.x), o1 = step(v.y);
+            row_st(otile, lane, j, o0, o1);
+        }
+        __syncwarp();
+        tile_store(otile, b.peak, b.row, c0, k, mask, lane);
     }
-    for (int t = n16; t < n; t++) row[t] = step(row[t]);
-    ST(S_AGC_ATT) = att; ST(S_AGC_DEC) = dec; IST(I_AGC_HANGT) = hang_timer;
+    if (act) {
+        double* row = b.peak + (size_t)c * b.row;
+        for (int t = n16; t < n; t++) row[t] = step(row[t]);
+        ST(S_AGC_ATT) = att; ST(S_AGC_DEC) = dec; IST(I_AGC_HANGT) = hang_timer;
+    }
 }
 
 // ---- gain law, delayed signal, per-mode pointwise front end; CTA per channel
@@ -322,138 +398,174 @@ __global__ void __launch_bounds__(256) k_post_mid(PostBufs b, int n, int delay, 
     for (int q = 0; q < kYHist / 256; q++) yrow[threadIdx.x + q * 256] = keep[q];
 }
 
+constexpr double kInv2Pi = 1.0 / kTwoPi;
+constexpr double kRintMagic = 6755399441055744.0;      // 1.5 * 2^52: (v + magic) - magic == rint(v) for |v| < 2^51
 __device__ __forceinline__ double wrap_pi(double d)
 {
     return d - kTwoPi * rint(d * (1.0 / kTwoPi));
 }
 
-// ---- DC blockers and PLLs; thread per channel
-__global__ void __launch_bounds__(kSeq2Threads, 4) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
+// ---- DC blockers and PLLs; lane per channel, tiles of 32 channels x 16 samples through shared memory
+__global__ void __launch_bounds__(kSeq2Threads, 1) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
                                                   int audio_stride, int audio_off, const int* __restrict__ chan_map)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= b.nch) return;
-    const int mode = b.mode[c];
-    if (mode != POST_AM && mode != POST_SAM && mode != POST_FM) return;
-    float* aout = audio ? audio + (size_t)chan_map[c] * audio_stride + (u.stereo ? 2 : 1) * audio_off : nullptr;
-    double* vrow = b.v + (size_t)c * b.v_row + kHist;
-    const int n16 = n & ~15;
-    double cur[16], nxt[16];
-    if (mode == POST_AM) {
-        // DC removal H(z) = (1 - z^-1)/(1 - .99 z^-1), dsp/amdemod.cpp:73-78
-        double z1 = ST(S_Z1);
-        const double* urow = b.u + (size_t)c * b.row;
-        auto step = [&](double mag) -> double {
-            const double z0 = mag + (z1 * 0.99);
-            const double o = z0 - z1;
-            z1 = z0;
-            return o;
-        };
-        if (n16 > 0) load16(urow, cur);
-        for (int t0 = 0; t0 < n16; t0 += 16) {
-            if (t0 + 16 < n16) load16(urow + t0 + 16, nxt);
-#pragma unroll
-            for (int k = 0; k < 16; k++) vrow[t0 + k] = step(cur[k]);     // vrow is only 8-byte aligned (kHist offset)
-#pragma unroll
-            for (int k = 0; k < 16; k++) cur[k] = nxt[k];
-        }
-        for (int t = n16; t < n; t++) vrow[t] = step(urow[t]);
-        ST(S_Z1) = z1;
-        return;
+    extern __shared__ __align__(128) double sm_tiles[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = (blockIdx.x * (kSeq2Threads / 32) + warp) * 32, c = c0 + lane;
+    if (c0 >= b.nch) return;
+    const int mode = c < b.nch ? b.mode[c] : POST_NONE;
+    const bool act = mode == POST_AM || mode == POST_SAM || mode == POST_FM;
+    const bool sam_st = mode == POST_SAM && u.stereo;
+    // rows of the tile arrays this warp moves: theta in (SAM, FM), envelope in (AM, SAM), FIR row out (AM, FM),
+    // speculative biquad out (FM; it reuses the envelope array, which AM / SAM rows must keep)
+    const uint32_t m_th = __ballot_sync(0xffffffffu, mode == POST_SAM || mode == POST_FM);
+    const uint32_t m_u = __ballot_sync(0xffffffffu, mode == POST_AM || mode == POST_SAM);
+    const uint32_t m_v = __ballot_sync(0xffffffffu, mode == POST_AM || mode == POST_FM);
+    const uint32_t m_lp = __ballot_sync(0xffffffffu, mode == POST_FM);
+    if (!(m_th | m_u)) return;
+    double* ring = sm_tiles + warp * kSeq2WarpD;                  // stage s: theta tile at 2 s, envelope tile at 2 s + 1
+    double* o_v = ring + 2 * kSeq2Stages * kTileD;
+    double* o_lp = o_v + kTileD;
+    float* aout = (audio && act) ? audio + (size_t)chan_map[c] * audio_stride + (u.stereo ? 2 : 1) * audio_off : nullptr;
+    double* vbase = b.v + kHist;
+    const int nchunks = n / kTileT, n16 = nchunks * kTileT;
+    // state (a lane uses the fields of its mode)
+    double z1 = 0, y1 = 0, phase = 0, freq = 0, fm_dc = 0, w1 = 0, w2 = 0, lp = 0;
+    if (act) {
+        z1 = ST(S_Z1); y1 = ST(S_Y1); phase = ST(S_PHASE); freq = ST(S_FREQ); fm_dc = ST(S_FM_DC); w1 = ST(S_LP_W1); w2 = ST(S_LP_W2);
     }
-    double phase = ST(S_PHASE), freq = ST(S_FREQ);
-    const double* throw_ = b.th + (size_t)c * b.row;
-    if (mode == POST_SAM && u.stereo) {
-        // stereo SAM, dsp/samdemod.cpp:115-147: opposite NCO sign to the mono path (tmp = x e^{+j phase},
-        // err = -atan2(tmp)); BOTH parts of tmp are DC-blocked and go on to the Hilbert-pair FIR.
-        // arg(tmp) = -err, so tmp = |x| (cos err, -sin err).
-        double z1 = ST(S_Z1), y1 = ST(S_Y1);
-        const double* urow = b.u + (size_t)c * b.row;
-        double* v2row = b.v2 + (size_t)c * b.v_row + kHist;
-        for (int t = 0; t < n; t++) {
-            const double err = -wrap_pi(throw_[t] + phase);
-            freq += (u.sam_beta * err);
-            if (freq > u.sam_hi) freq = u.sam_hi;
-            else if (freq < u.sam_lo) freq = u.sam_lo;
-            phase = wrap_pi(phase + (freq + u.sam_alpha * err));
-            double sn, cs;
-            sincos(err, &sn, &cs);
-            const double z0 = urow[t] * cs + (z1 * 0.99);
-            const double y0 = -urow[t] * sn + (y1 * 0.99);
-            vrow[t] = z0 - z1;
-            v2row[t] = y0 - y1;
-            z1 = z0;
-            y1 = y0;
+    const bool is_fm = mode == POST_FM;
+    // The PLLs (dsp/samdemod.cpp:81-105, dsp/fmdemod.cpp:166-187). SAM: tmp = x e^{-j phase}, err = atan2(tmp) =
+    // wrap(arg x - phase); FM: tmp = x e^{+j phase}, err = -atan2(tmp) = -wrap(arg x + phase); arg x comes from k_post_mid.
+    // Dependent chain per sample: x (DADD) -> rint through the 1.5 * 2^52 constant (DFMA, DADD; DFRND alone costs 21
+    // clocks) -> err (DFMA) -> freq (DFMA) -> clamp (two compare + select; DMNMX costs 25 clocks each) -> phase (DADD).
+    // The phase is NOT wrapped per sample: the reference lets it run through the burst and takes fmod once at the end
+    // (dsp/fmdemod.cpp:188, dsp/samdemod.cpp:107); err depends on it modulo 2 pi only.
+    const double sgn = (is_fm || sam_st) ? 1.0 : -1.0;        // x = th + sgn * phase; err = sgn * (2 pi r - x)
+    const double alpha = is_fm ? u.fm_alpha : u.sam_alpha, beta = is_fm ? u.fm_beta : u.sam_beta;
+    const double hi = in_reg(is_fm ? u.fm_hi : u.sam_hi), lo = in_reg(is_fm ? u.fm_lo : u.sam_lo);
+    const double n2pi = sgn * kTwoPi;
+    auto pll = [&](double th) -> double {
+        const double x = fma(sgn, phase, th);
+        const double r = fma(x, kInv2Pi, kRintMagic) - kRintMagic;
+        const double err = fma(r, n2pi, -sgn * x);              // FM / stereo SAM: -(x - 2 pi r); SAM: x - 2 pi r
+        double f = fma(beta, err, freq);
+        const double pa = fma(alpha, err, phase);
+        f = f > hi ? hi : f;
+        f = f < lo ? lo : f;
+        freq = f;
+        phase = pa + f;
+        return err;
+    };
+    // AM: DC removal H(z) = (1 - z^-1)/(1 - .99 z^-1), dsp/amdemod.cpp:73-78
+    auto am_step = [&](double mag) -> double {
+        const double z0 = fma(z1, 0.99, mag);
+        const double o = z0 - z1;
+        z1 = z0;
+        return o;
+    };
+    auto sam_step = [&](double th, double mag) -> float {       // tmp.re = |x| cos(err), then the DC blocker
+        const double err = pll(th);
+        const double z0 = fma(mag, cos(err), z1 * 0.99);
+        const float o = (float)(z0 - z1);
+        z1 = z0;
+        return o;
+    };
+    // FM: the 3 kHz low-pass biquad (CIir::ProcessFilter, dsp/iir.cpp:171-180) only runs -- and only advances its state
+    // -- while the squelch is open, which is decided per burst from the whole burst (k_post_fir). It is a recurrence, so
+    // it is computed here SPECULATIVELY beside the PLL (independent dependency chain): outputs go to the (otherwise unused)
+    // envelope row and the end state to S_LP_W1N/W2N; k_post_fir commits or discards them.
+    const double qdc = 1.0 - u.fm_dc_alpha, kdc = u.fm_dc_alpha, na1 = -u.lp_a1, na2 = -u.lp_a2;
+    auto fm_step = [&](double th) -> double {
+        pll(th);
+        const double f = freq;
+        fm_dc = fma(qdc, fm_dc, kdc * f);
+        const double pre = (f - fm_dc) * u.fm_gain;
+        const double w0 = fma(na1, w1, fma(na2, w2, pre));
+        lp = fma(u.lp_b0, w0, fma(u.lp_b1, w1, u.lp_b2 * w2));
+        w2 = w1;
+        w1 = w0;
+        return pre;
+    };
+    // stereo SAM, dsp/samdemod.cpp:115-147: opposite NCO sign to the mono path; BOTH parts of tmp = |x| (cos err, -sin err)
+    // are DC-blocked and go on to the Hilbert-pair FIR
+    auto sam_stereo_step = [&](double th, double mag, double* o1, double* o2) {
+        const double err = pll(th);
+        double sn, cs;
+        sincos(err, &sn, &cs);
+        const double z0 = mag * cs + (z1 * 0.99);
+        const double y0 = -mag * sn + (y1 * 0.99);
+        *o1 = z0 - z1;
+        *o2 = y0 - y1;
+        z1 = z0;
+        y1 = y0;
+    };
+    auto fetch = [&](int k) {
+        double* st = ring + 2 * (k % kSeq2Stages) * kTileD;
+        tile_fetch(st, b.th, b.row, c0, k, m_th, lane);
+        tile_fetch(st + kTileD, b.u, b.row, c0, k, m_u, lane);
+    };
+    for (int k = 0; k < kSeq2Stages - 1; k++) { if (k < nchunks) fetch(k); cp_commit(); }
+    for (int k = 0; k < nchunks; k++) {
+        cp_wait<kSeq2Stages - 2>();
+        __syncwarp();                       // tile k has landed for every lane; the previous tile_store has read the output tiles
+        if (k + kSeq2Stages - 1 < nchunks) fetch(k + kSeq2Stages - 1);
+        cp_commit();
+        const double* xt = ring + 2 * (k % kSeq2Stages) * kTileD;
+        const double* xu = xt + kTileD;
+        if (is_fm) {
+#pragma unroll
+            for (int j = 0; j < kTileT / 2; j++) {
+                const double2 v = row_ld(xt, lane, j);
+                const double p0 = fm_step(v.x), l0 = lp;
+                const double p1 = fm_step(v.y), l1 = lp;
+                row_st(o_v, lane, j, p0, p1);
+                row_st(o_lp, lane, j, l0, l1);
+            }
+        } else if (mode == POST_AM) {
+#pragma unroll
+            for (int j = 0; j < kTileT / 2; j++) {
+                const double2 v = row_ld(xu, lane, j);
+                const double p0 = am_step(v.x), p1 = am_step(v.y);
+                row_st(o_v, lane, j, p0, p1);
+            }
+        } else if (sam_st) {
+            double* vrow = vbase + (size_t)c * b.v_row + k * kTileT;
+            double* v2row = b.v2 + kHist + (size_t)c * b.v_row + k * kTileT;
+            for (int j = 0; j < kTileT / 2; j++) {
+                const double2 t2 = row_ld(xt, lane, j), m2 = row_ld(xu, lane, j);
+                sam_stereo_step(t2.x, m2.x, vrow + 2 * j, v2row + 2 * j);
+                sam_stereo_step(t2.y, m2.y, vrow + 2 * j + 1, v2row + 2 * j + 1);
+            }
+        } else if (mode == POST_SAM) {
+#pragma unroll 2
+            for (int j = 0; j < kTileT / 2; j++) {
+                const double2 t2 = row_ld(xt, lane, j), m2 = row_ld(xu, lane, j);
+                const float o0 = sam_step(t2.x, m2.x), o1 = sam_step(t2.y, m2.y);
+                if (aout) { aout[k * kTileT + 2 * j] = o0; aout[k * kTileT + 2 * j + 1] = o1; }
+            }
         }
-        ST(S_Z1) = z1; ST(S_Y1) = y1;
-    } else if (mode == POST_SAM) {
-        // dsp/samdemod.cpp:81-105: tmp = x e^{-j phase}; err = atan2(tmp) = wrap(arg x - phase);
-        // tmp.re = |x| cos(err)
-        double z1 = ST(S_Z1);
-        const double* urow = b.u + (size_t)c * b.row;
-        double ucur[16], unxt[16];
-        auto step = [&](double th, double mag) -> float {
-            const double err = wrap_pi(th - phase);
-            freq += (u.sam_beta * err);
-            if (freq > u.sam_hi) freq = u.sam_hi;
-            else if (freq < u.sam_lo) freq = u.sam_lo;
-            phase = wrap_pi(phase + (freq + u.sam_alpha * err));
-            const double z0 = mag * cos(err) + (z1 * 0.99);
-            const float o = (float)(z0 - z1);
-            z1 = z0;
-            return o;
-        };
-        if (n16 > 0) { load16(throw_, cur); load16(urow, ucur); }
-        for (int t0 = 0; t0 < n16; t0 += 16) {
-            if (t0 + 16 < n16) { load16(throw_ + t0 + 16, nxt); load16(urow + t0 + 16, unxt); }
-#pragma unroll
-            for (int k = 0; k < 16; k++) { const float o = step(cur[k], ucur[k]); if (aout) aout[t0 + k] = o; }
-#pragma unroll
-            for (int k = 0; k < 16; k++) { cur[k] = nxt[k]; ucur[k] = unxt[k]; }
-        }
-        for (int t = n16; t < n; t++) { const float o = step(throw_[t], urow[t]); if (aout) aout[t] = o; }
-        ST(S_Z1) = z1;
-    } else {
-        // dsp/fmdemod.cpp:166-187: tmp = x e^{+j phase}; err = -atan2(tmp) = -wrap(arg x + phase)
-        // The 3 kHz low-pass biquad (CIir::ProcessFilter, dsp/iir.cpp:171-180) only runs -- and only
-        // advances its state -- while the squelch is open, which is decided per burst from the whole
-        // burst (k_post_fir). It is a recurrence, so it is computed here SPECULATIVELY beside the PLL
-        // (independent dependency chain): outputs go to the (otherwise unused) envelope row and the
-        // end state to S_LP_W1N/W2N; k_post_fir commits or discards them.
-        double fm_dc = ST(S_FM_DC);
-        double w1 = ST(S_LP_W1), w2 = ST(S_LP_W2);
-        const double qdc = 1.0 - u.fm_dc_alpha;
-        double* lprow = b.u + (size_t)c * b.row;
-        double lp = 0.0;
-        auto step = [&](double th) -> double {
-            const double err = -wrap_pi(th + phase);
-            freq += (u.fm_beta * err);
-            if (freq > u.fm_hi) freq = u.fm_hi;
-            else if (freq < u.fm_lo) freq = u.fm_lo;
-            phase = wrap_pi(phase + (freq + u.fm_alpha * err));
-            fm_dc = qdc * fm_dc + u.fm_dc_alpha * freq;
-            const double pre = (freq - fm_dc) * u.fm_gain;
-            const double w0 = pre - u.lp_a1 * w1 - u.lp_a2 * w2;
-            lp = u.lp_b0 * w0 + u.lp_b1 * w1 + u.lp_b2 * w2;
-            w2 = w1;
-            w1 = w0;
-            return pre;
-        };
-        if (n16 > 0) load16(throw_, cur);
-        for (int t0 = 0; t0 < n16; t0 += 16) {
-            if (t0 + 16 < n16) load16(throw_ + t0 + 16, nxt);
-            double lpo[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) { vrow[t0 + k] = step(cur[k]); lpo[k] = lp; }
-            store16(lprow + t0, lpo);
-#pragma unroll
-            for (int k = 0; k < 16; k++) cur[k] = nxt[k];
-        }
-        for (int t = n16; t < n; t++) { vrow[t] = step(throw_[t]); lprow[t] = lp; }
-        ST(S_FM_DC) = fm_dc;
-        ST(S_LP_W1N) = w1; ST(S_LP_W2N) = w2;
+        __syncwarp();
+        tile_store(o_v, vbase, b.v_row, c0, k, m_v, lane);
+        tile_store(o_lp, b.u, b.row, c0, k, m_lp, lane);
     }
-    ST(S_PHASE) = phase; ST(S_FREQ) = freq;
+    if (!act) return;
+    {   // the last n % 16 samples straight from the rows
+        const double* throw_ = b.th + (size_t)c * b.row;
+        double* urow = b.u + (size_t)c * b.row;
+        double* vrow = vbase + (size_t)c * b.v_row;
+        double* v2row = b.v2 + kHist + (size_t)c * b.v_row;
+        for (int t = n16; t < n; t++) {
+            if (is_fm) { vrow[t] = fm_step(throw_[t]); urow[t] = lp; }
+            else if (mode == POST_AM) vrow[t] = am_step(urow[t]);
+            else if (sam_st) sam_stereo_step(throw_[t], urow[t], vrow + t, v2row + t);
+            else { const float o = sam_step(throw_[t], urow[t]); if (aout) aout[t] = o; }
+        }
+    }
+    ST(S_Z1) = z1;
+    if (sam_st) ST(S_Y1) = y1;
+    if (mode != POST_AM) { ST(S_PHASE) = wrap_pi(phase); ST(S_FREQ) = freq; }    // fmod(m_NcoPhase, K_2PI) at the end of the burst
+    if (is_fm) { ST(S_FM_DC) = fm_dc; ST(S_LP_W1N) = w1; ST(S_LP_W2N) = w2; }
 }
 
 // ---- Kaiser FIRs, squelch, biquad; CTA per channel. dynamic smem: (kHist + max_n + kFirMax) doubles
@@ -595,7 +707,7 @@ PostBank::~PostBank()
 int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream_t st, LaunchCounter* lc)
 {
     nch_ = nch; stride_ = stride; rate_ = rate; st_ = st; lc_ = lc;
-    max_n_ = max_samples;
+    max_n_ = round_up(max_samples, 2);      // rows stay 16-byte aligned for the bulk copies of the sequential kernels
     y_row_ = kYHist + max_n_;
     v_row_ = round_up(kHist + max_n_, 2);
     // CSMeter, dsp/smeter.cpp:66-69
@@ -684,6 +796,8 @@ int PostBank::init(int nch, int stride, double rate, int max_samples, cudaStream
     const size_t smem_fir = (size_t)(2 * (kHist + max_n_) + kFirMax + 16) * sizeof(double);
     if (smem_pre > 200 * 1024) { set_error("post: burst capacity %d too large", max_n_); return CUTESDR_E_ARG; }
     CSDR_CK(cudaFuncSetAttribute(k_post_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pre));
+    CSDR_CK(cudaFuncSetAttribute(k_post_seq1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeq1Smem));
+    CSDR_CK(cudaFuncSetAttribute(k_post_seq2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeq2Smem));
     CSDR_CK(cudaFuncSetAttribute(k_post_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_fir, 1024)));
     dirty_ = true;
     return CUTESDR_OK;
@@ -809,9 +923,9 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
     const size_t smem_fir = (size_t)((uni_.stereo ? 2 : 1) * (kHist + max_n_) + kFirMax + 16) * sizeof(double);
     const int seq_blocks = (nch_ + 31) / 32;
     k_post_pre<<<nch_, 256, 2 * (size_t)(uni_.agc_window - 1 + n) * sizeof(double), st_>>>(b, n, uni_.agc_window);
-    k_post_seq1<<<(2 * seq_blocks * 32 + kSeqThreads - 1) / kSeqThreads, kSeqThreads, 0, st_>>>(b, n, uni_);
+    k_post_seq1<<<(2 * seq_blocks * 32 + kSeqThreads - 1) / kSeqThreads, kSeqThreads, kSeq1Smem, st_>>>(b, n, uni_);
     k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, uni_.stereo, d_audio, audio_stride, audio_off, d_chan_map);
-    k_post_seq2<<<(seq_blocks * 32 + kSeq2Threads - 1) / kSeq2Threads, kSeq2Threads, 0, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
+    k_post_seq2<<<(seq_blocks * 32 + kSeq2Threads - 1) / kSeq2Threads, kSeq2Threads, kSeq2Smem, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_fir<<<nch_, 256, smem_fir, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     lc_->n += 5;
     CSDR_CK(cudaGetLastError());
