@@ -10,7 +10,7 @@
 // output goes channel-major [c][row_stride] (one contiguous 1024-sample run per burst and channel).
 // Filters are designed on the device (k_fir_design) and the first burst of a stream is computed in direct form
 // (k_fir_first).
-// The FFT is a shared-memory Stockham autosort (five radix-4 passes + one radix-2, ping-pong buffers).
+// The FFT is a Stockham autosort in three passes (radix 16, 16, 8) with the butterflies in registers.
 #include "fastfir.cuh"
 
 namespace csdr {
@@ -23,102 +23,163 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b)
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// 2048 = 4^5 * 2: five radix-4 Stockham passes and one radix-2 pass (autosort: natural order in and
-// out, ping-pong buffers). 256 threads; a radix-4 pass gives every thread two butterflies.
-// tw[m] = e^{-2 pi i m / 2048}; CONJ selects the inverse kernel.
+// 2048 = 16 x 16 x 8: three Stockham passes (radix 16, 16, 8) with the butterflies in REGISTERS. 128 threads, thread j
+// owns butterfly j of the radix-16 passes (inputs j + 128 r, r = 0..15) and butterflies j, j + 128 of the radix-8 pass
+// (inputs jj + 256 r). Between passes the data crosses shared memory once (one padded buffer: element i at i + i / 16,
+// which makes the stride-16 writes of the first pass and every other access pattern below conflict-free). The last
+// forward pass leaves thread j with elements j + 128 m, m = 0..15 -- exactly the inputs of the first inverse pass -- so
+// the spectrum is multiplied by H in registers and never written out: 4 shared-memory crossings per overlap-save
+// window instead of 14, straight from the decimator ring to the burst row.
+// tw[m] = e^{-2 pi i m / 2048}, m < 1024; CONJ selects the inverse kernel.
 template <bool CONJ>
 __device__ __forceinline__ float2 twiddle(const float2* __restrict__ tw, int m)
 {
     // m in [0, 2048): the table holds the first half, the second half is its negation
-    float2 w = tw[m & 1023];
+    float2 w = __ldg(tw + (m & 1023));
     if (m & 1024) { w.x = -w.x; w.y = -w.y; }
     if (CONJ) w.y = -w.y;
     return w;
 }
-
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward kernels) or +i (inverse)
 template <bool CONJ>
-__device__ __forceinline__ void stockham_r4(const float2* __restrict__ src, float2* __restrict__ dst,
-                                            const float2* __restrict__ tw, int ns)
+__device__ __forceinline__ float2 rot90(float2 a) { return CONJ ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+// multiply by e^{-+2 pi i m / 16}
+template <bool CONJ, int M>
+__device__ __forceinline__ float2 mul_w16(float2 a)
 {
-    // butterflies j = 0..511; inputs j + r*512; k = j mod ns; outputs (j-k)*4 + k + r*ns
-    const int tw_mul = 512 / ns;           // 2048 / (4 ns)
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int j = threadIdx.x + q * 256;
-        const int k = j & (ns - 1);
-        float2 a0 = src[j], a1 = src[j + 512], a2 = src[j + 1024], a3 = src[j + 1536];
-        if (ns > 1) {
-            a1 = cmulf(a1, twiddle<CONJ>(tw, k * tw_mul));
-            a2 = cmulf(a2, twiddle<CONJ>(tw, 2 * k * tw_mul));
-            a3 = cmulf(a3, twiddle<CONJ>(tw, 3 * k * tw_mul));
-        }
-        const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
-        const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
-        // forward: multiply d13 by -i; inverse: by +i
-        const float2 r13 = CONJ ? make_float2(-d13.y, d13.x) : make_float2(d13.y, -d13.x);
-        const int j0 = ((j - k) << 2) + k;
-        dst[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
-        dst[j0 + ns] = make_float2(d02.x + r13.x, d02.y + r13.y);
-        dst[j0 + 2 * ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
-        dst[j0 + 3 * ns] = make_float2(d02.x - r13.x, d02.y - r13.y);
-    }
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    constexpr int m = M & 15;
+    if (m == 0) return a;
+    if (m == 4) return rot90<CONJ>(a);
+    if (m == 8) return make_float2(-a.x, -a.y);
+    if (m == 12) return rot90<!CONJ>(a);
+    // w = (wr, -+wi)
+    constexpr float wr = (m == 1 || m == 15) ? c1 : (m == 2 || m == 14) ? h : (m == 3 || m == 13) ? s1 : (m == 5 || m == 11) ? -s1
+                        : (m == 6 || m == 10) ? -h : -c1;
+    constexpr float wi0 = (m == 1 || m == 7) ? s1 : (m == 2 || m == 6) ? h : (m == 3 || m == 5) ? c1 : (m == 9 || m == 15) ? -s1
+                         : (m == 10 || m == 14) ? -h : -c1;       // sin(2 pi m / 16)
+    const float wi = CONJ ? wi0 : -wi0;
+    return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
 }
-
+// 4-point DFT in place: x[q] = sum_r a[r] e^{-+2 pi i r q / 4}
 template <bool CONJ>
-__device__ __forceinline__ void stockham_r2_last(const float2* __restrict__ src, float2* __restrict__ dst,
-                                                 const float2* __restrict__ tw)
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3)
 {
-    // final pass: ns = 1024, k = j, w = e^{-+2 pi i j / 2048}
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int j = threadIdx.x + q * 256;
-        const float2 a = src[j];
-        const float2 b = cmulf(src[j + 1024], twiddle<CONJ>(tw, j));
-        dst[j] = make_float2(a.x + b.x, a.y + b.y);
-        dst[j + 1024] = make_float2(a.x - b.x, a.y - b.y);
-    }
+    const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), r13 = rot90<CONJ>(csub(a1, a3));
+    a0 = cadd(s02, s13);
+    a1 = cadd(d02, r13);
+    a2 = csub(s02, s13);
+    a3 = csub(d02, r13);
 }
-
+// 16-point DFT: input a[r], output a[q] (natural order). r = 4 r1 + r0, q = q0 + 4 q1:
+// w16^(rq) = w4^(r1 q0) w16^(r0 q0) w4^(r0 q1)
 template <bool CONJ>
-__device__ __forceinline__ float2* fft2048(float2* src, float2* dst, const float2* __restrict__ tw)
+__device__ __forceinline__ void dft16(float2* a)
 {
-    for (int ns = 1; ns < 1024; ns <<= 2) {
-        stockham_r4<CONJ>(src, dst, tw, ns);
-        __syncthreads();
-        float2* t = src; src = dst; dst = t;
-    }
-    stockham_r2_last<CONJ>(src, dst, tw);
+    // step A: over r1 for every r0 -> B[r0][q0] stored at a[4 q0 + r0]
+    dft4<CONJ>(a[0], a[4], a[8], a[12]);
+    dft4<CONJ>(a[1], a[5], a[9], a[13]);
+    dft4<CONJ>(a[2], a[6], a[10], a[14]);
+    dft4<CONJ>(a[3], a[7], a[11], a[15]);
+    // step B: B[r0][q0] *= w16^(r0 q0)
+    a[5] = mul_w16<CONJ, 1>(a[5]);   a[6] = mul_w16<CONJ, 2>(a[6]);   a[7] = mul_w16<CONJ, 3>(a[7]);
+    a[9] = mul_w16<CONJ, 2>(a[9]);   a[10] = mul_w16<CONJ, 4>(a[10]); a[11] = mul_w16<CONJ, 6>(a[11]);
+    a[13] = mul_w16<CONJ, 3>(a[13]); a[14] = mul_w16<CONJ, 6>(a[14]); a[15] = mul_w16<CONJ, 9>(a[15]);
+    // step C: over r0 for every q0 -> X[q0 + 4 q1] lands at a[4 q0 + q1]
+    dft4<CONJ>(a[0], a[1], a[2], a[3]);
+    dft4<CONJ>(a[4], a[5], a[6], a[7]);
+    dft4<CONJ>(a[8], a[9], a[10], a[11]);
+    dft4<CONJ>(a[12], a[13], a[14], a[15]);
+}
+// X[q], q = q0 + 4 q1, sits at a[4 q0 + q1] after dft16
+__device__ __forceinline__ constexpr int dft16_slot(int q) { return 4 * (q & 3) + (q >> 2); }
+// 8-point DFT: r = 4 r1 + r0, q = q0 + 2 q1: w8^(rq) = (-1)^(r1 q0) w8^(r0 q0) w4^(r0 q1). Output X[q0 + 2 q1] at a[4 q0 + q1].
+template <bool CONJ>
+__device__ __forceinline__ void dft8(float2* a)
+{
+#pragma unroll
+    for (int r0 = 0; r0 < 4; r0++) { const float2 s = cadd(a[r0], a[r0 + 4]), d = csub(a[r0], a[r0 + 4]); a[r0] = s; a[r0 + 4] = d; }
+    a[5] = mul_w16<CONJ, 2>(a[5]);
+    a[6] = mul_w16<CONJ, 4>(a[6]);
+    a[7] = mul_w16<CONJ, 6>(a[7]);
+    dft4<CONJ>(a[0], a[1], a[2], a[3]);
+    dft4<CONJ>(a[4], a[5], a[6], a[7]);
+}
+__device__ __forceinline__ constexpr int dft8_slot(int q) { return 4 * (q & 1) + (q >> 1); }
+
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+constexpr int kFftPadded = kFirFft + kFirFft / 16;
+
+// passes 1 and 2 of a transform: a[r] = element j + 128 r on entry; on exit the data is in `buf` (pass-2 output order)
+template <bool CONJ>
+__device__ __forceinline__ void fft2048_head(float2* a, float2* buf, const float2* __restrict__ tw, int j)
+{
+    dft16<CONJ>(a);                                            // ns = 1: no twiddles, outputs 16 j + q
+#pragma unroll
+    for (int q = 0; q < 16; q++) buf[17 * j + q] = a[dft16_slot(q)];          // fpad(16 j + q) = 17 j + q
     __syncthreads();
-    return dst;
+#pragma unroll
+    for (int r = 0; r < 16; r++) a[r] = buf[fpad(j + 128 * r)];
+    __syncthreads();
+    const int k = j & 15;                                      // ns = 16: twiddle unit 2048 / 256 = 8
+#pragma unroll
+    for (int r = 1; r < 16; r++) a[r] = cmulf(a[r], twiddle<CONJ>(tw, 8 * k * r));
+    dft16<CONJ>(a);
+    const int o = ((j - k) << 4) + k;                          // outputs o + 16 q
+#pragma unroll
+    for (int q = 0; q < 16; q++) buf[fpad(o + 16 * q)] = a[dft16_slot(q)];
+    __syncthreads();
+}
+// pass 3 (radix 8, ns = 256) for butterfly jj: reads buf, leaves X[jj + 256 q] in a[dft8_slot(q)]
+template <bool CONJ>
+__device__ __forceinline__ void fft2048_tail(float2* a, const float2* buf, const float2* __restrict__ tw, int jj)
+{
+#pragma unroll
+    for (int r = 0; r < 8; r++) a[r] = buf[fpad(jj + 256 * r)];
+#pragma unroll
+    for (int r = 1; r < 8; r++) a[r] = cmulf(a[r], twiddle<CONJ>(tw, jj * r));
+    dft8<CONJ>(a);
 }
 
-__global__ void __launch_bounds__(256) k_fastfir(const float2* __restrict__ ring, long long first_burst,
+__global__ void __launch_bounds__(128) k_fastfir(const float2* __restrict__ ring, long long first_burst,
                                                  const float2* __restrict__ H, const int* __restrict__ filt_id,
-                                                 const float2* __restrict__ tw_g, float2* __restrict__ y, int stride)
+                                                 const float2* __restrict__ tw, float2* __restrict__ y, int stride)
 {
-    __shared__ float2 bufA[kFirFft];
-    __shared__ float2 bufB[kFirFft];
-    __shared__ float2 tw[1024];
-    const int c = blockIdx.x;
+    __shared__ float2 buf[kFftPadded];
+    const int c = blockIdx.x, j = threadIdx.x;
     const long long burst = first_burst + blockIdx.y;
     const long long w0 = burst * kBurst - kBurst;          // first sample of the 2048 window
     const float2* r = ring + (size_t)c * kDecRing;
-    for (int i = threadIdx.x; i < 1024; i += 256) tw[i] = tw_g[i];
-    for (int i = threadIdx.x; i < kFirFft; i += 256) {
-        const long long j = w0 + i;
+    float2 a[16], lo[8], hi[8];
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        const long long i = w0 + j + 128 * m;
         // samples before the stream start are the reference's zero-initialised overlap buffer
-        bufA[i] = j < 0 ? make_float2(0.f, 0.f) : r[(size_t)(j & (kDecRing - 1))];
+        a[m] = i < 0 ? make_float2(0.f, 0.f) : r[(size_t)(i & (kDecRing - 1))];
     }
-    __syncthreads();
-    float2* X = fft2048<false>(bufA, bufB, tw);
-    float2* other = (X == bufA) ? bufB : bufA;
+    fft2048_head<false>(a, buf, tw, j);
+    fft2048_tail<false>(lo, buf, tw, j);                   // X[j + 256 q]
+    fft2048_tail<false>(hi, buf, tw, j + 128);             // X[j + 128 + 256 q]
+    __syncthreads();                                       // every thread has read buf
+    // CpxMpy, dsp/fastfir.cpp:312-321, on the registers: a[m] = H[j + 128 m] X[j + 128 m]
     const float2* Hc = H + (size_t)filt_id[c] * kFirFft;
-    for (int i = threadIdx.x; i < kFirFft; i += 256) X[i] = cmulf(Hc[i], X[i]);   // CpxMpy, dsp/fastfir.cpp:312-321
-    __syncthreads();
-    float2* Y = fft2048<true>(X, other, tw);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        a[2 * q] = cmulf(__ldg(Hc + j + 256 * q), lo[dft8_slot(q)]);
+        a[2 * q + 1] = cmulf(__ldg(Hc + j + 128 + 256 * q), hi[dft8_slot(q)]);
+    }
+    fft2048_head<true>(a, buf, tw, j);
+    fft2048_tail<true>(lo, buf, tw, j);
+    fft2048_tail<true>(hi, buf, tw, j + 128);
     // keep samples 1024..2047 (dsp/fastfir.cpp:291-294); channel-major rows: coalesced stores
     float2* yo = y + (size_t)c * stride + (size_t)blockIdx.y * kBurst;
-    for (int i = threadIdx.x; i < kBurst; i += 256) yo[i] = Y[kBurst + i];
+#pragma unroll
+    for (int q = 4; q < 8; q++) {
+        yo[j + 256 * q - kBurst] = lo[dft8_slot(q)];
+        yo[j + 128 + 256 * q - kBurst] = hi[dft8_slot(q)];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -349,7 +410,7 @@ int FirBank::run(const float2* d_ring, long long first_burst, int nb, float2* d_
         if (nb == 0) return CUTESDR_OK;
     }
     dim3 grid(nch_, nb);
-    k_fastfir<<<grid, 256, 0, st_>>>(d_ring, first_burst, d_H_, d_id_, d_tw_, d_y, y_stride);
+    k_fastfir<<<grid, 128, 0, st_>>>(d_ring, first_burst, d_H_, d_id_, d_tw_, d_y, y_stride);
     lc_->n++;
     CSDR_CK(cudaGetLastError());
     return CUTESDR_OK;
