@@ -1836,8 +1836,10 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
         CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const int groups = stride_ / kH3Ch;
         // ~hs_ctas x 2 warps per SM in total; a slice is at least 16 outputs (128 rows) so the ~100 priming rows stay a fraction
-        int slices = std::max(1, std::min(n2 / 16, (sms * tun_.hs_ctas * kH3Warps + groups / 2) / groups));
-        slices = (slices + kH3Warps - 1) / kH3Warps * kH3Warps;
+        // -- rounded DOWN to whole CTAs: every CTA lives as long as the kernel, so the grid must fit in ONE wave
+        // (sms * hs_ctas resident CTAs; 448 CTAs on 444 slots ran as two waves and doubled the pass)
+        int slices = std::max(1, std::min(n2 / 16, (sms * tun_.hs_ctas * kH3Warps) / groups));
+        slices = std::max(kH3Warps, slices / kH3Warps * kH3Warps);
         const int per_slice = (n2 + slices - 1) / slices;
         OutDesc o2;
         if (3 < nhb) {
