@@ -30,7 +30,6 @@ Tuning Tuning::from_env()
 {
     Tuning t;
     t.no_tc = getenv("CUTESDR_NO_TC") != nullptr;
-    t.tc_f16 = getenv("CUTESDR_TC_F16") != nullptr;
     t.no_hbchain = getenv("CUTESDR_NO_HBCHAIN") != nullptr;
     t.hbtail = getenv("CUTESDR_HBTAIL") != nullptr;
     t.no_overlap = getenv("CUTESDR_NO_OVERLAP") != nullptr;
@@ -698,21 +697,6 @@ __global__ void k_tc_coeffs_f16(const NcoDev* __restrict__ nco, int nch, int gro
     for (int pl = 0; pl < 4; pl++) row[24 * pl + kp] = w[pl];
 }
 
-// max(|re|, |im|) over [saved halo | block], as the bit pattern of a non-negative float (atomicMax on the word):
-// the power-of-two input scale of the fp16 form of kernel 1T comes from it, so that form is as scale-free as fp32
-__global__ void __launch_bounds__(256) k_absmax(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, int L,
-                                                unsigned* __restrict__ out)
-{
-    float m = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x - kHaloMax; i < L; i += gridDim.x * blockDim.x) {
-        const float2 v = i < 0 ? halo_cur[kHaloMax + i] : fetch_sample(x, fmt, i);
-        m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
-}
-
 template <int NCR, int NHB, int G0, int G1> struct TcStrip {
     static __device__ __forceinline__ void run(const float* re, const float* im, float2& S, float2 w, CicSt* st, float2* ev, Hb11St* hs,
                                                TcEmit& em)
@@ -730,26 +714,21 @@ template <int NCR, int NHB, int G1> struct TcStrip<NCR, NHB, G1, G1> {
 template <int NCR, int NHB, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_mix_tc(const void* __restrict__ x, int fmt, const float2* __restrict__ halo_cur, float2* __restrict__ halo_next, int L, int seg_len,
-             const float* __restrict__ coef_tab, const unsigned* __restrict__ absmax_bits, const NcoDev* __restrict__ nco,
+             const float* __restrict__ coef_tab, const NcoDev* __restrict__ nco,
              const unsigned long long* __restrict__ phase_cur, unsigned long long* __restrict__ phase_next, int nch, OutDesc od, float scale)
 {
     typedef TcCfg<NCR, NHB> Cfg;
-    // F16: operands are fp16 hi + lo (same 11 significant bits as tf32, kind::f16 runs at twice the rate and takes K = 16):
-    // a 16-byte shared-memory chunk holds 8 samples, an X row is 2 chunks = ONE MMA K-step, an A plane is 24 TMEM columns.
+    // F16 = the form for int16 wire samples (fmt 1). An int16 splits EXACTLY into two fp16 numbers, v / 64 = hi + lo with
+    // hi = floor((v + 32768) / 64) - 512 (an integer in [-512, 511]) and lo = ((v + 32768) mod 64) / 64, so the Hankel
+    // operand is exact, all four partial products (A_hi + A_lo)(X_hi + X_lo) are kept, and kind::f16 runs at twice the
+    // tf32 rate with K = 16 per MMA: 24 MMAs per accumulator and tile instead of 36, no input-dependent scale, and an
+    // error that only comes from the 22-bit coefficient split. A 16-byte shared-memory chunk holds 8 samples, an X row
+    // is 2 chunks = ONE MMA K-step, an A plane is 24 TMEM columns. Samples that are not int16 in this launch (the saved
+    // halo of the previous block, which is float32) go through a float -> fp16 hi/lo split with the same 1/64 scale.
     constexpr int kPl = F16 ? 2 * kTcP : kTcPlane;            // bytes per B plane
     constexpr int kACols = F16 ? 24 : 48;                     // TMEM columns per A plane
     constexpr int kKSteps = F16 ? 3 : 6;
-    // power-of-two input scale (fp16 only): block maximum -> [2^9, 2^10); exact, undone at the output scale
-    float s_in = 1.f, s_out = 1.f;
-    if constexpr (F16) {
-        const float mx = __uint_as_float(*absmax_bits);
-        if (mx > 0.f && mx < 3.0e38f) {
-            int ex;
-            frexpf(mx, &ex);
-            s_in = ldexpf(1.f, 10 - ex);
-            s_out = ldexpf(1.f, ex - 10);
-        }
-    }
+    constexpr float s_in = F16 ? 1.0f / 64.0f : 1.0f, s_out = F16 ? 64.0f : 1.0f;
     extern __shared__ __align__(128) unsigned char tc_smem[];
     unsigned char* sB = tc_smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + kTcBarOff);
@@ -811,10 +790,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int c_lo = (pw & 1) * kHalf, c_hi = min(kChunks, c_lo + kHalf);
         // The global loads of a tile are issued one tile ahead of its conversion (DRAM latency is ~1 us, more than a
         // tile time): two register sets alternate.
-        struct Pending { int st, my; };
-        auto issue_loads = [&](int mt, float4* va, float4* vb) {
+        struct Pending { int st, my; bool raw; };
+        // returns true when the registers hold RAW int16 samples (F16 form, whole tile inside the block): va[j] then
+        // carries four (I, Q) words and vb[j] is unused
+        auto issue_loads = [&](int mt, float4* va, float4* vb) -> bool {
             const int i_lo = 16 * (mt - 2);
-            const bool fast = fmt == 0 && i_lo >= 0 && i_lo + 16 * kTcRows <= L;
+            const bool inside = i_lo >= 0 && i_lo + 16 * kTcRows <= L;
+            const bool fast = fmt == 0 && inside;
+            const bool raw = F16 && fmt == 1 && inside;
 #pragma unroll
             for (int j = 0; j < kRounds; j++) {
                 const int idx = c_lo + lane + 32 * j;                     // chunk (row idx / 4, q = idx % 4)
@@ -822,7 +805,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 vb[j] = va[j];
                 if (idx < c_hi) {
-                    if (fast) {
+                    if (raw) {
+                        va[j] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const short2*>(x) + i0));
+                    } else if (fast) {
                         const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(x) + i0);
                         va[j] = __ldg(q);
                         vb[j] = __ldg(q + 1);
@@ -833,6 +818,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     }
                 }
             }
+            return raw;
         };
         auto flush = [&](const Pending& pd, const float4* va, const float4* vb) {
             // convert a tile's samples (in registers) and hand the stage to the MMA warps
@@ -845,6 +831,32 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     const float4 a = va[j], b = vb[j];
                     if constexpr (F16) {
                         // 4 samples = half of a 16-byte chunk: row idx / 4, chunk (idx / 2) % 2, half idx % 2
+                        const int off = 16 * (idx >> 2) + kTcP * ((idx >> 1) & 1) + 8 * (idx & 1);
+                        if (pd.raw) {
+                            // (I, Q) int16 words of samples 0..3 -> (I0 I1), (I2 I3), (Q0 Q1), (Q2 Q3); per pair: u = v + 32768,
+                            // fp16 bit patterns 0x6400 | field are 1024 + field, so hi = (1024 + u / 64) - 1536 and
+                            // lo = (1024 + u % 64) / 64 - 16, both exact
+                            const uint32_t w0 = __float_as_uint(a.x), w1 = __float_as_uint(a.y), w2 = __float_as_uint(a.z), w3 = __float_as_uint(a.w);
+                            const uint32_t pk[4] = {__byte_perm(w0, w1, 0x5410), __byte_perm(w2, w3, 0x5410), __byte_perm(w0, w1, 0x7632),
+                                                    __byte_perm(w2, w3, 0x7632)};
+                            uint32_t hi[4], lo[4];
+                            const __half2 c1536 = __floats2half2_rn(1536.f, 1536.f), c64 = __floats2half2_rn(1.f / 64.f, 1.f / 64.f),
+                                          c16 = __floats2half2_rn(-16.f, -16.f);
+#pragma unroll
+                            for (int h = 0; h < 4; h++) {
+                                const uint32_t u = pk[h] ^ 0x80008000u;
+                                const uint32_t hb = ((u >> 6) & 0x03ff03ffu) | 0x64006400u, lb = (u & 0x003f003fu) | 0x64006400u;
+                                const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&hb), c1536);
+                                const __half2 lv = __hfma2(*reinterpret_cast<const __half2*>(&lb), c64, c16);
+                                hi[h] = *reinterpret_cast<const uint32_t*>(&hv);
+                                lo[h] = *reinterpret_cast<const uint32_t*>(&lv);
+                            }
+                            *reinterpret_cast<uint2*>(pl + off) = make_uint2(hi[0], hi[1]);
+                            *reinterpret_cast<uint2*>(pl + kPl + off) = make_uint2(lo[0], lo[1]);
+                            *reinterpret_cast<uint2*>(pl + 2 * kPl + off) = make_uint2(hi[2], hi[3]);
+                            *reinterpret_cast<uint2*>(pl + 3 * kPl + off) = make_uint2(lo[2], lo[3]);
+                            continue;
+                        }
                         const float xr[4] = {a.x * s_in, a.z * s_in, b.x * s_in, b.z * s_in};
                         const float xi[4] = {a.y * s_in, a.w * s_in, b.y * s_in, b.w * s_in};
                         __half2 rh[2], rl[2], ih[2], il[2];
@@ -856,7 +868,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                             rl[h] = __floats2half2_rn(xr[2 * h] - rf.x, xr[2 * h + 1] - rf.y);
                             il[h] = __floats2half2_rn(xi[2 * h] - jf.x, xi[2 * h + 1] - jf.y);
                         }
-                        const int off = 16 * (idx >> 2) + kTcP * ((idx >> 1) & 1) + 8 * (idx & 1);
                         auto put = [&](int plane, const __half2* v) {
                             uint2 u;
                             u.x = *reinterpret_cast<const uint32_t*>(&v[0]);
@@ -883,7 +894,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // this warp pair's tiles are those of segment (pw >> 1): tile k of the segment is global tile number 2 k + e
         // while both segments are alive, so the (stage, use count) sequence is recomputed the same way every role does
         float4 va0[kRounds], vb0[kRounds], va1[kRounds], vb1[kRounds];
-        Pending p0 = {-1, 0}, p1 = {-1, 0};
+        Pending p0 = {-1, 0, false}, p1 = {-1, 0, false};
         int cnt = 0, mine = 0;
         for (int k = 0; k < max_tiles; k++) {
 #pragma unroll 1
@@ -893,13 +904,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (k >= tiles) continue;
                 const int my = cnt++;
                 if ((my & 1) != (pw >> 1)) continue;
-                const Pending now = {my % kTcStages, my};
+                Pending now = {my % kTcStages, my, false};
                 if ((mine++ & 1) == 0) {
-                    issue_loads(m0 + kTcN * k, va0, vb0);
+                    now.raw = issue_loads(m0 + kTcN * k, va0, vb0);
                     p0 = now;
                     if (p1.st >= 0) { flush(p1, va1, vb1); p1.st = -1; }
                 } else {
-                    issue_loads(m0 + kTcN * k, va1, vb1);
+                    now.raw = issue_loads(m0 + kTcN * k, va1, vb1);
                     p1 = now;
                     if (p0.st >= 0) { flush(p0, va0, vb0); p0.st = -1; }
                 }
@@ -936,11 +947,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     const uint32_t d = d0 + (uint32_t)(2 * kTcN * slot);
                     // planes: A 0=Ar_hi 1=Ar_lo 2=Ai_hi 3=Ai_lo (48 TMEM columns each);  B 0=Xr_hi 1=Xr_lo 2=Xi_hi 3=Xi_lo.
                     // D_re = Ar Xr - Ai Xi,  D_im = Ar Xi + Ai Xr; small terms (lo*hi, hi*lo) first.
-                    constexpr int a_pl[6] = {1, 0, 3, 2, 0, 2};
-                    constexpr int b_re[6] = {0, 1, 2, 3, 0, 2}, n_re[6] = {0, 0, 1, 1, 0, 1};
-                    constexpr int b_im[6] = {2, 3, 0, 1, 2, 0};
+                    // tf32: lo*lo is dropped (2^-22 relative); fp16 (exact int16 operand): all four partial products
+                    constexpr int kTerms = F16 ? 8 : 6;
+                    constexpr int a_pl[8] = {1, 0, 3, 2, 0, 2, 1, 3};
+                    constexpr int b_re[8] = {0, 1, 2, 3, 0, 2, 1, 3}, n_re[8] = {0, 0, 1, 1, 0, 1, 0, 1};
+                    constexpr int b_im[8] = {2, 3, 0, 1, 2, 0, 3, 1};
+                    // issue order: the two lo*lo terms (fp16 only) first, then as before
+                    constexpr int order[8] = {6, 7, 0, 1, 2, 3, 4, 5};
 #pragma unroll
-                    for (int t = 0; t < 6; t++) {
+                    for (int tt = 0; tt < 8; tt++) {
+                        const int t = order[tt];
+                        if (t >= kTerms) continue;
+                        const bool first_term = F16 ? tt == 0 : tt == 2;
                         const int ap = a_pl[t];
                         const int bp = half ? b_im[t] : b_re[t];
                         const uint32_t id = (!half && n_re[t]) ? idesc_na : idesc;
@@ -949,8 +967,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                             // tf32: K-step = 8 samples = chunks 2 ks, 2 ks + 1 of the row pair; fp16: K-step = one whole row
                             const uint32_t baddr = F16 ? b0 + bp * kPl + 16 * ks : b0 + bp * kPl + 16 * (ks >> 1) + kTcP * ((2 * ks) & 3);
                             const uint64_t bd = ((uint64_t)b_hi32 << 32) | (uint64_t)(((baddr >> 4) & 0x3fff) | lo_lbo);
-                            if constexpr (F16) tc_mma_ts_f16(d, tm + (uint32_t)(kACols * ap + 8 * ks), bd, id, (t | ks) ? 1u : 0u);
-                            else tc_mma_ts(d, tm + (uint32_t)(kACols * ap + 8 * ks), bd, id, (t | ks) ? 1u : 0u);
+                            const uint32_t acc = (first_term && ks == 0) ? 0u : 1u;
+                            if constexpr (F16) tc_mma_ts_f16(d, tm + (uint32_t)(kACols * ap + 8 * ks), bd, id, acc);
+                            else tc_mma_ts(d, tm + (uint32_t)(kACols * ap + 8 * ks), bd, id, acc);
                         }
                     }
                     tc_commit(b_empty + st);
@@ -1072,7 +1091,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
 }
 
-typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const float*, const unsigned*, const NcoDev*,
+typedef void (*K1TFn)(const void*, int, const float2*, float2*, int, int, const float*, const NcoDev*,
                       const unsigned long long*, unsigned long long*, int, OutDesc, float);
 static K1TFn k1t_kernel(int ncr, int nhb, bool f16)
 {
@@ -1500,7 +1519,7 @@ Decimator::~Decimator()
     for (auto& p : ev_pool_) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaFree(d_nco_);
     cudaFree(d_tc_coef_);
-    cudaFree(d_absmax_);
+    cudaFree(d_tc_coef16_);
     cudaFree(d_phase_[0]);
     cudaFree(d_phase_[1]);
     for (float2* p : d_stage_) cudaFree(p);
@@ -1665,14 +1684,10 @@ int Decimator::init(int nch, double in_rate, double max_bw, int block_len, cudaS
         CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         tc_groups_ = (stride_ + 127) / 128;
         CSDR_CK(cudaMalloc(&d_tc_coef_, (size_t)tc_groups_ * 128 * 192 * sizeof(float)));
-        // CUTESDR_TC_F16=1: fp16 hi/lo operands instead of tf32 (twice the tensor rate, same accuracy, scale-free through the
-        // block maximum). Opt-in: inside the step the kernel is not tensor-bound, so the halved MMA time does not pay for the
-        // extra k_absmax pass yet (alone 106 vs 120 us, tensor pipe 35 % vs 66 % active, issue slots 75 % either way; 0.336 vs 0.312 ms per step).
-        tc_f16_ = tun_.tc_f16;
-        K1TFn tf = k1t_kernel(ncic_ - 4, nhbf_, tc_f16_);
-        CSDR_CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-        CSDR_CK(cudaMalloc(&d_absmax_, sizeof(unsigned)));
-        CSDR_CK(cudaMemsetAsync(d_absmax_, 0, sizeof(unsigned), st_));
+        // two forms of the A table: tf32 hi/lo for float32 / int24 blocks, fp16 hi/lo for int16 blocks (see k_mix_tc)
+        CSDR_CK(cudaMalloc(&d_tc_coef16_, (size_t)tc_groups_ * 128 * 192 * sizeof(float)));
+        CSDR_CK(cudaFuncSetAttribute(k1t_kernel(ncic_ - 4, nhbf_, false), cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+        CSDR_CK(cudaFuncSetAttribute(k1t_kernel(ncic_ - 4, nhbf_, true), cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
         // one persistent CTA per SM, kTcSegs interleaved time segments per CTA; every segment pays PRE priming
         // outputs and rounds up to whole MMA tiles
         const int pre = tc_pre(ncic_ - 4, nhbf_);
@@ -1789,22 +1804,17 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
     if (tc_ && L % 256 == 0) {
         if (tc_dirty_) {
             const int n = tc_groups_ * 128 * 48;
-            if (tc_f16_) k_tc_coeffs_f16<<<(n / 2 + 255) / 256, 256, 0, st_>>>(d_nco_, stride_, tc_groups_, reinterpret_cast<uint32_t*>(d_tc_coef_));
-            else k_tc_coeffs<<<(n + 255) / 256, 256, 0, st_>>>(d_nco_, stride_, tc_groups_, d_tc_coef_);
-            lc_->n++;
+            k_tc_coeffs<<<(n + 255) / 256, 256, 0, st_>>>(d_nco_, stride_, tc_groups_, d_tc_coef_);
+            k_tc_coeffs_f16<<<(n / 2 + 255) / 256, 256, 0, st_>>>(d_nco_, stride_, tc_groups_, reinterpret_cast<uint32_t*>(d_tc_coef16_));
+            lc_->n += 2;
             CSDR_CK(cudaGetLastError());
             tc_dirty_ = false;
         }
-        if (tc_f16_) {
-            CSDR_CK(cudaMemsetAsync(d_absmax_, 0, sizeof(unsigned), st_));
-            k_absmax<<<296, 256, 0, st_>>>(d_x, fmt, halo_cur, L, d_absmax_);
-            lc_->n++;
-            CSDR_CK(cudaGetLastError());
-        }
+        tc_f16_ = fmt == 1;            // int16 blocks take the exact fp16 form
         const int sl = std::min(tc_seg_len_, L);
         dim3 grid(((L + sl - 1) / sl + kTcSegs - 1) / kTcSegs, tc_groups_);
-        k1t_kernel(ncic_ - 4, nhbf_, tc_f16_)<<<grid, kTcThreads, kTcSmem, st_>>>(d_x, fmt, halo_cur, halo_next, L, sl, d_tc_coef_, d_absmax_, d_nco_, pc, pn,
-                                                                          stride_, od, scale);
+        k1t_kernel(ncic_ - 4, nhbf_, tc_f16_)<<<grid, kTcThreads, kTcSmem, st_>>>(d_x, fmt, halo_cur, halo_next, L, sl, tc_f16_ ? d_tc_coef16_ : d_tc_coef_,
+                                                                          d_nco_, pc, pn, stride_, od, scale);
     } else if (L % Q == 0) {
         const int threads = std::min(256, round_up(stride_, 32));
         dim3 grid((L + tile_len_ - 1) / tile_len_, (stride_ + threads - 1) / threads);

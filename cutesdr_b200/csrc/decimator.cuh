@@ -22,7 +22,7 @@ inline int sample_bytes(int fmt) { return fmt == 0 ? 8 : (fmt == 1 ? 4 : 6); }
 // Tuning / ablation knobs, read from the environment ONCE per Decimator::init (never on the launch path).
 // None is needed for correctness; DESIGN.md section 7 lists them.
 struct Tuning {
-    bool no_tc = false, tc_f16 = false, no_hbchain = false, hbtail = false, no_overlap = false, debug_timing = false;
+    bool no_tc = false, no_hbchain = false, hbtail = false, no_overlap = false, debug_timing = false;
     bool no_hbstream = false, no_hbtail = false;
     int fuse_hb = -1, tile = 0, tc_seg = 0, hs_halo = 300, hs_ctas = 3, tc_spare = 0;
     static Tuning from_env();
@@ -76,7 +76,7 @@ public:
     // kernel 1T in use? and the real multiply-adds (MAC = 2 flop) of its GEMM per full block, counted ONCE per product
     // (fp32-equivalent: the three tf32 partial products that emulate one fp32 product count as one)
     bool tensor_path() const { return tc_; }
-    bool tensor_f16() const { return tc_ && tc_f16_; }        // fp16 hi/lo operands (kind::f16) instead of tf32
+    bool tensor_f16() const { return tc_ && tc_f16_; }        // the last block ran the fp16 form (int16 wire samples, kind::f16)
     double tensor_flops_per_block() const { return tc_ ? 2.0 * (128.0 * tc_groups_) * (block_len_ / 16.0) * 192.0 : 0.0; }
 
     int nch() const { return nch_; }
@@ -103,7 +103,7 @@ private:
     bool tc_ = false, tc_dirty_ = true, tc_f16_ = false;
     int tc_seg_len_ = 0, tc_groups_ = 0;
     float* d_tc_coef_ = nullptr;
-    unsigned* d_absmax_ = nullptr;     // max |sample| of [halo | block] as float bits (input scale of the fp16 form)
+    float* d_tc_coef16_ = nullptr;     // fp16 hi/lo form of the kernel-1T coefficient table (int16 blocks)
     NcoDev* d_nco_ = nullptr;
     unsigned long long* d_phase_[2] = {nullptr, nullptr};
     int phase_cur_ = 0;

@@ -116,6 +116,7 @@ int cutesdr_mgpu_init(cutesdr_mgpu** out, const void* id128, int rank, int world
     CSDR_CK(cudaSetDevice(device));
     std::unique_ptr<cutesdr_mgpu> m(new cutesdr_mgpu());
     m->rank = rank; m->world = world; m->device = device;
+    if (const char* e = getenv("CUTESDR_BCAST_CHUNK_KB")) { const long kb = atol(e); if (kb >= 64) m->chunk_bytes = (size_t)kb << 10; }
     CSDR_CK(cudaStreamCreateWithFlags(&m->st_comm, cudaStreamNonBlocking));
     if (world > 1) {
         CSDR_TRY(nccl_ready());

@@ -160,7 +160,7 @@ void cutesdr_mgpu_destroy(cutesdr_mgpu* m);
 int cutesdr_mgpu_info(cutesdr_mgpu* m, int* rank, int* world, int* nccl_version, long long* blocks, long long* bytes_bcast);
 int cutesdr_mgpu_channel_slice(int n_channels, int rank, int world, int* first, int* count);
 /* cutesdr_bank_process_async_raw for one DSP block whose samples only rank 0 has: iq_rank0 (PINNED host memory, format
- * fmt, n_in == block_length; ignored on the other ranks) is copied to rank 0's GPU in 1 MiB chunks and every chunk is
+ * fmt, n_in == block_length; ignored on the other ranks) is copied to rank 0's GPU in 4 MiB chunks and every chunk is
  * broadcast as soon as it has landed (the copy of chunk k+1 overlaps the broadcast of chunk k), directly into the
  * bank's input slot on every rank; the block's kernels, the audio D2H and the host-buffer contract are those of
  * cutesdr_bank_process_async. Every rank must make the same sequence of calls. world == 1 degenerates to process_async. */

@@ -58,7 +58,7 @@ def _info(m, c):
     return M.demod_info(m, AgcHangOn=(c % 8 == 0))
 
 
-def _gpu_bank(fs, modes, carriers, infos, iq, check, audio_rate=0.0, blanker=False, spectrum=None):
+def _gpu_bank(fs, modes, carriers, infos, iq, check, audio_rate=0.0, blanker=False, spectrum=None, int16=False):
     """Runs the whole bank over the stream block by block (host entry point, cutesdr_bank_process); returns
     {channel: audio} for the checked channels and the per-block spectrum screens when `spectrum` is given."""
     nch = len(modes)
@@ -79,8 +79,14 @@ def _gpu_bank(fs, modes, carriers, infos, iq, check, audio_rate=0.0, blanker=Fal
         fb = cs.CFft()
         fb.SetFFTParams(65536, False, 0.0, fs)
         fb.SetFFTAve(4)
+    f16_form = []
     for k in range(len(iq) // L):
-        audio, n_out = bank.ProcessData(iq[k * L:(k + 1) * L])
+        if int16:       # the radio's wire format: interleaved int16 I, Q (the stream is integer-valued)
+            blk = np.ascontiguousarray(iq[k * L:(k + 1) * L]).view(np.float32).astype(np.int16).reshape(-1, 2)
+            audio, n_out = bank.ProcessRaw(blk, 1)
+            f16_form.append(bool(bank.kernel_model(1)[0]))
+        else:
+            audio, n_out = bank.ProcessData(iq[k * L:(k + 1) * L])
         for c in check:
             outs[c].append(audio[c, :n_out[c]].copy())
         if fb is not None:
@@ -88,6 +94,9 @@ def _gpu_bank(fs, modes, carriers, infos, iq, check, audio_rate=0.0, blanker=Fal
             fb.put_device(ptr + 8 * spectrum["offset"], 65536)
             screens.append([fb.GetScreenIntegerFFTData(*a) for a in spectrum["screens"]])
     tc = bank.kernel_model()[0]
+    if int16 and tc:
+        # every block but the first (whose oscillator start-up gain is applied in float32) ran the fp16 form
+        assert not f16_form[0] and all(f16_form[1:]), f16_form
     sm = {c: bank.GetSMeterAve(c) for c in check[:8]}
     del bank
     return {c: np.concatenate(outs[c]) for c in check}, screens, tc, sm
@@ -211,6 +220,29 @@ def test_cfg4_1024_channels_seeded_64_vs_reference(refbig, no_tc):
         got, _, tc, _ = _gpu_bank(fs, modes, carriers, infos, iq, check, audio_rate=48000.0)
     assert tc == (no_tc is None)
     _compare(ref, got, modes, "cfg4 1024-ch NBFM -> 48 kHz @ 100.1472 Msps (%s)" % ("kernel 1T" if tc else "CUDA-core kernel 1"), pert)
+
+
+def test_cfg4_int16_wire_samples_fp16_form_of_kernel_1t_vs_reference(refbig):
+    """The same bank fed the radio's int16 wire format (cutesdr_bank_process_raw): kernel 1T then runs its fp16 form
+    (exact hi/lo split of the samples, kind::f16, all four partial products). The reference sees the same integers."""
+    fs, nch = 100147200.0, 1024
+    modes = [M.DEMOD_FM] * nch
+    infos = [M.demod_info(M.DEMOD_FM) for _ in range(nch)]
+    check = sorted(int(v) for v in np.random.default_rng(20266).choice(nch, 64, replace=False))
+
+    def make():
+        iq, carriers = syn_iq_fft(fs, NBLK * 1001472, modes, carrier_grid(nch, 78125.0), seed=20266, decim=2048)
+        v = iq.view(np.float32)
+        v *= np.float32(30000.0 / np.abs(v).max())
+        np.rint(v, out=v)                                   # integer-valued, inside the int16 range
+        ref, _ = _ref_chains(refbig, fs, modes, carriers, infos, iq, check, audio_rate=48000.0)
+        pert, _ = _ref_chains(refbig, fs, modes, carriers, infos, _perturb_1ulp(iq, 1), check, audio_rate=48000.0)
+        return iq, carriers, ref, pert
+
+    iq, carriers, ref, pert = _cached("cfg4i16", make)
+    got, _, tc, _ = _gpu_bank(fs, modes, carriers, infos, iq, check, audio_rate=48000.0, int16=True)
+    assert tc
+    _compare(ref, got, modes, "cfg4 1024-ch NBFM -> 48 kHz @ 100.1472 Msps, int16 wire samples (kernel 1T, fp16 form)", pert)
 
 
 @pytest.mark.parametrize("no_tc", [None, "1"], ids=["k_mix_tc", "CUTESDR_NO_TC"])

@@ -1003,3 +1003,79 @@ def test_retune_storm_leaves_other_channels_bit_identical(lib, orc):
         assert best > SNR_MIN, "moved channel %d (%s at block %d): best alignment %.1f dB" % (c, M.MODE_NAMES[mode], k0, best)
         checked += 1
     assert checked >= 3
+
+
+def test_process_async_host_buffer_may_be_rewritten_after_two_calls(lib):
+    """The header's contract for cutesdr_bank_process_async: the iq buffer handed to call k must stay unchanged until
+    call k+2 has returned -- and no longer. A producer that recycles TWO host buffers and overwrites each one right after
+    the second following call gets the same bits as one that keeps every block alive (the library waits on the host for
+    the slot's previous H2D copy before it returns)."""
+    fs, nch = 2e6, 6
+    modes = [[M.DEMOD_AM, M.DEMOD_USB][c % 2] for c in range(nch)]
+    carriers = carrier_grid(nch, 200e3)
+    infos = [M.demod_info(m, HiCut=2800, LowCut=100) if m == M.DEMOD_USB else M.demod_info(m) for m in modes]
+    banks = []
+    for _ in range(2):
+        b = cs.ReceiverBank(nch, fs)
+        for c in range(nch):
+            b.SetDemod(c, modes[c], infos[c])
+            b.SetDemodFreq(c, -carriers[c])
+        banks.append(b)
+    L = banks[0].block_length()
+    nblk = 40
+    iq = syn_iq(fs, nblk * L, modes, carriers, seed=78)
+    stride = 2304
+    keep = [np.zeros((nch, stride), dtype=np.float32) for _ in range(nblk)]
+    recy = [np.zeros((nch, stride), dtype=np.float32) for _ in range(nblk)]
+    n_keep = [np.zeros(nch, dtype=np.int32) for _ in range(nblk)]
+    n_recy = [np.zeros(nch, dtype=np.int32) for _ in range(nblk)]
+    import torch
+    pinned = [torch.empty(2 * L, dtype=torch.float32).pin_memory() for _ in range(3)]       # pinned: the H2D copy is a real DMA
+    ring = [t.numpy().view(np.complex64) for t in pinned]            # buffer k % 3 is rewritten right after call k+2
+    for k in range(nblk):
+        blk = iq[k * L:(k + 1) * L]
+        banks[0].process_async_ptr(L, blk.ctypes.data, keep[k].ctypes.data, stride, n_keep[k])
+        ring[k % 3][:] = blk
+        banks[1].process_async_ptr(L, ring[k % 3].ctypes.data, recy[k].ctypes.data, stride, n_recy[k])
+        if k >= 2:
+            ring[(k - 2) % 3][:] = np.complex64(1e9)                 # poison: a late DMA read would wreck the audio
+    banks[0].synchronize()
+    banks[1].synchronize()
+    for k in range(nblk):
+        assert np.array_equal(n_keep[k], n_recy[k])
+        for c in range(nch):
+            assert np.array_equal(keep[k][c, :n_keep[k][c]], recy[k][c, :n_recy[k][c]])
+
+
+def test_two_banks_on_two_devices_in_one_process(lib):
+    """Per-device function attributes (> 48 KB dynamic shared memory) are set for every device a bank lives on: two banks
+    on two GPUs of one process run the same stream and give the same bits (skipped on a one-GPU box)."""
+    import ctypes as C
+    n = np.zeros(1, dtype=np.int32)
+    lib.cutesdr_device_count(n.ctypes.data_as(C.POINTER(C.c_int)))
+    if n[0] < 2:
+        pytest.skip("needs two CUDA devices")
+    fs, nch = 100147200.0, 64
+    modes = [M.DEMOD_FM] * nch
+    carriers = carrier_grid(nch, 78125.0)
+    infos = [M.demod_info(M.DEMOD_FM) for _ in range(nch)]
+    outs = []
+    iq = None
+    for dev in (0, 1):
+        b = cs.ReceiverBank(nch, fs, device=dev)
+        b.SetAudioRate(48000.0)
+        for c in range(nch):
+            b.SetDemod(c, modes[c], infos[c])
+            b.SetDemodFreq(c, -carriers[c])
+        L = b.block_length()
+        if iq is None:
+            iq = syn_iq(fs, 6 * L, modes, carriers, seed=5)
+        got = []
+        for k in range(6):
+            audio, n_out = b.ProcessData(iq[k * L:(k + 1) * L])
+            got.append([audio[c, :n_out[c]].copy() for c in range(nch)])
+        outs.append(got)
+    for k in range(6):
+        for c in range(nch):
+            assert np.array_equal(outs[0][k][c], outs[1][k][c])
+    assert sum(len(outs[0][k][0]) for k in range(6)) > 0
