@@ -1005,9 +1005,14 @@ int cutesdr_bank_kernel_model(cutesdr_bank* b, int which, int* on_tensor_cores, 
     std::lock_guard<std::mutex> lk(b->mu);
     CSDR_CK(cudaSetDevice(b->device));
     if (b->layout_dirty) CSDR_TRY(b->rebuild());
-    int all = b->groups.empty() ? 0 : 1;
+    int all = 0;
     double fl = 0.0;
+    bool any = false;
     for (auto& g : b->groups) {
+        bool used = false;                  // groups whose slots are all parked run no kernels
+        for (int u : g->chans) used |= (u >= 0);
+        if (!used) continue;
+        if (!any) { any = true; all = 1; }
         if (!g->dec.tensor_path() || (which == 1 && !g->dec.tensor_f16())) all = 0;
         fl += g->dec.tensor_flops_per_block();
     }

@@ -857,16 +857,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                             *reinterpret_cast<uint2*>(pl + 3 * kPl + off) = make_uint2(lo[2], lo[3]);
                             continue;
                         }
-                        const float xr[4] = {a.x * s_in, a.z * s_in, b.x * s_in, b.z * s_in};
-                        const float xi[4] = {a.y * s_in, a.w * s_in, b.y * s_in, b.w * s_in};
+                        // samples that did not arrive as whole int16 tiles (the float32 halo of the previous block, tiles that
+                        // straddle the block ends): the SAME split in float arithmetic -- u = x + 32768, hi = floor(u / 64) - 512,
+                        // lo = (u mod 64) / 64 -- so a sample's operand never depends on which tile or segment carried it
+                        const float xr[4] = {a.x, a.z, b.x, b.z};
+                        const float xi[4] = {a.y, a.w, b.y, b.w};
                         __half2 rh[2], rl[2], ih[2], il[2];
+                        auto split = [&](float x, float& hi, float& lo) {
+                            const float u = x + 32768.0f;
+                            const float q = floorf(u * s_in);
+                            hi = q - 512.0f;
+                            lo = fmaf(q, -64.0f, u) * s_in;
+                        };
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
-                            rh[h] = __floats2half2_rn(xr[2 * h], xr[2 * h + 1]);
-                            ih[h] = __floats2half2_rn(xi[2 * h], xi[2 * h + 1]);
-                            const float2 rf = __half22float2(rh[h]), jf = __half22float2(ih[h]);
-                            rl[h] = __floats2half2_rn(xr[2 * h] - rf.x, xr[2 * h + 1] - rf.y);
-                            il[h] = __floats2half2_rn(xi[2 * h] - jf.x, xi[2 * h + 1] - jf.y);
+                            float h0, l0, h1, l1;
+                            split(xr[2 * h], h0, l0);
+                            split(xr[2 * h + 1], h1, l1);
+                            rh[h] = __floats2half2_rn(h0, h1);
+                            rl[h] = __floats2half2_rn(l0, l1);
+                            split(xi[2 * h], h0, l0);
+                            split(xi[2 * h + 1], h1, l1);
+                            ih[h] = __floats2half2_rn(h0, h1);
+                            il[h] = __floats2half2_rn(l0, l1);
                         }
                         auto put = [&](int plane, const __half2* v) {
                             uint2 u;

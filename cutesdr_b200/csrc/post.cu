@@ -213,14 +213,20 @@ __device__ __forceinline__ void tile_fetch(double* tile, const double* base, siz
 }
 __device__ __forceinline__ void tile_store(const double* tile, double* base, size_t stride, int c0, int k, uint32_t rowmask, int lane)
 {
+    // all eight chunks into their own registers first, then the eight stores: a store reads its registers long after it
+    // issues, and a load that reuses them has to wait for that (the compiler otherwise cycles through two register quads
+    // and the eight load/store pairs serialise on the store pipe's latency)
     const int j = lane & 7;
+    double2 v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int r = 4 * i + (lane >> 3);
-        if ((rowmask >> r) & 1u) {
-            const double2 v = *reinterpret_cast<const double2*>(tile + r * kTileT + ((j ^ (r & 7)) << 1));
-            *reinterpret_cast<double2*>(base + (size_t)(c0 + r) * stride + (size_t)k * kTileT + 2 * j) = v;
-        }
+        v[i] = *reinterpret_cast<const double2*>(tile + r * kTileT + ((j ^ (r & 7)) << 1));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int r = 4 * i + (lane >> 3);
+        if ((rowmask >> r) & 1u) *reinterpret_cast<double2*>(base + (size_t)(c0 + r) * stride + (size_t)k * kTileT + 2 * j) = v[i];
     }
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -239,35 +245,134 @@ __device__ __forceinline__ void row_st(double* tile, int lane, int j, double a, 
 // under a predicate inside a select, which turns a two-instruction clamp into a branch)
 __device__ __forceinline__ double in_reg(double v) { asm volatile("" : "+d"(v)); return v; }
 
-// ---- sequential poles; even warps run the AGC averagers of 32 channels, odd warps the S-meter of the same channels.
-// The loops are bound by one dependent FP64 chain per lane, so the warps are PACKED: kSeqThreads per CTA puts the whole
-// bank on a handful of SMs instead of one 32-thread CTA on each of 64 SMs -- kernel 1T needs a whole SM (every register)
+// A compute warp and its HELPER warp. The compute warp's lanes run one dependent FP64 chain each and should issue nothing
+// else: every instruction of an in-order warp that is not part of the chain delays it. So the tile traffic belongs to a
+// second warp: the helper queues the cp.async fetches (kStages - 1 tiles ahead; cp.async.mbarrier.arrive.noinc flips the
+// tile's `full` barrier when its copies have landed) and writes finished output tiles back; the compute warp only waits
+// on `full`, walks its 16 samples out of shared memory, and hands the stage (`empty`) and the output slot (`ofull`) over
+// with one elected arrive each. Two output slots alternate (`oempty` returns them).
+template <int NIN, int NOUT, int S>
+struct TilePipe {
+    static constexpr int kBarBytes = 128;
+    static constexpr int kDoubles = kBarBytes / 8 + (S * NIN + 2 * NOUT) * kTileD;       // shared memory per warp pair
+    uint64_t* bars;
+    double* tiles;
+    __device__ __forceinline__ TilePipe(double* base) : bars(reinterpret_cast<uint64_t*>(base)), tiles(base + kBarBytes / 8) {}
+    __device__ __forceinline__ uint32_t full(int s) const { return smem_u32(bars + s); }
+    __device__ __forceinline__ uint32_t empty(int s) const { return smem_u32(bars + S + s); }
+    __device__ __forceinline__ uint32_t ofull(int o) const { return smem_u32(bars + 2 * S + o); }
+    __device__ __forceinline__ uint32_t oempty(int o) const { return smem_u32(bars + 2 * S + 2 + o); }
+    __device__ __forceinline__ double* in_tile(int s, int a) const { return tiles + (s * NIN + a) * kTileD; }
+    __device__ __forceinline__ double* out_tile(int o, int a) const { return tiles + (S * NIN + o * NOUT + a) * kTileD; }
+    __device__ __forceinline__ void init() const          // one thread of the pair, before the CTA-wide barrier
+    {
+        for (int s = 0; s < S; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(full(s)));        // every helper lane's copies
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty(s)));
+        }
+        for (int o = 0; o < 2; o++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ofull(o)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(oempty(o)));
+        }
+    }
+    // try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase flips. A compute warp and a
+    // helper warp share every SM sub-partition; a warp that polls in a tight loop takes issue slots from the other.
+    static __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity)
+    {
+        asm volatile(
+            "{\n\t.reg .pred p;\n"
+            "W_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+            "@p bra D_%=;\n\t"
+            "bra W_%=;\n"
+            "D_%=:\n\t}\n" ::"r"(bar), "r"(parity), "r"(0x989680)
+            : "memory");
+    }
+    static __device__ __forceinline__ void arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+    // whole warp: every lane is past its accesses, then one lane signals
+    static __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
+    {
+        __syncwarp();
+        if (lane == 0) arrive(bar);
+    }
+    // ---- compute warp
+    __device__ __forceinline__ const double* acquire_in(int k) const { wait(full(k % S), (uint32_t)(k / S) & 1u); return in_tile(k % S, 0); }
+    __device__ __forceinline__ void release_in(int k, int lane) const { warp_arrive(empty(k % S), lane); }
+    __device__ __forceinline__ double* acquire_out(int k) const
+    {
+        if (k >= 2) wait(oempty(k & 1), (uint32_t)((k >> 1) - 1) & 1u);
+        return out_tile(k & 1, 0);
+    }
+    __device__ __forceinline__ void release_out(int k, int lane) const { warp_arrive(ofull(k & 1), lane); }
+    // ---- helper warp: src[a] / dst[a] point at sample 0 of row 0 of the arrays; in_mask[a] / out_mask[a] pick the rows
+    // `post(tile 0 of the slot, chunk)` runs on every helper lane between the compute warp's hand-over and the stores
+    template <class Post>
+    __device__ __forceinline__ void serve(int nchunks, int c0, int lane, const double* const* src, const size_t* sstride, const uint32_t* in_mask,
+                                          double* const* dst, const size_t* dstride, const uint32_t* out_mask, bool with_out, Post&& post) const
+    {
+        const int iters = with_out ? nchunks + S - 1 : nchunks;
+        for (int i = 0; i < iters; i++) {
+            if (i < nchunks) {
+                const int s = i % S;
+                if (i >= S) wait(empty(s), (uint32_t)(i / S - 1) & 1u);
+#pragma unroll
+                for (int a = 0; a < NIN; a++) tile_fetch(in_tile(s, a), src[a], sstride[a], c0, i, in_mask[a], lane);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full(s)) : "memory");
+            }
+            const int j = i - (S - 1);
+            if (NOUT > 0 && with_out && j >= 0) {
+                wait(ofull(j & 1), (uint32_t)(j >> 1) & 1u);
+                post(out_tile(j & 1, 0), j);
+                __syncwarp();
+#pragma unroll
+                for (int a = 0; a < NOUT; a++) tile_store(out_tile(j & 1, a), dst[a], dstride[a], c0, j, out_mask[a], lane);
+                warp_arrive(oempty(j & 1), lane);
+            }
+        }
+    }
+};
+
+// ---- sequential poles. CTA = 4 compute warps + their 4 helper warps; compute warp pairs (2p, 2p+1) run the AGC averagers
+// and the S-meter of the same 32 channels. The loops are bound by one dependent FP64 chain per lane, so the warps are
+// PACKED on a handful of SMs instead of one 32-thread CTA on each of 64 SMs -- kernel 1T needs a whole SM (every register)
 // per CTA and cannot start on an SM that hosts even one of these warps for as long as they live.
-constexpr int kSeqThreads = 256;
-constexpr int kSeq2Threads = 128;
-constexpr int kSeq1Stages = 4;
-constexpr int kSeq2Stages = 4;
-constexpr int kSeq1WarpD = (kSeq1Stages + 1) * kTileD;          // doubles of shared memory per warp: input ring + one output tile
-constexpr int kSeq2WarpD = (2 * kSeq2Stages + 2) * kTileD;      // (th, u) ring + (v, lp) output tiles
-constexpr int kSeq1Smem = (kSeqThreads / 32) * kSeq1WarpD * 8;
-constexpr int kSeq2Smem = (kSeq2Threads / 32) * kSeq2WarpD * 8;
+constexpr int kSeqPairs = 4;                     // compute warps per CTA (each with a helper warp)
+constexpr int kSeqThreads = 64 * kSeqPairs;
+constexpr int kSeqStages = 4;
+typedef TilePipe<1, 1, kSeqStages> Seq1Pipe;
+typedef TilePipe<2, 2, kSeqStages> Seq2Pipe;
+constexpr int kSeq1Smem = kSeqPairs * Seq1Pipe::kDoubles * 8;
+constexpr int kSeq2Smem = kSeqPairs * Seq2Pipe::kDoubles * 8;
 __global__ void __launch_bounds__(kSeqThreads, 1) k_post_seq1(PostBufs b, int n, PostUniform u)
 {
     extern __shared__ __align__(128) double sm_tiles[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * (kSeqThreads / 32) + warp;
+    const int pair = warp % kSeqPairs;
+    const bool helper = warp >= kSeqPairs;
+    Seq1Pipe pipe(sm_tiles + pair * Seq1Pipe::kDoubles);
+    if (!helper && lane == 0) pipe.init();
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int gw = blockIdx.x * kSeqPairs + pair;
     const int c0 = (gw >> 1) * 32, c = c0 + lane;
     const bool smeter_warp = (gw & 1) != 0;
     if (c0 >= b.nch) return;
     const bool in_bank = c < b.nch;
     const int mode = in_bank ? b.mode[c] : POST_NONE;
     const int nchunks = n / kTileT, n16 = nchunks * kTileT;
-    double* ring = sm_tiles + warp * kSeq1WarpD;
-    double* otile = ring + kSeq1Stages * kTileD;
+    const bool act = in_bank && (smeter_warp ? mode != POST_AGC_ONLY : PAR(P_AGC_ON) != 0.0);
+    const uint32_t mask = __ballot_sync(0xffffffffu, act);
+    if (!mask) return;
+    if (helper) {
+        double* arr = smeter_warp ? b.smag : b.peak;
+        const double* src[1] = {arr};
+        double* dst[1] = {arr};
+        const size_t st[1] = {(size_t)b.row};
+        const uint32_t im[1] = {mask}, om[1] = {smeter_warp ? 0u : mask};
+        pipe.serve(nchunks, c0, lane, src, st, im, dst, st, om, !smeter_warp, [](double*, int) {});
+        return;
+    }
     if (smeter_warp) {
-        const bool act = in_bank && mode != POST_AGC_ONLY;
-        const uint32_t mask = __ballot_sync(0xffffffffu, act);
-        if (!mask) return;
         // CSMeter::ProcessData, dsp/smeter.cpp:77-91
         double sm_att = 0, sm_dec = 0, sm_ave = 0, sm_peak = 0;
         if (act) { sm_att = ST(S_SM_ATT); sm_dec = ST(S_SM_DEC); sm_ave = ST(S_SM_AVE); sm_peak = ST(S_SM_PEAK); }
@@ -282,18 +387,14 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_post_seq1(PostBufs b, int n,
             sm_dec = sa > sd ? sa : sd;
             sm_peak = mag > sm_peak ? mag : sm_peak;
         };
-        for (int k = 0; k < kSeq1Stages - 1; k++) { if (k < nchunks) tile_fetch(ring + k * kTileD, b.smag, b.row, c0, k, mask, lane); cp_commit(); }
         for (int k = 0; k < nchunks; k++) {
-            cp_wait<kSeq1Stages - 2>();
-            __syncwarp();
-            const int kn = k + kSeq1Stages - 1;
-            if (kn < nchunks) tile_fetch(ring + (kn % kSeq1Stages) * kTileD, b.smag, b.row, c0, kn, mask, lane);
-            cp_commit();
-            const double* x = ring + (k % kSeq1Stages) * kTileD;
-            if (act) {
+            const double* x = pipe.acquire_in(k);
+            double2 v[kTileT / 2];
 #pragma unroll
-                for (int j = 0; j < kTileT / 2; j++) { const double2 v = row_ld(x, lane, j); step(v.x); step(v.y); }
-            }
+            for (int j = 0; j < kTileT / 2; j++) v[j] = row_ld(x, lane, j);
+            pipe.release_in(k, lane);
+#pragma unroll
+            for (int j = 0; j < kTileT / 2; j++) { step(v[j].x); step(v[j].y); }
         }
         if (act) {
             const double* row = b.smag + (size_t)c * b.row;
@@ -303,9 +404,6 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_post_seq1(PostBufs b, int n,
         }
         return;
     }
-    const bool act = in_bank && PAR(P_AGC_ON) != 0.0;
-    const uint32_t mask = __ballot_sync(0xffffffffu, act);
-    if (!mask) return;
     // attack/decay averagers of CAgc::ProcessData, dsp/agc.cpp:235-276; row <- max(attack, decay)
     const int cs = act ? c : c0 + __ffs(mask) - 1;          // idle lanes read a valid channel's parameters
     const bool use_hang = b.par[(size_t)P_AGC_HANG * b.stride + cs] != 0.0;
@@ -327,22 +425,21 @@ __global__ void __launch_bounds__(kSeqThreads, 1) k_post_seq1(PostBufs b, int n,
         hang_timer = use_hang ? (gd ? 0 : hang_timer + (hold ? 1 : 0)) : hang_timer;
         return att > dec ? att : dec;
     };
-    for (int k = 0; k < kSeq1Stages - 1; k++) { if (k < nchunks) tile_fetch(ring + k * kTileD, b.peak, b.row, c0, k, mask, lane); cp_commit(); }
     for (int k = 0; k < nchunks; k++) {
-        cp_wait<kSeq1Stages - 2>();
-        __syncwarp();                       // tile k has landed for every lane; the previous tile_store has read otile
-        const int kn = k + kSeq1Stages - 1;
-        if (kn < nchunks) tile_fetch(ring + (kn % kSeq1Stages) * kTileD, b.peak, b.row, c0, kn, mask, lane);
-        cp_commit();
-        const double* x = ring + (k % kSeq1Stages) * kTileD;
+        // The warp issues in order: a shared-memory store of step t's result would hold back step t+1 until the select
+        // at the end of step t has retired. So the tile's 16 inputs come into registers first, the 16 steps run back to
+        // back, and the results leave together at the end (idle lanes run along on harmless values: no divergence).
+        const double* x = pipe.acquire_in(k);
+        double2 v[kTileT / 2];
 #pragma unroll
-        for (int j = 0; j < kTileT / 2; j++) {          // idle lanes run along on harmless values: no divergence
-            const double2 v = row_ld(x, lane, j);
-            const double o0 = step(v.x), o1 = step(v.y);
-            row_st(otile, lane, j, o0, o1);
-        }
-        __syncwarp();
-        tile_store(otile, b.peak, b.row, c0, k, mask, lane);
+        for (int j = 0; j < kTileT / 2; j++) v[j] = row_ld(x, lane, j);
+        pipe.release_in(k, lane);
+#pragma unroll
+        for (int j = 0; j < kTileT / 2; j++) { v[j].x = step(v[j].x); v[j].y = step(v[j].y); }
+        double* y = pipe.acquire_out(k);
+#pragma unroll
+        for (int j = 0; j < kTileT / 2; j++) row_st(y, lane, j, v[j].x, v[j].y);
+        pipe.release_out(k, lane);
     }
     if (act) {
         double* row = b.peak + (size_t)c * b.row;
@@ -405,36 +502,88 @@ __device__ __forceinline__ double wrap_pi(double d)
     return d - kTwoPi * rint(d * (1.0 / kTwoPi));
 }
 
-// ---- DC blockers and PLLs; lane per channel, tiles of 32 channels x 16 samples through shared memory
-__global__ void __launch_bounds__(kSeq2Threads, 1) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
+// ---- DC blockers and PLLs; lane per channel, tiles of 32 channels x 16 samples through shared memory; CTA = 4 compute
+// warps + their 4 helper warps (see TilePipe)
+__global__ void __launch_bounds__(kSeqThreads, 1) k_post_seq2(PostBufs b, int n, PostUniform u, float* __restrict__ audio,
                                                   int audio_stride, int audio_off, const int* __restrict__ chan_map)
 {
     extern __shared__ __align__(128) double sm_tiles[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c0 = (blockIdx.x * (kSeq2Threads / 32) + warp) * 32, c = c0 + lane;
+    const int pair = warp % kSeqPairs;
+    const bool helper = warp >= kSeqPairs;
+    Seq2Pipe pipe(sm_tiles + pair * Seq2Pipe::kDoubles);
+    if (!helper && lane == 0) pipe.init();
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int c0 = (blockIdx.x * kSeqPairs + pair) * 32, c = c0 + lane;
     if (c0 >= b.nch) return;
     const int mode = c < b.nch ? b.mode[c] : POST_NONE;
     const bool act = mode == POST_AM || mode == POST_SAM || mode == POST_FM;
     const bool sam_st = mode == POST_SAM && u.stereo;
-    // rows of the tile arrays this warp moves: theta in (SAM, FM), envelope in (AM, SAM), FIR row out (AM, FM),
+    // rows of the tile arrays this warp pair moves: theta in (SAM, FM), envelope in (AM, SAM), FIR row out (AM, FM),
     // speculative biquad out (FM; it reuses the envelope array, which AM / SAM rows must keep)
     const uint32_t m_th = __ballot_sync(0xffffffffu, mode == POST_SAM || mode == POST_FM);
     const uint32_t m_u = __ballot_sync(0xffffffffu, mode == POST_AM || mode == POST_SAM);
     const uint32_t m_v = __ballot_sync(0xffffffffu, mode == POST_AM || mode == POST_FM);
     const uint32_t m_lp = __ballot_sync(0xffffffffu, mode == POST_FM);
     if (!(m_th | m_u)) return;
-    double* ring = sm_tiles + warp * kSeq2WarpD;                  // stage s: theta tile at 2 s, envelope tile at 2 s + 1
-    double* o_v = ring + 2 * kSeq2Stages * kTileD;
-    double* o_lp = o_v + kTileD;
-    float* aout = (audio && act) ? audio + (size_t)chan_map[c] * audio_stride + (u.stereo ? 2 : 1) * audio_off : nullptr;
     double* vbase = b.v + kHist;
     const int nchunks = n / kTileT, n16 = nchunks * kTileT;
-    // state (a lane uses the fields of its mode)
-    double z1 = 0, y1 = 0, phase = 0, freq = 0, fm_dc = 0, w1 = 0, w2 = 0, lp = 0;
-    if (act) {
-        z1 = ST(S_Z1); y1 = ST(S_Y1); phase = ST(S_PHASE); freq = ST(S_FREQ); fm_dc = ST(S_FM_DC); w1 = ST(S_LP_W1); w2 = ST(S_LP_W2);
-    }
     const bool is_fm = mode == POST_FM;
+    const bool tail = n16 < n;
+    if (helper) {
+        const double* src[2] = {b.th, b.u};
+        const size_t sst[2] = {(size_t)b.row, (size_t)b.row};
+        const uint32_t im[2] = {m_th, m_u};
+        double* dst[2] = {vbase, b.u};
+        const size_t dst_st[2] = {(size_t)b.v_row, (size_t)b.row};
+        const uint32_t om[2] = {m_v, m_lp};
+        // FM: what follows the PLL -- the 10 ms DC tracker on the loop frequency, the output gain and the 3 kHz low-pass
+        // biquad (dsp/fmdemod.cpp:184-187, CIir::ProcessFilter dsp/iir.cpp:171-180) -- is a pair of LINEAR recurrences
+        // that only consume the PLL's frequency. The compute warp hands the raw frequency over in the output tile; the
+        // helper's lanes turn it into the two output rows, so the PLL chain never waits behind them (one in-order warp
+        // running both took 180 clocks per sample for a 76-clock chain). The biquad only advances while the squelch is
+        // open, which is decided per burst from the whole burst (k_post_fir): it is computed here SPECULATIVELY, outputs
+        // to the (otherwise unused) envelope row, end state to S_LP_W1N/W2N; k_post_fir commits or discards them.
+        double fm_dc = 0, w1 = 0, w2 = 0;
+        if (is_fm) { fm_dc = ST(S_FM_DC); w1 = ST(S_LP_W1); w2 = ST(S_LP_W2); }
+        const double qdc = 1.0 - u.fm_dc_alpha, kdc = u.fm_dc_alpha, na1 = -u.lp_a1, na2 = -u.lp_a2;
+        auto fm_post = [&](double f, double& lp) -> double {
+            fm_dc = fma(qdc, fm_dc, kdc * f);
+            const double pre = (f - fm_dc) * u.fm_gain;
+            const double w0 = fma(na1, w1, fma(na2, w2, pre));
+            lp = fma(u.lp_b0, w0, fma(u.lp_b1, w1, u.lp_b2 * w2));
+            w2 = w1;
+            w1 = w0;
+            return pre;
+        };
+        pipe.serve(nchunks, c0, lane, src, sst, im, dst, dst_st, om, true, [&](double* o_v, int) {
+            if (!is_fm) return;
+            double* o_lp = o_v + kTileD;
+            double2 f[kTileT / 2], l[kTileT / 2];
+#pragma unroll
+            for (int j = 0; j < kTileT / 2; j++) f[j] = row_ld(o_v, lane, j);
+#pragma unroll
+            for (int j = 0; j < kTileT / 2; j++) { f[j].x = fm_post(f[j].x, l[j].x); f[j].y = fm_post(f[j].y, l[j].y); }
+#pragma unroll
+            for (int j = 0; j < kTileT / 2; j++) { row_st(o_v, lane, j, f[j].x, f[j].y); row_st(o_lp, lane, j, l[j].x, l[j].y); }
+        });
+        if (tail) {
+            // the last n % 16 samples: the compute warp left the raw frequency in the FIR row
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+            if (is_fm) {
+                double* vrow = vbase + (size_t)c * b.v_row;
+                double* urow = b.u + (size_t)c * b.row;
+                for (int t = n16; t < n; t++) { double lp; vrow[t] = fm_post(vrow[t], lp); urow[t] = lp; }
+            }
+        }
+        if (is_fm) { ST(S_FM_DC) = fm_dc; ST(S_LP_W1N) = w1; ST(S_LP_W2N) = w2; }
+        return;
+    }
+    float* aout = (audio && act) ? audio + (size_t)chan_map[c] * audio_stride + (u.stereo ? 2 : 1) * audio_off : nullptr;
+    // state (a lane uses the fields of its mode)
+    double z1 = 0, y1 = 0, phase = 0, freq = 0;
+    if (act) { z1 = ST(S_Z1); y1 = ST(S_Y1); phase = ST(S_PHASE); freq = ST(S_FREQ); }
     // The PLLs (dsp/samdemod.cpp:81-105, dsp/fmdemod.cpp:166-187). SAM: tmp = x e^{-j phase}, err = atan2(tmp) =
     // wrap(arg x - phase); FM: tmp = x e^{+j phase}, err = -atan2(tmp) = -wrap(arg x + phase); arg x comes from k_post_mid.
     // Dependent chain per sample: x (DADD) -> rint through the 1.5 * 2^52 constant (DFMA, DADD; DFRND alone costs 21
@@ -449,13 +598,28 @@ __global__ void __launch_bounds__(kSeq2Threads, 1) k_post_seq2(PostBufs b, int n
         const double x = fma(sgn, phase, th);
         const double r = fma(x, kInv2Pi, kRintMagic) - kRintMagic;
         const double err = fma(r, n2pi, -sgn * x);              // FM / stereo SAM: -(x - 2 pi r); SAM: x - 2 pi r
-        double f = fma(beta, err, freq);
+        const double f = fma(beta, err, freq);
         const double pa = fma(alpha, err, phase);
-        f = f > hi ? hi : f;
-        f = f < lo ? lo : f;
-        freq = f;
-        phase = pa + f;
+        const bool over = f > hi, under = f < lo;               // both compares on the unclamped value, side by side
+        const double fc = over ? hi : (under ? lo : f);
+        freq = fc;
+        phase = pa + fc;
         return err;
+    };
+    // The same step with the NEXT sample's detector input started early: x' = th' + sgn (pa + fc) is formed as
+    // fma(sgn, fc, fma(sgn, pa, th')) -- the inner part is ready before the clamp is, which takes the phase addition out
+    // of the dependent chain (x -> rint -> err -> freq -> clamp -> x').
+    auto pll_x = [&](double x, double th_next) -> double {
+        const double r = fma(x, kInv2Pi, kRintMagic) - kRintMagic;
+        const double err = fma(r, n2pi, -sgn * x);
+        const double f = fma(beta, err, freq);
+        const double pa = fma(alpha, err, phase);
+        const double t1 = fma(sgn, pa, th_next);
+        const bool over = f > hi, under = f < lo;
+        const double fc = over ? hi : (under ? lo : f);
+        freq = fc;
+        phase = pa + fc;
+        return fma(sgn, fc, t1);
     };
     // AM: DC removal H(z) = (1 - z^-1)/(1 - .99 z^-1), dsp/amdemod.cpp:73-78
     auto am_step = [&](double mag) -> double {
@@ -471,22 +635,6 @@ __global__ void __launch_bounds__(kSeq2Threads, 1) k_post_seq2(PostBufs b, int n
         z1 = z0;
         return o;
     };
-    // FM: the 3 kHz low-pass biquad (CIir::ProcessFilter, dsp/iir.cpp:171-180) only runs -- and only advances its state
-    // -- while the squelch is open, which is decided per burst from the whole burst (k_post_fir). It is a recurrence, so
-    // it is computed here SPECULATIVELY beside the PLL (independent dependency chain): outputs go to the (otherwise unused)
-    // envelope row and the end state to S_LP_W1N/W2N; k_post_fir commits or discards them.
-    const double qdc = 1.0 - u.fm_dc_alpha, kdc = u.fm_dc_alpha, na1 = -u.lp_a1, na2 = -u.lp_a2;
-    auto fm_step = [&](double th) -> double {
-        pll(th);
-        const double f = freq;
-        fm_dc = fma(qdc, fm_dc, kdc * f);
-        const double pre = (f - fm_dc) * u.fm_gain;
-        const double w0 = fma(na1, w1, fma(na2, w2, pre));
-        lp = fma(u.lp_b0, w0, fma(u.lp_b1, w1, u.lp_b2 * w2));
-        w2 = w1;
-        w1 = w0;
-        return pre;
-    };
     // stereo SAM, dsp/samdemod.cpp:115-147: opposite NCO sign to the mono path; BOTH parts of tmp = |x| (cos err, -sin err)
     // are DC-blocked and go on to the Hilbert-pair FIR
     auto sam_stereo_step = [&](double th, double mag, double* o1, double* o2) {
@@ -500,54 +648,70 @@ __global__ void __launch_bounds__(kSeq2Threads, 1) k_post_seq2(PostBufs b, int n
         z1 = z0;
         y1 = y0;
     };
-    auto fetch = [&](int k) {
-        double* st = ring + 2 * (k % kSeq2Stages) * kTileD;
-        tile_fetch(st, b.th, b.row, c0, k, m_th, lane);
-        tile_fetch(st + kTileD, b.u, b.row, c0, k, m_u, lane);
-    };
-    for (int k = 0; k < kSeq2Stages - 1; k++) { if (k < nchunks) fetch(k); cp_commit(); }
-    for (int k = 0; k < nchunks; k++) {
-        cp_wait<kSeq2Stages - 2>();
-        __syncwarp();                       // tile k has landed for every lane; the previous tile_store has read the output tiles
-        if (k + kSeq2Stages - 1 < nchunks) fetch(k + kSeq2Stages - 1);
-        cp_commit();
-        const double* xt = ring + 2 * (k % kSeq2Stages) * kTileD;
-        const double* xu = xt + kTileD;
-        if (is_fm) {
+    // Every row of the tile is FM (the usual case: a group's channels are sorted by mode): one straight-line loop for
+    // the whole warp. The warp issues in order, and ptxas sinks a shared-memory load to just in front of its first use
+    // when both sit in one basic block -- a ~30-clock LDS in the dependent chain of every second sample. So the tile's
+    // inputs come into registers FIRST, the stage is handed back (the elected arrive ends the basic block), then the 16
+    // steps run back to back out of registers; a step's frequency goes to the output tile as soon as it exists (the next
+    // step needs it at the same moment, so the store costs an issue slot and no wait).
+    if (m_th == m_lp && m_u == 0u) {
+        for (int k = 0; k < nchunks; k++) {
+            const double* xt = pipe.acquire_in(k);
+            double2 v[kTileT / 2];
+#pragma unroll
+            for (int j = 0; j < kTileT / 2; j++) v[j] = row_ld(xt, lane, j);
+            pipe.release_in(k, lane);
+            double* o_v = pipe.acquire_out(k);      // the helper turns the loop frequency into the two output rows
+            double x = fma(sgn, phase, v[0].x);
 #pragma unroll
             for (int j = 0; j < kTileT / 2; j++) {
-                const double2 v = row_ld(xt, lane, j);
-                const double p0 = fm_step(v.x), l0 = lp;
-                const double p1 = fm_step(v.y), l1 = lp;
-                row_st(o_v, lane, j, p0, p1);
-                row_st(o_lp, lane, j, l0, l1);
+                x = pll_x(x, v[j].y);
+                const double f0 = freq;
+                x = pll_x(x, j + 1 < kTileT / 2 ? v[j + 1].x : 0.0);
+                row_st(o_v, lane, j, f0, freq);
             }
-        } else if (mode == POST_AM) {
-#pragma unroll
-            for (int j = 0; j < kTileT / 2; j++) {
-                const double2 v = row_ld(xu, lane, j);
-                const double p0 = am_step(v.x), p1 = am_step(v.y);
-                row_st(o_v, lane, j, p0, p1);
-            }
-        } else if (sam_st) {
-            double* vrow = vbase + (size_t)c * b.v_row + k * kTileT;
-            double* v2row = b.v2 + kHist + (size_t)c * b.v_row + k * kTileT;
-            for (int j = 0; j < kTileT / 2; j++) {
-                const double2 t2 = row_ld(xt, lane, j), m2 = row_ld(xu, lane, j);
-                sam_stereo_step(t2.x, m2.x, vrow + 2 * j, v2row + 2 * j);
-                sam_stereo_step(t2.y, m2.y, vrow + 2 * j + 1, v2row + 2 * j + 1);
-            }
-        } else if (mode == POST_SAM) {
-#pragma unroll 2
-            for (int j = 0; j < kTileT / 2; j++) {
-                const double2 t2 = row_ld(xt, lane, j), m2 = row_ld(xu, lane, j);
-                const float o0 = sam_step(t2.x, m2.x), o1 = sam_step(t2.y, m2.y);
-                if (aout) { aout[k * kTileT + 2 * j] = o0; aout[k * kTileT + 2 * j + 1] = o1; }
-            }
+            pipe.release_out(k, lane);
         }
-        __syncwarp();
-        tile_store(o_v, vbase, b.v_row, c0, k, m_v, lane);
-        tile_store(o_lp, b.u, b.row, c0, k, m_lp, lane);
+    } else {
+        for (int k = 0; k < nchunks; k++) {
+            const double* xt = pipe.acquire_in(k);
+            const double* xu = xt + kTileD;
+            double* o_v = pipe.acquire_out(k);
+            if (is_fm) {
+#pragma unroll
+                for (int j = 0; j < kTileT / 2; j++) {
+                    const double2 v = row_ld(xt, lane, j);
+                    pll(v.x);
+                    const double f0 = freq;
+                    pll(v.y);
+                    row_st(o_v, lane, j, f0, freq);
+                }
+            } else if (mode == POST_AM) {
+#pragma unroll
+                for (int j = 0; j < kTileT / 2; j++) {
+                    const double2 v = row_ld(xu, lane, j);
+                    const double p0 = am_step(v.x), p1 = am_step(v.y);
+                    row_st(o_v, lane, j, p0, p1);
+                }
+            } else if (sam_st) {
+                double* vrow = vbase + (size_t)c * b.v_row + k * kTileT;
+                double* v2row = b.v2 + kHist + (size_t)c * b.v_row + k * kTileT;
+                for (int j = 0; j < kTileT / 2; j++) {
+                    const double2 t2 = row_ld(xt, lane, j), m2 = row_ld(xu, lane, j);
+                    sam_stereo_step(t2.x, m2.x, vrow + 2 * j, v2row + 2 * j);
+                    sam_stereo_step(t2.y, m2.y, vrow + 2 * j + 1, v2row + 2 * j + 1);
+                }
+            } else if (mode == POST_SAM) {
+#pragma unroll 2
+                for (int j = 0; j < kTileT / 2; j++) {
+                    const double2 t2 = row_ld(xt, lane, j), m2 = row_ld(xu, lane, j);
+                    const float o0 = sam_step(t2.x, m2.x), o1 = sam_step(t2.y, m2.y);
+                    if (aout) { aout[k * kTileT + 2 * j] = o0; aout[k * kTileT + 2 * j + 1] = o1; }
+                }
+            }
+            pipe.release_in(k, lane);
+            pipe.release_out(k, lane);
+        }
     }
     if (!act) return;
     {   // the last n % 16 samples straight from the rows
@@ -556,16 +720,16 @@ __global__ void __launch_bounds__(kSeq2Threads, 1) k_post_seq2(PostBufs b, int n
         double* vrow = vbase + (size_t)c * b.v_row;
         double* v2row = b.v2 + kHist + (size_t)c * b.v_row;
         for (int t = n16; t < n; t++) {
-            if (is_fm) { vrow[t] = fm_step(throw_[t]); urow[t] = lp; }
+            if (is_fm) { pll(throw_[t]); vrow[t] = freq; }
             else if (mode == POST_AM) vrow[t] = am_step(urow[t]);
             else if (sam_st) sam_stereo_step(throw_[t], urow[t], vrow + t, v2row + t);
             else { const float o = sam_step(throw_[t], urow[t]); if (aout) aout[t] = o; }
         }
     }
+    if (tail) asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");      // the helper finishes the FM tail
     ST(S_Z1) = z1;
     if (sam_st) ST(S_Y1) = y1;
     if (mode != POST_AM) { ST(S_PHASE) = wrap_pi(phase); ST(S_FREQ) = freq; }    // fmod(m_NcoPhase, K_2PI) at the end of the burst
-    if (is_fm) { ST(S_FM_DC) = fm_dc; ST(S_LP_W1N) = w1; ST(S_LP_W2N) = w2; }
 }
 
 // ---- Kaiser FIRs, squelch, biquad; CTA per channel. dynamic smem: (kHist + max_n + kFirMax) doubles
@@ -923,9 +1087,9 @@ int PostBank::run(int n, float* d_audio, int audio_stride, int audio_off, const 
     const size_t smem_fir = (size_t)((uni_.stereo ? 2 : 1) * (kHist + max_n_) + kFirMax + 16) * sizeof(double);
     const int seq_blocks = (nch_ + 31) / 32;
     k_post_pre<<<nch_, 256, 2 * (size_t)(uni_.agc_window - 1 + n) * sizeof(double), st_>>>(b, n, uni_.agc_window);
-    k_post_seq1<<<(2 * seq_blocks * 32 + kSeqThreads - 1) / kSeqThreads, kSeqThreads, kSeq1Smem, st_>>>(b, n, uni_);
+    k_post_seq1<<<(2 * seq_blocks + kSeqPairs - 1) / kSeqPairs, kSeqThreads, kSeq1Smem, st_>>>(b, n, uni_);
     k_post_mid<<<nch_, 256, 0, st_>>>(b, n, uni_.agc_delay, uni_.stereo, d_audio, audio_stride, audio_off, d_chan_map);
-    k_post_seq2<<<(seq_blocks * 32 + kSeq2Threads - 1) / kSeq2Threads, kSeq2Threads, kSeq2Smem, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
+    k_post_seq2<<<(seq_blocks + kSeqPairs - 1) / kSeqPairs, kSeqThreads, kSeq2Smem, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     k_post_fir<<<nch_, 256, smem_fir, st_>>>(b, n, uni_, d_audio, audio_stride, audio_off, d_chan_map);
     lc_->n += 5;
     CSDR_CK(cudaGetLastError());

@@ -7,10 +7,13 @@ run() { # label, env..., extra args
 import json; d=json.loads(open('gpurun_out/tmp.json').read()); print('$label', round(d['value']), d['ms_per_block'], round(d['e2e']['value']))"
 }
 EXTRA=""
-run base X=1
-run maxctas1 NCCL_MAX_CTAS=1
-run maxctas2 NCCL_MAX_CTAS=2
-run maxctas4 NCCL_MAX_CTAS=4
+run chunk4M X=1
+run chunk8M CUTESDR_BCAST_CHUNK_KB=8192
+run chunk2M CUTESDR_BCAST_CHUNK_KB=2048
 EXTRA="--ingest cs16"
-run cs16 X=1
-run cs16_maxctas2 NCCL_MAX_CTAS=2
+run cs16_chunk4M X=1
+run cs16_chunk2M CUTESDR_BCAST_CHUNK_KB=2048
+EXTRA="--scaling strong"
+run strong_cf32 X=1
+EXTRA="--scaling strong --ingest cs16"
+run strong_cs16 X=1

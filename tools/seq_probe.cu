@@ -64,6 +64,7 @@ __global__ void k_steps(double* out, long long* cyc, double alpha, double beta, 
     const double kTwoPi = 6.283185307179586, kInv2Pi = 1.0 / kTwoPi, kM = 6755399441055744.0;
     double phase = 0.1 * threadIdx.x, freq = 0, fm_dc = 0, w1 = 0, w2 = 0, lp = 0, acc = 0;
     double att = -5, dec = -5; int hang_timer = 0;
+    double fprev = 0;
     const double hi = in_reg(hi_), lo = in_reg(lo_), qdc = 1.0 - kdc, na1 = -a1, na2 = -a2;
     const bool use_hang = (threadIdx.x & 7) == 0;
     long long t0 = clock64();
@@ -89,6 +90,27 @@ __global__ void k_steps(double* out, long long* cyc, double alpha, double beta, 
                     w2 = w1; w1 = w0;
                     acc += pre;
                 }
+            } else if (WHICH == 3) {
+                // post-processing of the previous sample's frequency first (independent of this sample's PLL chain)
+                {
+                    const double f = fprev;
+                    fm_dc = fma(qdc, fm_dc, kdc * f);
+                    const double pre = (f - fm_dc) * gain;
+                    const double w0 = fma(na1, w1, fma(na2, w2, pre));
+                    lp = fma(b0, w0, fma(b1, w1, b2 * w2));
+                    w2 = w1; w1 = w0;
+                    acc += pre;
+                }
+                const double x = v + phase;
+                const double r = fma(x, kInv2Pi, kM) - kM;
+                const double err = fma(r, kTwoPi, -x);
+                double f = fma(beta, err, freq);
+                const double pa = fma(alpha, err, phase);
+                f = f > hi ? hi : f;
+                f = f < lo ? lo : f;
+                freq = f;
+                phase = pa + f;
+                fprev = f;
             } else if (WHICH == 2) {
                 const double peak = v;
                 const double ar = fma(1 - alpha, att, alpha * peak), af = fma(1 - beta, att, beta * peak);
@@ -104,7 +126,7 @@ __global__ void k_steps(double* out, long long* cyc, double alpha, double beta, 
     }
     long long t1 = clock64();
     if (threadIdx.x == 0) cyc[WHICH] = t1 - t0;
-    out[threadIdx.x] = phase + freq + lp + acc + att + dec + hang_timer;
+    out[threadIdx.x] = phase + freq + lp + acc + att + dec + hang_timer + fprev;
 }
 
 // FP64 pipe throughput of one SM: W warps, 8 independent DFMA chains each
@@ -136,6 +158,12 @@ static void run_steps()
             for (int rep = 0; rep < 2; rep++) k_tput<<<1, 32 * w>>>(d_out, d_cyc, 1e-9, 0.999999);
             cudaMemcpy(&h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost);
             printf("DFMA throughput, %2d warps on one SM:      %6.3f warp instructions per clock\n", w, (double)w * 8 * N / (double)h);
+        }
+        {
+            long long h[8];
+            for (int rep = 0; rep < 2; rep++) k_steps<3><<<1, 32>>>(d_out, d_cyc, 1.09, 0.6, 0.77, -0.77, 2e-3, 32000.0, -1.5, 0.6, 0.03, 0.06, 0.03);
+            cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost);
+            printf("FM step, post-processing one sample behind: %7.1f cycles per sample\n", (double)h[3] / N);
         }
         for (int w = 1; w <= 8; w *= 2) {
             long long h[8];
