@@ -254,7 +254,7 @@ def test_display_fft_anchor(lib):
 # CDemodulator (one receiver) per mode, with the PROFILE taps
 # ------------------------------------------------------------------------------------------------
 CHAIN_CASES = [(M.DEMOD_AM, -5000, 5000, 0), (M.DEMOD_SAM, -5000, 5000, 0), (M.DEMOD_FM, -5000, 5000, 0),
-               (M.DEMOD_USB, 100, 2800, 1), (M.DEMOD_LSB, -2800, -100, 0), (M.DEMOD_CWU, -250, 250, 0)]
+               (M.DEMOD_USB, 100, 2800, 1), (M.DEMOD_LSB, -2800, -100, 0), (M.DEMOD_CWU, -250, 250, 0), (M.DEMOD_CWL, -250, 250, 1)]
 # samples to skip before comparing: PLL acquisition / FM DC tracker (see test_oracle_vs_ref.py)
 SKIP = {M.DEMOD_SAM: 5 * 1024, M.DEMOD_FM: 12 * 1024}
 
@@ -264,7 +264,7 @@ def test_demodulator_chain_2msps(lib, orc, mode, lo, hi, hang):
     fs, fc = 2e6, 250000.0
     n = 700000
     iq = syn_iq(fs, n, [mode], [fc], seed=20261, total_amp=8000.0)
-    info = M.demod_info(mode, HiCut=hi, LowCut=lo, AgcHangOn=hang, Offset=700 if mode == M.DEMOD_CWU else 0)
+    info = M.demod_info(mode, HiCut=hi, LowCut=lo, AgcHangOn=hang, Offset=700 if mode in (M.DEMOD_CWU, M.DEMOD_CWL) else 0)
     a = orc.Demodulator()
     a.SetInputSampleRate(fs)
     a.SetDemod(mode, info)
