@@ -13,6 +13,7 @@
 // Recurrent state is double precision (averagers with 1e4-sample time constants would sit near
 // -85 dB in float32); burst data is float32. All rows are channel-major [c][row].
 #include "post.cuh"
+#include <type_traits>
 
 namespace csdr {
 
@@ -147,8 +148,15 @@ __global__ void __launch_bounds__(256) k_post_pre(PostBufs b, int n, int window)
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
         const float2 xf = yrow[t];
         const double xr = xf.x, xi = xf.y;
-        if (mode != POST_AGC_ONLY)     // dsp/smeter.cpp:76
-            b.smag[(size_t)c * b.row + t] = 10.0 * log10((xr * xr + xi * xi) / (32767.0 * 32767.0) + 1e-50);
+        if (mode != POST_AGC_ONLY) {   // dsp/smeter.cpp:76: 10 log10(|x|^2 / 32767^2 + 1e-50)
+            // The meter is displayed in 0.1 dB steps and checked to 0.02 dB: log2 of the double's mantissa in float32
+            // (error < 1e-6 dB) plus its exponent, instead of a double-precision log10 per sample.
+            const double p = (xr * xr + xi * xi) / (32767.0 * 32767.0) + 1e-50;
+            const int hiw = __double2hiint(p);
+            const int ex = ((hiw >> 20) & 0x7ff) - 1023;
+            const float mant = (float)__hiloint2double((hiw & 0x000fffff) | 0x3ff00000, __double2loint(p));      // [1, 2)
+            b.smag[(size_t)c * b.row + t] = 3.0102999566398120 * ((double)ex + (double)log2f(mant));
+        }
         double mag = fabs(xr);
         const double mim = fabs(xi);
         if (mim > mag) mag = mim;
@@ -463,7 +471,7 @@ __global__ void __launch_bounds__(256) k_post_mid(PostBufs b, int n, int delay, 
         double zr, zi;
         if (agc_on) {
             const double m = b.peak[(size_t)c * b.row + t];
-            const double gain = (m <= knee) ? fixed_gain : 0.7 * pow(10.0, m * (gain_slope - 1.0));   // dsp/agc.cpp:278-286
+            const double gain = (m <= knee) ? fixed_gain : 0.7 * exp10(m * (gain_slope - 1.0));   // dsp/agc.cpp:278-286 (pow(10., x): exp10 is the same function to an ulp at a third of the instructions)
             const float2 dl = yrow[kYHist + t - delay];            // m_SigDelayBuf: `delay` samples ago
             zr = (double)dl.x * gain;
             zi = (double)dl.y * gain;
@@ -768,35 +776,47 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
     // register window, so every tap costs one conflict-free shared load of x (consecutive positions across the
     // lanes) and one broadcast load of the coefficient per four multiply-adds -- a quarter of the shared-memory
     // traffic of one load per product. Each output still sums its products in ascending tap order.
-    const int Q = ((kHist + n + 3) >> 2) + 1;           // plane stride (doubles)
+    // AM: the filter output IS the audio -> double. FM: the filter (squelch high-pass) only feeds a rectified average that
+    // is compared with a threshold in steps of 100 -> float32 operands (half the shared-memory bytes, twice the FMA rate).
+    const int Q = ((kHist + n + 3) >> 2) + 1;           // plane stride (elements)
+    const bool f32 = mode == POST_FM;
     double* v = sm_d;                                   // 4 * Q doubles  (<= kHist + row + 8)
     double* h = sm_d + kHist + b.row + 8;
+    float* vf = reinterpret_cast<float*>(sm_d);
+    float* hf = reinterpret_cast<float*>(sm_d + kHist + b.row + 8);
     const int ntaps = (int)PAR(P_NTAPS);
     double* vrow = b.v + (size_t)c * b.v_row;
-    for (int i = threadIdx.x; i < kHist + n; i += blockDim.x) v[(i & 3) * Q + (i >> 2)] = vrow[i];
-    for (int i = threadIdx.x; i < kFirMax; i += blockDim.x) h[i] = b.taps[(size_t)c * kFirMax + i];
+    if (f32) {
+        for (int i = threadIdx.x; i < kHist + n; i += blockDim.x) vf[(i & 3) * Q + (i >> 2)] = (float)vrow[i];
+        for (int i = threadIdx.x; i < kFirMax; i += blockDim.x) hf[i] = (float)b.taps[(size_t)c * kFirMax + i];
+    } else {
+        for (int i = threadIdx.x; i < kHist + n; i += blockDim.x) v[(i & 3) * Q + (i >> 2)] = vrow[i];
+        for (int i = threadIdx.x; i < kFirMax; i += blockDim.x) h[i] = b.taps[(size_t)c * kFirMax + i];
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < kHist; i += blockDim.x) {       // FIR history for the next burst
         const int p = n + i;
-        vrow[i] = v[(p & 3) * Q + (p >> 2)];
+        vrow[i] = f32 ? (double)vf[(p & 3) * Q + (p >> 2)] : v[(p & 3) * Q + (p >> 2)];
     }
     // acc[j] = sum_k h[k] x[kHist + 4g + j - k]   (CFir::ProcessFilter, dsp/fir.cpp:72-91)
-    auto fir4 = [&](int g, double* acc) {
+    auto fir4_t = [&](int g, auto* acc, const auto* vv, const auto* hh) {
+        typedef typename std::remove_const<typename std::remove_pointer<decltype(vv)>::type>::type T;
         const int p0 = kHist + 4 * g;
-        double w0 = v[((p0)&3) * Q + ((p0) >> 2)], w1 = v[((p0 + 1) & 3) * Q + ((p0 + 1) >> 2)],
-               w2 = v[((p0 + 2) & 3) * Q + ((p0 + 2) >> 2)], w3 = v[((p0 + 3) & 3) * Q + ((p0 + 3) >> 2)];
-        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+        T w0 = vv[((p0)&3) * Q + ((p0) >> 2)], w1 = vv[((p0 + 1) & 3) * Q + ((p0 + 1) >> 2)],
+          w2 = vv[((p0 + 2) & 3) * Q + ((p0 + 2) >> 2)], w3 = vv[((p0 + 3) & 3) * Q + ((p0 + 3) >> 2)];
+        acc[0] = acc[1] = acc[2] = acc[3] = (T)0;
         for (int k = 0; k < ntaps; k++) {
-            const double hk = h[k];
+            const T hk = hh[k];
             acc[0] += hk * w0;
             acc[1] += hk * w1;
             acc[2] += hk * w2;
             acc[3] += hk * w3;
-            const int p = p0 - (k + 1);                 // >= 0: k + 1 <= kFirMax - 1 + 1 <= kHist + 1 and p0 >= kHist ... guarded below
+            const int p = p0 - (k + 1);
             w3 = w2; w2 = w1; w1 = w0;
-            w0 = p >= 0 ? v[(p & 3) * Q + (p >> 2)] : 0.0;
+            w0 = p >= 0 ? vv[(p & 3) * Q + (p >> 2)] : (T)0;
         }
     };
+    auto fir4 = [&](int g, double* acc) { fir4_t(g, acc, (const double*)v, (const double*)h); };
     if (mode == POST_AM) {
         // post filter of dsp/amdemod.cpp:80
         for (int g = threadIdx.x; 4 * g < n; g += blockDim.x) {
@@ -819,12 +839,12 @@ __global__ void __launch_bounds__(256) k_post_fir(PostBufs b, int n, PostUniform
     //   (1-a)^n s0 + a * sum_t (1-a)^(n-1-t) |hp[t]|
     double part = 0.0;
     for (int g = threadIdx.x; 4 * g < n; g += blockDim.x) {
-        double acc[4];
-        fir4(g, acc);
+        float acc[4];
+        fir4_t(g, acc, (const float*)vf, (const float*)hf);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int t = 4 * g + j;
-            if (t < n) part += fabs(acc[j]) * b.qpow[n - 1 - t];
+            if (t < n) part += (double)fabsf(acc[j]) * b.qpow[n - 1 - t];
         }
     }
 #pragma unroll
