@@ -387,182 +387,203 @@ def run_ours(args):
 
     name = args.workload
     w, total, first, nch, modes, carriers, infos = channel_plan(name, rank, world, args.scaling)
-    iq, snapped, L = make_stream(w, modes, carriers, args.ingest)
-    fmt = 0 if args.ingest == "cf32" else 1
-    bank = cs.ReceiverBank(nch, w["in_rate"], device=local)
-    if w["audio_rate"] > 0:
-        bank.SetAudioRate(w["audio_rate"])
-    if w.get("blanker"):
-        bank.SetupNoiseProc(True, 50.0, 50.0)
-    for i in range(nch):
-        c = first + i
-        bank.SetDemod(i, modes[c], infos[c])
-        bank.SetDemodFreq(i, -snapped[c])
-    assert bank.block_length() == L
-    fft = None
-    if w.get("spectrum") and rank == 0:
-        fft = cs.CFft(device=local)
-        fft.SetFFTParams(65536, False, 0.0, w["in_rate"])
-        fft.SetFFTAve(4)
     mg = open_multi_gpu(rank, world, local)          # cutesdr_mgpu_*: the NCCL communicator lives inside the library
-    stream = torch.cuda.ExternalStream(bank.stream(), device=dev)
-    nblk = BLOCKS_PER_STEP
 
-    # the 0.2 s stream: pinned on the host, resident on the device
-    if fmt == 0:
-        host = torch.from_numpy(iq.view(np.float32).reshape(nblk, 2 * L)).pin_memory()
-    else:
-        i16 = np.empty((nblk, 2 * L), dtype=np.int16)
-        v = iq.view(np.float32).reshape(nblk, 2 * L)
-        np.clip(np.rint(v), -32767, 32767, out=v)
-        i16[:] = v
-        host = torch.from_numpy(i16).pin_memory()
-    del iq
-    d_blocks = host.to(dev)
-    sample_bytes = 8 if fmt == 0 else 4
-    audio_stride = 2304
-    d_audio = torch.zeros((nch, audio_stride), dtype=torch.float32, device=dev)
-    h_audio2 = [torch.zeros((nch, audio_stride), dtype=torch.float32).pin_memory() for _ in range(2)]
-    n_out = np.zeros(nch, dtype=np.int32)
-    spec_args = (600, 1024, 0.0, -140.0, int(-w["in_rate"] / 2), int(w["in_rate"] / 2))
-    bank_stream = bank.stream()
+    def measure(ingest):
+        """value (device-resident blocks), e2e (host blocks through the C ABI) and kernel 1's roofline for one wire format"""
+        iq, snapped, L = make_stream(w, modes, carriers, ingest)
+        fmt = 0 if ingest == "cf32" else 1
+        bank = cs.ReceiverBank(nch, w["in_rate"], device=local)
+        if w["audio_rate"] > 0:
+            bank.SetAudioRate(w["audio_rate"])
+        if w.get("blanker"):
+            bank.SetupNoiseProc(True, 50.0, 50.0)
+        for i in range(nch):
+            c = first + i
+            bank.SetDemod(i, modes[c], infos[c])
+            bank.SetDemodFreq(i, -snapped[c])
+        assert bank.block_length() == L
+        fft = None
+        if w.get("spectrum") and rank == 0:
+            fft = cs.CFft(device=local)
+            fft.SetFFTParams(65536, False, 0.0, w["in_rate"])
+            fft.SetFFTAve(4)
+        stream = torch.cuda.ExternalStream(bank.stream(), device=dev)
+        nblk = BLOCKS_PER_STEP
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        # the 0.2 s stream: pinned on the host, resident on the device
+        if fmt == 0:
+            host = torch.from_numpy(iq.view(np.float32).reshape(nblk, 2 * L)).pin_memory()
+        else:
+            i16 = np.empty((nblk, 2 * L), dtype=np.int16)
+            v = iq.view(np.float32).reshape(nblk, 2 * L)
+            np.clip(np.rint(v), -32767, 32767, out=v)
+            i16[:] = v
+            host = torch.from_numpy(i16).pin_memory()
+        del iq
+        d_blocks = host.to(dev)
+        sample_bytes = 8 if fmt == 0 else 4
+        audio_stride = 2304
+        d_audio = torch.zeros((nch, audio_stride), dtype=torch.float32, device=dev)
+        h_audio2 = [torch.zeros((nch, audio_stride), dtype=torch.float32).pin_memory() for _ in range(2)]
+        n_out = np.zeros(nch, dtype=np.int32)
+        spec_args = (600, 1024, 0.0, -140.0, int(-w["in_rate"] / 2), int(w["in_rate"] / 2))
+        bank_stream = bank.stream()
 
-    def spectrum(k):
-        # the concurrent 65536-point spectrum at 10 frames/s: one frame every 10 blocks, taken from the block the
-        # channels saw (after the blanker), plus both plot mappings of CPlotter::draw
-        if fft is not None and k % (nblk // 2) == 0:
-            ptr, n = bank.last_block()
-            fft.put_device_async(ptr + 8 * 100000, 65536, bank_stream)
-            fft.GetPlot(*spec_args)
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
 
-    def step_device():
-        got = 0
-        for k in range(nblk):
-            got += bank.process_device(d_blocks[k].data_ptr(), L, d_audio.data_ptr(), audio_stride, fmt=fmt)
-            spectrum(k)
-        return got
+        def spectrum(k):
+            # the concurrent 65536-point spectrum at 10 frames/s: one frame every 10 blocks, taken from the block the
+            # channels saw (after the blanker), plus both plot mappings of CPlotter::draw
+            if fft is not None and k % (nblk // 2) == 0:
+                ptr, n = bank.last_block()
+                fft.put_device_async(ptr + 8 * 100000, 65536, bank_stream)
+                fft.GetPlot(*spec_args)
 
-    # ---- device-timed value
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    bank.kernel_timing(True)
-    bank.kernel_time(0)
-    launches0 = bank.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(args.steps):
+        def step_device():
+            got = 0
+            for k in range(nblk):
+                got += bank.process_device(d_blocks[k].data_ptr(), L, d_audio.data_ptr(), audio_stride, fmt=fmt)
+                spectrum(k)
+            return got
+
+        # ---- device-timed value
+        for _ in range(args.warmup):
             step_device()
-        bank.join()             # main stream waits for the burst side streams: ev1 covers all work
-        ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    launches = bank.launch_count() - launches0
-    k1_ms, k1_n = bank.kernel_time(0)
-    bank.kernel_timing(False)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    samples_per_step = nblk * L
-    value = (samples_per_step * total * args.steps) / (ms_max * 1e-3) / 1e6
+        barrier()
+        bank.kernel_timing(True)
+        bank.kernel_time(0)
+        launches0 = bank.launch_count()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(args.steps):
+                step_device()
+            bank.join()             # main stream waits for the burst side streams: ev1 covers all work
+            ev1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = ev0.elapsed_time(ev1)
+        launches = bank.launch_count() - launches0
+        k1_ms, k1_n = bank.kernel_time(0)
+        bank.kernel_timing(False)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        samples_per_step = nblk * L
+        value = (samples_per_step * total * args.steps) / (ms_max * 1e-3) / 1e6
 
-    # ---- end to end through the C ABI: host block -> (rank 0 H2D -> NCCL broadcast inside the library) -> bank -> D2H audio
-    e2e_steps = max(1, min(args.steps, 10))
-    d2h = [0]
+        # ---- end to end through the C ABI: host block -> (rank 0 H2D -> NCCL broadcast inside the library) -> bank -> D2H audio
+        e2e_steps = max(1, min(args.steps, 10))
+        d2h = [0]
 
-    def step_e2e():
-        for k in range(nblk):
-            hp = host[k].data_ptr()
-            if world == 1:
-                m = bank.process_async_raw_ptr(L, hp, fmt, h_audio2[k & 1].data_ptr(), audio_stride, n_out)
-            else:
-                m = bank.process_async_bcast_ptr(mg, L, hp if rank == 0 else None, fmt, h_audio2[k & 1].data_ptr(), audio_stride, n_out)
-            d2h[0] += int(m) * nch * 4
-            spectrum(k)
-
-    step_e2e()
-    bank.synchronize()
-    barrier()
-    d2h[0] = 0
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    bank.synchronize()
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = (samples_per_step * total * e2e_steps) / float(te.item()) / 1e6
-    mg_info = mg.info()
-
-    if rank == 0:
-        peaks = measured_peaks()
-        hbm_peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
-        hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        live = {}
-        for key, which in (("fp32_fma_tflops", 0), ("tcgen05_tf32_tflops", 1), ("tcgen05_f16_tflops", 2), ("hbm_copy_gbs", 3)):
-            try:
-                live[key] = cs.microbench(which, local)
-            except Exception as e:  # noqa: BLE001
-                live[key] = None
-                live[key + "_error"] = repr(e)
-        roof = None
-        if k1_n > 0 and k1_ms > 0:
-            per_launch_s = (k1_ms / k1_n) * 1e-3
-            groups = max(1, round(k1_n / max(1, args.steps * nblk)))
-            units = float(L) * nch / groups                     # sample*channels one launch processes
-            ach = 8.0 * units / per_launch_s / 1e9
-            traffic = None
-            try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[name]["dram_bytes_per_launch"]
-            except Exception:
-                pass
-            hbm_model = {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
-                         "note": "SURVEY 8(d) per-channel streaming MODEL (8 B per sample*channel); not a DRAM figure and not the "
-                                 "bound -- all channels share the staged samples; see traffic for the measured DRAM bytes"}
-            on_tc, flops_block = bank.kernel_model(0)
-            at_max = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
-            if on_tc and flops_block > 0:
-                f16 = bank.kernel_model(1)[0]          # which = 1: fp16 hi/lo operand form in use?
-                if peaks:
-                    dense = float(peaks["bf16_tflops"] if at_max else peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-                    psrc = "MEASURED_PEAKS.json dense bf16 %s figure%s" % ("burst" if at_max else "sustained", "" if f16 else " / 2 (kind::tf32)")
+        def step_e2e():
+            for k in range(nblk):
+                hp = host[k].data_ptr()
+                if world == 1:
+                    m = bank.process_async_raw_ptr(L, hp, fmt, h_audio2[k & 1].data_ptr(), audio_stride, n_out)
                 else:
-                    dense, psrc = 2250.0, "fallback: nominal 2.25 PFLOP/s bf16%s (B200_PROFILING.md)" % ("" if f16 else " / 2")
-                tpeak = dense if f16 else dense / 2.0
-                flops_launch = flops_block / groups
-                ach_t = flops_launch / per_launch_s / 1e12
-                roof = {"bound": "tensor", "achieved": ach_t, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_t / tpeak, "traffic": traffic,
-                        "kernel": "k_mix_tc (%s operands)" % ("fp16 hi/lo" if f16 else "tf32 hi/lo"), "launch_ms": k1_ms / k1_n,
-                        "launches": k1_n, "peak_source": psrc + ("; SM clock at max through the timed region" if at_max else ""),
-                        "flops_per_launch": flops_launch, "units_per_launch": units, "flops_per_unit": flops_launch / units,
-                        "executed": {"tflops": 3.0 * ach_t, "frac": 3.0 * ach_t / tpeak,
-                                     "note": "every fp32 product is three hi/lo partial-product MMAs: the tensor pipe executes 3x the algorithmic flops"},
-                        "peaks_measured_live": live, "hbm_model": hbm_model}
-            else:
-                ops = fp32_ops_per_sample(bank_stage_list(cs, w, modes[first], infos[first]))
-                fpeak = live.get("fp32_fma_tflops") or 2.0 * 148 * 128 * 1.965e9 / 1e12
-                ach_f = 2.0 * ops * units / per_launch_s / 1e12       # FMA = 2 flop
-                roof = {"bound": "fp32", "achieved": ach_f, "peak": fpeak, "unit": "TFLOP/s", "frac": ach_f / fpeak, "traffic": traffic,
-                        "kernel": "k_mix_cic", "launch_ms": k1_ms / k1_n, "launches": k1_n,
-                        "peak_source": "FP32 FMA issue peak measured live (cutesdr_microbench 0), FMA = 2 flop",
-                        "ops_per_unit": ops, "units_per_launch": units,
-                        "note": "algorithmic FP32 ops per sample*channel of the whole decimation ladder (SURVEY 8d) attributed to kernel 1 "
-                                "(it executes the NCO, the mixer and every CIC3 + the first half-band: > 90 % of them)",
-                        "peaks_measured_live": live, "hbm_model": hbm_model}
+                    m = bank.process_async_bcast_ptr(mg, L, hp if rank == 0 else None, fmt, h_audio2[k & 1].data_ptr(), audio_stride, n_out)
+                d2h[0] += int(m) * nch * 4
+                spectrum(k)
+
+        step_e2e()
+        bank.synchronize()
+        barrier()
+        d2h[0] = 0
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        bank.synchronize()
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = (samples_per_step * total * e2e_steps) / float(te.item()) / 1e6
+        mg_info = mg.info()
+
+        if rank == 0:
+            peaks = measured_peaks()
+            hbm_peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
+            hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+            live = {}
+            for key, which in (("fp32_fma_tflops", 0), ("tcgen05_tf32_tflops", 1), ("tcgen05_f16_tflops", 2), ("hbm_copy_gbs", 3)):
+                try:
+                    live[key] = cs.microbench(which, local)
+                except Exception as e:  # noqa: BLE001
+                    live[key] = None
+                    live[key + "_error"] = repr(e)
+            roof = None
+            if k1_n > 0 and k1_ms > 0:
+                per_launch_s = (k1_ms / k1_n) * 1e-3
+                groups = max(1, round(k1_n / max(1, args.steps * nblk)))
+                units = float(L) * nch / groups                     # sample*channels one launch processes
+                ach = 8.0 * units / per_launch_s / 1e9
+                traffic = None
+                try:
+                    traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))[name]["dram_bytes_per_launch"]
+                except Exception:
+                    pass
+                hbm_model = {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
+                             "note": "SURVEY 8(d) per-channel streaming MODEL (8 B per sample*channel); not a DRAM figure and not the "
+                                     "bound -- all channels share the staged samples; see traffic for the measured DRAM bytes"}
+                on_tc, flops_block = bank.kernel_model(0)
+                at_max = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
+                if on_tc and flops_block > 0:
+                    f16 = bank.kernel_model(1)[0]          # which = 1: fp16 hi/lo operand form in use?
+                    if peaks:
+                        dense = float(peaks["bf16_tflops"] if at_max else peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+                        psrc = "MEASURED_PEAKS.json dense bf16 %s figure%s" % ("burst" if at_max else "sustained", "" if f16 else " / 2 (kind::tf32)")
+                    else:
+                        dense, psrc = 2250.0, "fallback: nominal 2.25 PFLOP/s bf16%s (B200_PROFILING.md)" % ("" if f16 else " / 2")
+                    tpeak = dense if f16 else dense / 2.0
+                    flops_launch = flops_block / groups
+                    ach_t = flops_launch / per_launch_s / 1e12
+                    roof = {"bound": "tensor", "achieved": ach_t, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_t / tpeak, "traffic": traffic,
+                            "kernel": "k_mix_tc (%s operands)" % ("fp16 hi/lo" if f16 else "tf32 hi/lo"), "launch_ms": k1_ms / k1_n,
+                            "launches": k1_n, "peak_source": psrc + ("; SM clock at max through the timed region" if at_max else ""),
+                            "flops_per_launch": flops_launch, "units_per_launch": units, "flops_per_unit": flops_launch / units,
+                            "executed": {"tflops": (4.0 if f16 else 3.0) * ach_t, "frac": (4.0 if f16 else 3.0) * ach_t / tpeak,
+                                         "note": ("int16 samples split exactly into fp16 hi + lo, coefficients into fp16 hi + lo: all four "
+                                                  "partial-product MMAs per product, the tensor pipe executes 4x the algorithmic flops" if f16 else
+                                                  "every fp32 product is three hi/lo partial-product MMAs: the tensor pipe executes 3x the algorithmic flops")},
+                            "peaks_measured_live": live, "hbm_model": hbm_model}
+                else:
+                    ops = fp32_ops_per_sample(bank_stage_list(cs, w, modes[first], infos[first]))
+                    fpeak = live.get("fp32_fma_tflops") or 2.0 * 148 * 128 * 1.965e9 / 1e12
+                    ach_f = 2.0 * ops * units / per_launch_s / 1e12       # FMA = 2 flop
+                    roof = {"bound": "fp32", "achieved": ach_f, "peak": fpeak, "unit": "TFLOP/s", "frac": ach_f / fpeak, "traffic": traffic,
+                            "kernel": "k_mix_cic", "launch_ms": k1_ms / k1_n, "launches": k1_n,
+                            "peak_source": "FP32 FMA issue peak measured live (cutesdr_microbench 0), FMA = 2 flop",
+                            "ops_per_unit": ops, "units_per_launch": units,
+                            "note": "algorithmic FP32 ops per sample*channel of the whole decimation ladder (SURVEY 8d) attributed to kernel 1 "
+                                    "(it executes the NCO, the mixer and every CIC3 + the first half-band: > 90 % of them)",
+                            "peaks_measured_live": live, "hbm_model": hbm_model}
+        res = {"ingest": ingest, "L": L, "value": value, "ms_max": ms_max, "e2e_value": e2e_value, "e2e_steps": e2e_steps,
+               "h2d": sample_bytes * L * nblk, "d2h": d2h[0] // e2e_steps, "launches": int(launches), "clocks": clocks,
+               "roof": roof if rank == 0 else None, "mg_info": mg_info, "nblk": nblk}
+        del bank
+        torch.cuda.synchronize()
+        return res
+
+    nblk = BLOCKS_PER_STEP
+    main_res = measure(args.ingest)
+    alt_res = None
+    if name == "cfg4" and not args.no_alt_ingest:
+        alt_res = measure("cs16" if args.ingest == "cf32" else "cf32")
+    L, value, ms_max, e2e_value, e2e_steps = main_res["L"], main_res["value"], main_res["ms_max"], main_res["e2e_value"], main_res["e2e_steps"]
+    launches, clocks, roof, mg_info = main_res["launches"], main_res["clocks"], main_res["roof"], main_res["mg_info"]
+    sample_bytes_step, d2h_step = main_res["h2d"], main_res["d2h"]
+    if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
             try:
@@ -575,14 +596,24 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                 "realtime_factor": value / (w["in_rate"] * total / 1e6), "ms_per_block": ms_max / args.steps / nblk,
-                "arithmetic": ("float32 chain; kernel 1 on tensor cores = every fp32 product as 3 hi/lo MMAs, fp32 accumulation"
+                "arithmetic": (("float32 chain; kernel 1 on tensor cores = int16 samples as exact fp16 hi + lo, every product as 4 hi/lo MMAs, fp32 accumulation"
+                                if "fp16" in roof.get("kernel", "") else
+                                "float32 chain; kernel 1 on tensor cores = every fp32 product as 3 hi/lo MMAs, fp32 accumulation")
                                if (roof and roof.get("bound") == "tensor") else "float32 chain (CUDA cores)"),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "Msps*ch", "h2d_bytes_per_step": sample_bytes * L * nblk,
-                        "d2h_bytes_per_step": d2h[0] // e2e_steps, "steps": e2e_steps,
+                "e2e": {"value": e2e_value, "unit": "Msps*ch", "h2d_bytes_per_step": sample_bytes_step,
+                        "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
                         "api": "cutesdr_bank_process_async_raw" if world == 1 else "cutesdr_bank_process_async_bcast (NCCL inside libcutesdr_cuda)",
                         "mgpu": mg_info},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        if alt_res is not None:
+            ar = alt_res["roof"] or {}
+            line["alt_ingest"] = {
+                "ingest": alt_res["ingest"], "value": alt_res["value"], "unit": "Msps*ch", "ms_per_block": alt_res["ms_max"] / args.steps / nblk,
+                "e2e": {"value": alt_res["e2e_value"], "unit": "Msps*ch", "h2d_bytes_per_step": alt_res["h2d"], "d2h_bytes_per_step": alt_res["d2h"]},
+                "roofline": {k: ar.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "launch_ms", "peak_source", "executed")},
+                "note": "the same workload and run with the stream in the radio's other sample format (int16 I/Q words take kernel 1T's fp16 "
+                        "form and halve the host->device bytes; complex64 takes the tf32 form)"}
         emit(line)
     del mg
     if world > 1:
@@ -605,6 +636,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS) + ["cfg2"])
     ap.add_argument("--ingest", default="cf32", choices=["cf32", "cs16"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-alt-ingest", action="store_true", help="skip the second measurement with the other sample format")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
