@@ -63,10 +63,11 @@ cutesdr_bank::~cutesdr_bank()
     groups.clear();
     nb.reset();
     cudaFree(d_x);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kAsyncSlots; k++) {
         cudaFree(d_xs[k]);
         if (ev_h2d[k]) cudaEventDestroy(ev_h2d[k]);
         if (ev_free[k]) cudaEventDestroy(ev_free[k]);
+        if (ev_host[k]) cudaEventDestroy(ev_host[k]);
     }
     if (ev_d2h) cudaEventDestroy(ev_d2h);
     if (st_h2d) { cudaStreamSynchronize(st_h2d); cudaStreamDestroy(st_h2d); }
@@ -238,7 +239,7 @@ int cutesdr_bank::rebuild()
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr;
         CSDR_CK(cudaMalloc(&d_x, (size_t)L * sizeof(float2)));
-        for (int k = 0; k < 2; k++) { cudaFree(d_xs[k]); d_xs[k] = nullptr; }
+        for (int k = 0; k < kAsyncSlots; k++) { cudaFree(d_xs[k]); d_xs[k] = nullptr; }
         for (int k = 0; k < 2; k++) if (!d_halo[k]) CSDR_CK(cudaMalloc(&d_halo[k], (size_t)kHaloMax * sizeof(float2)));
         CSDR_CK(cudaHostAlloc(&h_stage, (size_t)L * sizeof(float2), cudaHostAllocDefault));
         h_fill = 0;
@@ -851,20 +852,21 @@ static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt
     if (!b->st_h2d) {
         CSDR_CK(cudaStreamCreateWithFlags(&b->st_h2d, cudaStreamNonBlocking));
         CSDR_CK(cudaStreamCreateWithFlags(&b->st_d2h, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < kAsyncSlots; k++) {
             CSDR_CK(cudaEventCreateWithFlags(&b->ev_h2d[k], cudaEventDisableTiming));
             CSDR_CK(cudaEventCreateWithFlags(&b->ev_free[k], cudaEventDisableTiming));
+            CSDR_CK(cudaEventCreateWithFlags(&b->ev_host[k], cudaEventDisableTiming));
         }
         CSDR_CK(cudaEventCreateWithFlags(&b->ev_d2h, cudaEventDisableTiming));
     }
-    const int slot = (int)(b->async_blocks & 1);
+    const int slot = (int)(b->async_blocks % kAsyncSlots);
     if (!b->d_xs[slot]) CSDR_CK(cudaMalloc(&b->d_xs[slot], (size_t)b->L * sizeof(float2)));
-    // H2D of this block on the copy stream, as soon as the slot's previous block has been consumed
-    if (b->async_blocks >= 2) {
-        // The header's promise ("iq must stay unchanged until the second following call") is enforced here: the copy
-        // that read the host buffer handed in two calls ago used this slot; the host waits for it before the call
-        // returns, so a producer that runs ahead of the GPU can never overwrite samples the DMA has not read yet.
-        if (!from_device && need_iq) CSDR_CK(cudaEventSynchronize(b->ev_h2d[slot]));
+    // The header's promise ("iq must stay unchanged until the second following call") is enforced here: the host waits
+    // for the copy that read the buffer handed in two calls ago before this call returns, so a producer that runs ahead
+    // of the GPU can never overwrite samples the DMA has not read yet.
+    if (b->async_blocks >= 2 && !from_device && need_iq) CSDR_CK(cudaEventSynchronize(b->ev_host[(b->async_blocks - 2) % kAsyncSlots]));
+    // the transfer into this slot starts as soon as the block that used it kAsyncSlots calls ago has been consumed
+    if (b->async_blocks >= kAsyncSlots) {
         CSDR_CK(cudaStreamWaitEvent(b->st_h2d, b->ev_free[slot], 0));
         if (mg) CSDR_CK(cudaStreamWaitEvent(mg->st_comm, b->ev_free[slot], 0));
     }
@@ -873,6 +875,7 @@ static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt
         // has landed, straight into this slot on every rank; ev_h2d[slot] fires when the whole block is here
         std::lock_guard<std::mutex> lk2(mg->mu);
         CSDR_TRY(mgpu_bcast_block(mg, iq, b->d_xs[slot], (size_t)b->L * sample_bytes(fmt), b->st_h2d, b->ev_h2d[slot]));
+        CSDR_CK(cudaEventRecord(b->ev_host[slot], b->st_h2d));          // after the last host -> device chunk
     } else if (from_device) {
         // the block sits in the caller's device buffer and is read in stream order with respect to src_stream: the
         // copy into the slot waits for everything queued there so far (an NCCL broadcast, ...), and src_stream
@@ -885,6 +888,7 @@ static int bank_process_async(cutesdr_bank* b, int n_in, const void* iq, int fmt
     } else {
         CSDR_CK(cudaMemcpyAsync(b->d_xs[slot], iq, (size_t)b->L * sample_bytes(fmt), cudaMemcpyHostToDevice, b->st_h2d));
         CSDR_CK(cudaEventRecord(b->ev_h2d[slot], b->st_h2d));
+        CSDR_CK(cudaEventRecord(b->ev_host[slot], b->st_h2d));
     }
     CSDR_CK(cudaStreamWaitEvent(b->st, b->ev_h2d[slot], 0));
     const void* dblk = nullptr;

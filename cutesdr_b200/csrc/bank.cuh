@@ -25,6 +25,11 @@ struct ChanCfg {
     std::vector<float> tap[5];
 };
 
+// input slots of the pipelined entry points: the transfer of block k+3 (host -> GPU, and the NCCL broadcast on several
+// GPUs) may run while block k is still being processed -- with two slots a transfer that takes longer than one block's
+// kernels (8 ranks: 2 x ~0.1 ms of broadcast latency per block) stalled the pipeline
+constexpr int kAsyncSlots = 4;
+
 struct Group {
     double max_bw = 0;
     std::vector<int> chans;              // user channel index of each local slot in use (-1 = parked slot)
@@ -87,9 +92,9 @@ struct cutesdr_bank {
     int L = 0;                           // m_InBufLimit
     float2* d_x = nullptr;               // [L] staging of host / blanked blocks
     // pipelined host interface (process_async): two H2D staging slots on a copy stream, D2H on another
-    float2* d_xs[2] = {nullptr, nullptr};
+    float2* d_xs[csdr::kAsyncSlots] = {};
     cudaStream_t st_h2d = 0, st_d2h = 0;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_d2h = nullptr;
+    cudaEvent_t ev_h2d[csdr::kAsyncSlots] = {}, ev_free[csdr::kAsyncSlots] = {}, ev_host[csdr::kAsyncSlots] = {}, ev_d2h = nullptr;
     long long async_blocks = 0;
     bool d2h_pending = false;
     float2* d_halo[2] = {nullptr, nullptr};   // [kHaloMax] tail of the previous block (double buffer)
