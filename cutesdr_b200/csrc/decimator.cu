@@ -1195,6 +1195,7 @@ __global__ void __launch_bounds__(256) k_hb11_chain(const float2* __restrict__ i
 // out of it, exactly like K2a. Same operation order as k_halfband (centre tap, then the outermost pair inwards),
 // so either path gives the same bits.
 // ------------------------------------------------------------------------------------------
+constexpr int kTailMaxPerThread = 12;     // outputs of one stage a thread of k_hb_tail holds in registers
 struct TailCfg {
     int ns;
     int len[4];
@@ -1203,7 +1204,7 @@ struct TailCfg {
 };
 
 template <int CH>
-__global__ void __launch_bounds__(256) k_hb_tail(const float2* __restrict__ in, unsigned in_mask, long long in_base, int stride, int n_out,
+__global__ void __launch_bounds__(256, 4) k_hb_tail(const float2* __restrict__ in, unsigned in_mask, long long in_base, int stride, int n_out,
                                                  TailCfg cfg, OutDesc od)
 {
     constexpr int RPW = 32 / CH;
@@ -1229,26 +1230,41 @@ __global__ void __launch_bounds__(256) k_hb_tail(const float2* __restrict__ in, 
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    // A stage's outputs stay in registers until every thread has read its inputs, then overwrite the front of the SAME
+    // buffer: the CTA needs c[0] rows of shared memory instead of c[0] + c[1] + ..., which lets the tile be 1.5x longer at
+    // the same number of resident CTAs -- the whole grid in ONE wave (1024 CTAs on 740 slots ran as two).
     for (int j = 0; j < cfg.ns; j++) {
         const int N = cfg.len[j], half = (N - 1) >> 1, n_j = cfg.c[j + 1];
         const bool last = j + 1 == cfg.ns;
-        float2* nxt = buf + cfg.c[j] * CH;
-        for (int i = RPW * warp + sub; i < n_j; i += 8 * RPW) {
-            const float2* x = buf + (2 * i) * CH + l;          // oldest tap of output i
-            const float2 xc = x[half * CH];
-            float2 acc = make_float2(0.5f * xc.x, 0.5f * xc.y);
-            int t = cfg.toff[j];
-            for (int k = 0; k < half; k += 2, t++) {
-                const float h = c_hb_taps[t];
-                const float2 u = x[k * CH], v = x[(N - 1 - k) * CH];
-                acc.x = fmaf(h, u.x + v.x, acc.x);
-                acc.y = fmaf(h, u.y + v.y, acc.y);
+        float2 outv[kTailMaxPerThread];
+#pragma unroll
+        for (int q = 0; q < kTailMaxPerThread; q++) {
+            const int i = RPW * warp + sub + q * 8 * RPW;
+            float2 acc = make_float2(0.f, 0.f);
+            if (i < n_j) {
+                const float2* x = buf + (2 * i) * CH + l;          // oldest tap of output i
+                const float2 xc = x[half * CH];
+                acc = make_float2(0.5f * xc.x, 0.5f * xc.y);
+                int t = cfg.toff[j];
+                for (int k = 0; k < half; k += 2, t++) {
+                    const float h = c_hb_taps[t];
+                    const float2 u = x[k * CH], v = x[(N - 1 - k) * CH];
+                    acc.x = fmaf(h, u.x + v.x, acc.x);
+                    acc.y = fmaf(h, u.y + v.y, acc.y);
+                }
+                if (last && o0 + i < n_out) store_out(od, o0 + i, c, acc);
             }
-            if (!last) nxt[i * CH + l] = acc;
-            else if (o0 + i < n_out) store_out(od, o0 + i, c, acc);
+            outv[q] = acc;
         }
-        if (!last) __syncthreads();
-        buf = nxt;
+        if (!last) {
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < kTailMaxPerThread; q++) {
+                const int i = RPW * warp + sub + q * 8 * RPW;
+                if (i < n_j) buf[i * CH + l] = outv[q];
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -1940,22 +1956,38 @@ int Decimator::run_block(const void* d_x, const float2* halo_cur, float2* halo_n
             TailCfg cfg;
             cfg.ns = ns;
             const int n_out = L >> lens_.size();
-            int T = 32;
-            while (T > 8 && (long long)((n_out + T - 1) / T) * (stride_ / CH) < 592) T >>= 1;       // keep >= ~4 CTAs per SM
+            // tile length: every CTA lives about as long as its c[0] input rows; pick the T that minimises waves x rows
+            int dev = 0, sms = 148;
+            CSDR_CK(cudaGetDevice(&dev));
+            CSDR_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            int T = 8;
+            long long best = -1;
+            for (int cand = 64; cand >= 8; cand -= 8) {
+                int c[5];
+                c[ns] = cand;
+                for (int j = ns - 1; j >= 0; j--) c[j] = 2 * c[j + 1] + lens_[k1_stages() + s_first + j] - 2;
+                bool fits = true;
+                for (int j = 0; j < ns; j++) fits &= (c[j + 1] * CH + 255) / 256 <= kTailMaxPerThread;
+                const size_t bytes = (size_t)c[0] * CH * sizeof(float2);
+                if (!fits || bytes > 160 * 1024) continue;
+                const int per_sm = (int)std::min<size_t>(4, (227 * 1024) / (bytes + 1024));       // __launch_bounds__(256, 4)
+                const long long ctas = (long long)((n_out + cand - 1) / cand) * (stride_ / CH);
+                const long long waves = (ctas + (long long)sms * per_sm - 1) / ((long long)sms * per_sm);
+                const long long cost = waves * c[0];
+                if (best < 0 || cost < best) { best = cost; T = cand; }
+            }
             cfg.c[ns] = T;
             for (int j = ns - 1; j >= 0; j--) {
                 cfg.len[j] = lens_[k1_stages() + s_first + j];
                 cfg.toff[j] = tap_offset_for(cfg.len[j]);
                 cfg.c[j] = 2 * cfg.c[j + 1] + cfg.len[j] - 2;
             }
-            size_t rows = 0;
-            for (int j = 0; j < ns; j++) rows += cfg.c[j];
-            const size_t smem = rows * CH * sizeof(float2);
+            const size_t smem = (size_t)cfg.c[0] * CH * sizeof(float2);
             // rows of history the first tile reaches back into the input ring (it persists between blocks)
             long long hist = 0;
             for (int j = ns - 1; j >= 0; j--) hist = 2 * hist + (cfg.len[j] - 1);
             const int n_in0 = L >> (k1_stages() + s_first);
-            if (smem <= 160 * 1024 && hist + n_in0 <= stage_rows_[s_first]) {
+            if (best >= 0 && smem <= 160 * 1024 && hist + n_in0 <= stage_rows_[s_first]) {
                 OutDesc o2;
                 o2.p = d_ring_;
                 o2.mask = 0;

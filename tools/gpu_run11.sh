@@ -1,13 +1,13 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -s > gpurun_out/r02s_gputests.log 2>&1; echo "pytest exit $?"
-tail -3 gpurun_out/r02s_gputests.log
-python bench.py > gpurun_out/r02s_bench.json 2> gpurun_out/r02s_bench.err; echo "bench exit $?"
-cat gpurun_out/r02s_bench.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02s_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r02s_ncu.log 2>&1
+python -m pytest tests -m gpu -x -q -s > gpurun_out/r02af_gputests.log 2>&1; echo "pytest exit $?"
+tail -3 gpurun_out/r02af_gputests.log
+python bench.py > gpurun_out/r02af_bench.json 2> gpurun_out/r02af_bench.err; echo "bench exit $?"
+cat gpurun_out/r02af_bench.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02af_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r02af_ncu.log 2>&1
 python - <<'PY'
 import csv,collections
-rows=list(csv.reader(open('gpurun_out/r02s_launches.csv',errors='ignore')))
+rows=list(csv.reader(open('gpurun_out/r02af_launches.csv',errors='ignore')))
 hdr=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]
 h=rows[hdr]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
 d=collections.defaultdict(lambda:[0,0.0])
