@@ -920,6 +920,8 @@ int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, voi
 int cutesdr_bank_process_device_raw(cutesdr_bank* b, const void* d_iq, int fmt, int n_in, void* d_audio, int audio_stride, int* n_out_max)
 {
     if (!b || !d_iq || fmt < 0 || fmt > 2) { set_error("bank_process_device: bad arguments"); return CUTESDR_E_ARG; }
+    // kernel 1 reads complex64 / int16 blocks with 16-byte vector loads
+    if (fmt != 2 && (reinterpret_cast<uintptr_t>(d_iq) & 15u)) { set_error("bank_process_device: the device block must be 16-byte aligned"); return CUTESDR_E_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     CSDR_CK(cudaSetDevice(b->device));
     if (b->layout_dirty) CSDR_TRY(b->rebuild());

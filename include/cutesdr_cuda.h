@@ -178,7 +178,8 @@ int cutesdr_bank_process_async(cutesdr_bank* b, int n_in, const float* iq, float
 /* Same, with the block already resident in device memory (d_iq: complex64[n_in], n_in must
  * equal block_length) and results left in device memory: d_audio float32
  * [n_channels][audio_stride] (may be NULL to keep them internal). Asynchronous on the bank's
- * stream; *n_out_max is known on return (burst timing is deterministic). */
+ * stream; *n_out_max is known on return (burst timing is deterministic). d_iq must be 16-byte
+ * aligned (kernel 1 reads it with vector loads); CUTESDR_E_ARG otherwise. */
 int cutesdr_bank_process_device(cutesdr_bank* b, const void* d_iq, int n_in, void* d_audio, int audio_stride,
                                 int* n_out_max);
 /* same with the device block still in a wire format (fmt as in cutesdr_bank_process_raw) */
