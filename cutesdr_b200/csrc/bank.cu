@@ -484,6 +484,19 @@ int cutesdr_device_count(int* n)
     return CUTESDR_OK;
 }
 
+int cutesdr_host_alloc(void** p, size_t bytes)
+{
+    if (!p || bytes == 0) { set_error("host_alloc: bad arguments"); return CUTESDR_E_ARG; }
+    *p = nullptr;
+    CSDR_CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return CUTESDR_OK;
+}
+
+void cutesdr_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 int cutesdr_device_memory(int device, long long* free_bytes, long long* total_bytes)
 {
     CSDR_CK(cudaSetDevice(device));

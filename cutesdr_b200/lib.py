@@ -36,6 +36,8 @@ PROTOTYPES = {
     "cutesdr_version": (C.c_char_p, []),
     "cutesdr_device_count": (C.c_int, [_ip]),
     "cutesdr_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
+    "cutesdr_host_alloc": (C.c_int, [_pp, C.c_size_t]),
+    "cutesdr_host_free": (None, [_vp]),
     "cutesdr_device_memory": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "cutesdr_bank_create": (C.c_int, [_pp, C.c_int, C.c_double, C.c_int]),
     "cutesdr_bank_destroy": (None, [_vp]),

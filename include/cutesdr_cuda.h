@@ -25,6 +25,7 @@
 
 #include <stdint.h>
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -62,6 +63,11 @@ int cutesdr_device_count(int* n);
  * them): which = 0 FP32 FMA issue peak [TFLOP/s], 1 tcgen05 kind::tf32 dense peak [TFLOP/s], 2 tcgen05 kind::f16
  * dense peak [TFLOP/s], 3 HBM copy bandwidth [GB/s, read + write]. Each takes a few milliseconds. */
 int cutesdr_microbench(int device, int which, double* value);
+/* Page-locked host memory for the iq / audio buffers of the pipelined entry points (cutesdr_bank_process_async*), for
+ * hosts that do not link the CUDA runtime themselves (no reference counterpart: the reference's buffers are plain
+ * arrays, dsp/demodulator.cpp:77-80). */
+int cutesdr_host_alloc(void** p, size_t bytes);
+void cutesdr_host_free(void* p);
 /* cudaMemGetInfo of `device` (tests use it to show that a long-running, constantly retuned bank does not grow) */
 int cutesdr_device_memory(int device, long long* free_bytes, long long* total_bytes);
 

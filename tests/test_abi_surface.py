@@ -85,3 +85,20 @@ def test_reference_interface_sources_compile_unchanged_against_the_compat_header
     stub = os.path.join(ROOT, "tests", "cpp", "qt_stub")
     for f in ("sdrinterface.cpp", "soundout.cpp"):
         _syntax_only(["-I" + stub, "-I" + os.path.join(stub, "alt"), "-I" + ref, os.path.join(ref, "interface", f)])
+
+
+def test_cpp_multi_gpu_host_links_against_the_c_abi_alone(tmp_path):
+    """tests/cpp/mgpu_host.cpp is a multi-GPU host written against include/cutesdr_cuda.h only (cutesdr_mgpu_unique_id /
+    _init / _channel_slice, cutesdr_bank_process_async_bcast, pinned buffers from cutesdr_host_alloc): it compiles as
+    plain C++11, links against nothing but libcutesdr_cuda.so, and -- without a GPU -- fails loudly with the library's
+    error instead of falling back to anything."""
+    import subprocess
+    import torch
+    exe = str(tmp_path / "mgpu_host")
+    subprocess.check_call(["g++", "-O1", "-std=gnu++11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "mgpu_host.cpp"), "-L" + os.path.join(ROOT, "cutesdr_b200"), "-lcutesdr_cuda",
+                           "-Wl,-rpath," + os.path.join(ROOT, "cutesdr_b200")])
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (the GPU path of this host is bench.py --gpus N)")
+    r = subprocess.run([exe, "0", "1", str(tmp_path / "id")], capture_output=True, text=True)
+    assert r.returncode == 3 and "mgpu_host:" in r.stderr

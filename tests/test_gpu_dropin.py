@@ -49,3 +49,23 @@ def test_same_host_source_against_shims_and_reference(tmp_path, mode, lo, hi):
     assert snr_db(ra, ga) > 90.0
     assert len(r48) == len(g48) and np.max(np.abs(r48.astype(np.int32) - g48.astype(np.int32))) <= 1
     assert rov == gov and np.max(np.abs(rs - gs)) <= 1
+
+
+def test_cpp_multi_gpu_host_runs_through_the_c_abi(tmp_path):
+    """tests/cpp/mgpu_host.cpp (C ABI only: cutesdr_mgpu_*, cutesdr_bank_process_async_bcast, cutesdr_host_alloc) on the
+    GPUs of this box: one process per GPU when there are two, a world of one otherwise."""
+    exe = os.path.join(ROOT, "tests", "cpp", "mgpu_host")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp binaries not built (run __graft_entry__.build())")
+    import torch
+    world = 2 if torch.cuda.device_count() >= 2 else 1
+    idf = str(tmp_path / "nccl_id")
+    procs = [subprocess.Popen([exe, str(r), str(world), idf, "256", "8"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(world)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for r, (p, (out, err)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, (r, out, err)
+        assert "rank %d/%d" % (r, world) in out and "8 blocks" in out
+        # 8 blocks of ~10 ms at 48 kHz: three or four FIR bursts of ~1002 resampled samples each have completed
+        n = int(out.strip().split(",")[-1].split()[0])
+        assert 2500 < n < 4500, out
